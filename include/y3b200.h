@@ -1,0 +1,148 @@
+/* y3b200 -- C ABI of the B200-native YOLOv3 inference hot path.
+ *
+ * The reference (ronen-halevy/yolo-v3-tf2) has no FFI: its hot path is three Python/Keras call sites.  Each entry point
+ * below replaces one of them; the Python package yolo_v3_tf2_b200.core.* binds these symbols with ctypes and mirrors
+ * the reference signatures (see INTEGRATION.md for the reference-side stub).
+ *
+ *   reference interface                                              replaced by
+ *   ---------------------------------------------------------------  -------------------------------------------
+ *   ParseModel.build_model       core/parse_model.py:279-314         y3_net_create / y3_net_load_conv / y3_net_plan_*
+ *   model(x) / model.predict(x)  inference.py:109,127,162            y3_net_forward
+ *   yolo_decode                  core/yolo_decode_layer.py:15-36     y3_decode
+ *   yolo_nms (argmax/max/score)  core/yolo_nms.py:18-24              y3_class_reduce
+ *   tf.image.non_max_suppression_padded via yolo_nms :26-33          y3_nms
+ *   Inference.gather_valid_detections_results inference.py:21-28     y3_gather_detections
+ *   one Conv2D(+BN+LeakyReLU+Add+UpSampling2D) core/parse_model.py:13-75,143-160   y3_conv2d_bf16 (unit-test entry)
+ *
+ * Conventions: every function returns 0 on success or a Y3_ERR_* code; y3_last_error() returns a thread-local message.
+ * All tensor pointers are DEVICE pointers unless the parameter name ends in _host.  The caller owns every input and
+ * output buffer; the library owns the context, packed weights, the activation arena and its tensor maps.  Calls are
+ * asynchronous on the given stream (cudaStream_t passed as void*; NULL = default stream).  A context is bound to one
+ * GPU and is not thread-safe.  There is no CPU fallback anywhere: on a machine without an sm_100 GPU every compute
+ * entry point fails with Y3_ERR_CUDA / Y3_ERR_UNSUPPORTED.
+ */
+#ifndef Y3B200_H
+#define Y3B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Y3_OK 0
+#define Y3_ERR_INVALID 1      /* bad argument / malformed graph (Python raises ValueError) */
+#define Y3_ERR_UNSUPPORTED 2  /* valid but not implemented on this path (e.g. maxpool) */
+#define Y3_ERR_CUDA 3         /* CUDA runtime / driver failure, message has the CUDA error string */
+#define Y3_ERR_STATE 4        /* call order violated (weights missing, net not planned, ...) */
+
+typedef struct y3_ctx y3_ctx;
+typedef struct y3_net y3_net;
+
+/* ---- layer list: the flattened form of the reference's per-sub-model yaml layer lists ---------------------------
+ * Tensor ids: 0 is the network input image; layer i (0-based) produces tensor i+1.
+ * Y3_OP_CONV     src0            conv(k, stride, filters) [+BN] [+leaky]   parse_model.py:13-56
+ * Y3_OP_SHORTCUT src0=x src1=from    x + from                              parse_model.py:143-160
+ * Y3_OP_UPSAMPLE src0            nearest x2                                parse_model.py:59-75
+ * Y3_OP_CONCAT   src0,src1       channel concat [src0, src1]               parse_model.py:102-140
+ * Y3_OP_YOLO     src0            [B,g,g,3*(5+C)] -> [B,g,g,3,5+C] view; marks a network output   parse_model.py:163-213
+ * Y3_OP_MAXPOOL  (yolov3-tiny)   rejected with Y3_ERR_UNSUPPORTED for now  parse_model.py:78-99
+ */
+enum { Y3_OP_CONV = 0, Y3_OP_SHORTCUT = 1, Y3_OP_UPSAMPLE = 2, Y3_OP_CONCAT = 3, Y3_OP_YOLO = 4, Y3_OP_MAXPOOL = 5 };
+
+typedef struct {
+    int32_t op;
+    int32_t src0;
+    int32_t src1;             /* -1 when unused */
+    int32_t ksize;            /* conv: 1 or 3 */
+    int32_t stride;           /* conv: 1 or 2 ; upsample: 2 */
+    int32_t filters;          /* conv: output channels */
+    int32_t pad;              /* conv: yaml 'pad'; stride 1 and pad==1 -> 'same', stride 1 and pad==0 -> 'valid',
+                                 stride 2 -> ZeroPadding2D(((1,0),(1,0))) + 'valid' (parse_model.py:29-35) */
+    int32_t batch_normalize;  /* conv: 1 = BN follows (no bias), 0 = conv bias */
+    int32_t activation;       /* conv: 0 linear, 1 leaky(0.1) */
+} y3_layer_desc;
+
+/* what the planner decided for one layer; lets CPU-only tests check the host logic without a GPU */
+typedef struct {
+    int32_t H, W, C;          /* output shape of the layer's tensor */
+    int32_t kernel;           /* 0 none (fused/view), 1 tcgen05 conv, 2 direct conv, 3 add, 4 upsample, 5 copy */
+    int32_t fused_add;        /* conv: residual tensor id added in the epilogue, else -1 */
+    int32_t fused_upsample;   /* conv: 1 if the epilogue writes the 2x upsampled tensor */
+    int32_t buffer;           /* arena buffer id holding this tensor, -1 for views of fused ops / outputs */
+    int32_t chan_offset;      /* channel offset inside the buffer (concat slices) */
+    int32_t pix_stride;       /* channels between consecutive pixels of the buffer */
+    int32_t block_n, swizzle, stages;   /* tcgen05 tile configuration */
+    int64_t arena_offset;     /* byte offset of the buffer inside the activation arena */
+} y3_layer_plan;
+
+const char* y3_last_error(void);
+int y3_version(void);
+
+/* device < 0 creates a planning-only context (no CUDA calls; usable on a CPU-only machine for y3_net_plan_*). */
+int y3_ctx_create(int device, y3_ctx** out);
+void y3_ctx_destroy(y3_ctx* ctx);
+int y3_ctx_sm_count(y3_ctx* ctx);
+
+/* Build the network plan for images of H x W, up to max_batch images, nclasses classes.  Validates the graph
+ * (Y3_ERR_INVALID mirrors the reference's ValueError / AssertionError cases) and, on a GPU context, allocates the
+ * activation arena and weight storage. */
+int y3_net_create(y3_ctx* ctx, const y3_layer_desc* layers, int n_layers, int H, int W, int max_batch, int nclasses,
+                  y3_net** out);
+void y3_net_destroy(y3_net* net);
+int y3_net_num_convs(y3_net* net);
+int y3_net_num_outputs(y3_net* net);
+int y3_net_get_plan(y3_net* net, y3_layer_plan* plans_host, int n_layers);
+int64_t y3_net_arena_bytes(y3_net* net);
+/* output k: grid height/width and channel count 3*(5+C) */
+int y3_net_output_shape(y3_net* net, int k, int* gh, int* gw, int* ch);
+
+/* Weights of conv number conv_idx (creation order, = Keras conv2d_<idx> and Darknet file order, convert.py:93-137) in
+ * the reference layout: kernel HWIO fp32 (kh,kw,Cin,Cout); either bias[Cout] or the four BN vectors (Keras order
+ * gamma, beta, moving_mean, moving_variance) with epsilon (Keras default 1e-3).  BN is folded, the result rounded to
+ * bf16 and packed for the kernel.  Host pointers. */
+int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel_hwio_host, const float* bias_host,
+                     const float* bn_gamma_host, const float* bn_beta_host, const float* bn_mean_host,
+                     const float* bn_var_host, float bn_eps);
+
+/* x: [B,H,W,3] fp32 NHWC in [0,1].  outs[k]: [B,gh_k,gw_k,3,5+C] fp32 for every output in model order. */
+int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream);
+
+/* grids[s]: [B,gh[s],gw[s],3,5+C] fp32; anchors_host: 3x3x2 fp32 (scale, anchor, (w,h)) image fractions.
+ * bboxes [B,N,4], conf [B,N,1], probs [B,N,C]; scores [B,N] and class_idx [B,N] (int64) optional (both or neither). */
+int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, int n_scales,
+              const float* anchors_host, int B, int nclasses, float* bboxes, float* conf, float* probs, float* scores,
+              int64_t* class_idx, void* stream);
+
+int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, int N, int nclasses, float* scores,
+                    int64_t* class_idx, void* stream);
+
+/* selected [B,max_boxes] int32 zero padded, num_valid [B] int32, status [B] int32 (0 ok, 1 = kept-list overflow) */
+int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, int max_boxes, float iou_thr,
+           float score_thr, int32_t* selected, int32_t* num_valid, int32_t* status, void* stream);
+
+int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_idx, const float* scores,
+                         const int32_t* selected, const int32_t* num_valid, int B, int N, int max_boxes,
+                         float* out_boxes, int64_t* out_classes, float* out_scores, void* stream);
+
+/* One fused conv layer on bf16 NHWC views (unit-test entry; the net executor runs the same kernel).
+ * x: [B,H,W,Cin] bf16 with pixel stride x_stride elements.  w_packed: [Cout_pad][k][k][Cin] bf16 (Cout_pad = Cout
+ * rounded up to the tile width returned by y3_conv_block_n).  bias: [Cout_pad] fp32.  residual optional.
+ * out: bf16 (or fp32) view with pixel stride out_stride; upsample=1 writes the (2Ho,2Wo) nearest-upsampled tensor. */
+int y3_conv_block_n(int cin, int cout);
+int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, const void* w_packed,
+                   const float* bias, int ksize, int stride, int Cout, int leaky, const void* residual,
+                   int64_t res_stride, void* out, int64_t out_stride, int out_fp32, int upsample, void* stream);
+
+/* Debug: fetch one 128-pixel x (swizzle/2)-channel A tile through the conv kernel's TMA path and return the raw
+ * (swizzled) shared-memory image, 128*swizzle bytes. */
+int y3_dbg_tma_tile(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, int ksize, int stride,
+                    int swizzle, int tap_r, int tap_s, int c0, int m0, void* out_bytes, void* stream);
+
+/* last device-side watchdog code (0 = none) */
+int y3_watchdog_code(y3_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

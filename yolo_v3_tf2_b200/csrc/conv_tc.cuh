@@ -1,0 +1,342 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Replaces the Keras call chain ZeroPadding2D -> Conv2D -> BatchNormalization -> LeakyReLU (-> Add) (-> UpSampling2D)
+// of reference core/parse_model.py:13-56 (conv), :143-160 (shortcut), :59-75 (upsample) for every conv whose input
+// channel count is a multiple of 32 (all of Darknet-53 + neck + heads except the very first 3-channel conv).
+//
+//   GEMM view:  D[M, N] = A[M, K] * W[N, K]^T       M = B*Ho*Wo output pixels, N = Cout, K = k*k*Cin ordered (r, s, c)
+//   A tile   :  128 pixels x BLOCK_K channels of ONE filter tap, fetched by TMA straight from the NHWC activation:
+//               - 1x1 convs: plain 2-D tiled tensor map over [pixels, channels]
+//               - 3x3 convs: im2col-mode tensor map (C, W, H, N); the hardware walks 128 consecutive output pixels,
+//                 applies the traversal stride (1 or 2), adds the tap offset and zero-fills the padding halo.  The
+//                 reference's asymmetric stride-2 padding ((1,0),(1,0)) then VALID (parse_model.py:34-35) is expressed
+//                 by the bounding-box corners lower = -1, upper = 0 - (k-1).
+//   W tile   :  BLOCK_N x BLOCK_K slice of the BN-folded bf16 weight matrix [Cout_pad, K] (2-D tiled tensor map)
+//   D        :  fp32 accumulator in TMEM, 128 lanes x BLOCK_N columns, double buffered so the epilogue of tile i
+//               overlaps the MMAs of tile i+1.
+//
+// Warp roles (256 threads, one persistent CTA per SM):
+//   warp 0  TMA producer (one elected lane)         warp 1  MMA issuer (one lane issues tcgen05.mma)
+//   warp 2  TMEM allocator                          warp 3  idle
+//   warps 4-7  epilogue: tcgen05.ld -> +bias -> LeakyReLU(0.1) -> +residual -> bf16 (or fp32 for heads) -> global,
+//              optionally replicated 2x2 (nearest upsample) into a channel slice of a wider buffer (concat).
+#pragma once
+#include "ptx.cuh"
+
+namespace y3 {
+
+struct ConvArgs {
+    int M;                 // B*Ho*Wo
+    int Ho, Wo;            // output spatial size
+    int stride;            // 1 or 2
+    int lower;             // im2col lower corner (= -pad_before) for w and h
+    int a_im2col;          // 0: 2-D tiled A map (1x1), 1: im2col A map
+    int ksize;             // 1 or 3
+    int kblocks_per_tap;   // Cin / BLOCK_K
+    int num_k_blocks;      // ksize*ksize*kblocks_per_tap
+    int tiles_m, tiles_n;
+    int cout;              // valid output channels (<= tiles_n*BLOCK_N)
+    const float* bias;     // [tiles_n*BLOCK_N] fp32 (folded BN shift or conv bias, zero padded)
+    int leaky;             // 1: LeakyReLU(0.1)
+    const __nv_bfloat16* residual;  // optional, same pixel indexing as the output (dense pixel index m)
+    long long res_stride;  // elements between consecutive pixels of the residual view
+    void* out;             // bf16 (or fp32 if out_fp32) view base
+    long long out_stride;  // elements between consecutive pixels of the output view
+    int out_fp32;
+    int upsample;          // 1: write every output pixel to the 2x2 block (2p+dy, 2q+dx) of a (2Ho, 2Wo) view
+};
+
+constexpr int kConvThreads = 256;
+constexpr int kBlockM = 128;
+
+template <int BLOCK_N, int SWZ, int STAGES>
+struct ConvSmem {
+    static constexpr int A_BYTES = kBlockM * SWZ;
+    static constexpr int B_BYTES = BLOCK_N * SWZ;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int XPOSE_BYTES = 4 * 32 * 33 * 4;        // per-epilogue-warp 32x33 fp32 transpose tile
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16; // full/empty + tmem full/empty + tmem ptr
+    static constexpr int TOTAL = 1024 /*align slack*/ + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
+};
+
+template <int BLOCK_N, int SWZ, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+    using S = ConvSmem<BLOCK_N, SWZ, STAGES>;
+    constexpr int BLOCK_K = SWZ / 2;   // bf16 elements per swizzle row
+    constexpr int UMMA_K = 16;
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_base + STAGES * S::A_BYTES;
+    float* xpose = reinterpret_cast<float*>(smem_gen + S::TILE_BYTES);
+    const uint32_t bar_base = smem_base + S::TILE_BYTES + S::XPOSE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_ptr_gen =
+        reinterpret_cast<volatile uint32_t*>(smem_gen + S::TILE_BYTES + S::XPOSE_BYTES + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+                const int m0 = tm * kBlockM;
+                int cw = 0, ch = 0, cn = 0;
+                if (p.a_im2col) {
+                    const int hw = p.Ho * p.Wo;
+                    cn = m0 / hw;
+                    const int rem = m0 - cn * hw;
+                    const int po = rem / p.Wo;
+                    const int qo = rem - po * p.Wo;
+                    cw = qo * p.stride + p.lower;
+                    ch = po * p.stride + p.lower;
+                }
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
+                    mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+                    const int tap = kb / p.kblocks_per_tap;
+                    const int c0 = (kb - tap * p.kblocks_per_tap) * BLOCK_K;
+                    if (p.a_im2col) {
+                        const int r = tap / p.ksize, s = tap - r * p.ksize;
+                        tma_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), c0, cw, ch, cn,
+                                           (uint16_t)s, (uint16_t)r);
+                    } else {
+                        tma_load_2d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), c0, m0);
+                    }
+                    tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, tn * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x200 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase, 0x300 + stage);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc<SWZ>(smem_a + stage * S::A_BYTES);
+                    const uint64_t bdesc = make_smem_desc<SWZ>(smem_b + stage * S::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(empty_bar(stage));   // smem slot reusable once these MMAs have read it
+                    if (kb == p.num_k_blocks - 1) umma_commit(tfull_bar(acc));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // row of the 128-row tile owned by this thread
+        float* xp = xpose + q * (32 * 33);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int m = tm * kBlockM + row;
+            const bool row_ok = m < p.M;
+            const int n_base = tn * BLOCK_N;
+
+            // output pixel index (dense, or top-left of the 2x2 upsample block)
+            long long opix = m;
+            long long up_row = 0;   // pixels per output row when upsampling
+            if (p.upsample) {
+                const int hw = p.Ho * p.Wo;
+                const int n = m / hw;
+                const int rem = m - n * hw;
+                const int po = rem / p.Wo;
+                const int qo = rem - po * p.Wo;
+                up_row = 2LL * p.Wo;
+                opix = ((long long)n * 2 * p.Ho + 2 * po) * up_row + 2 * qo;
+            }
+
+            mbar_wait(tfull_bar(acc), acc_phase, 0x400 + acc);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32 + (BLOCK_N % 32 ? 1 : 0); ++c) {
+                const int ncol = n_base + c * 32;   // first output channel of this chunk
+                if (ncol >= p.cout) break;          // warp-uniform
+                uint32_t v[32];
+                if (BLOCK_N % 32 == 0 || c * 32 + 32 <= BLOCK_N) {
+                    tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+                } else {
+                    uint32_t h[16];
+                    tmem_ld_32x16(t_row + (uint32_t)(c * 32), h);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[16 + j] = 0u; }
+                }
+                // residual prefetch overlaps the TMEM load latency
+                uint4 rres[4];
+                const bool has_res = (p.residual != nullptr) && row_ok;
+                if (has_res) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (long long)m * p.res_stride + ncol);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
+                }
+                tmem_ld_wait();
+
+                float f[32];
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + ncol);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = __ldg(bp + j);
+                    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+                    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+                    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+                }
+                if (p.leaky) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
+                }
+                if (has_res) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 r2 = __bfloat1622float2(h2[e]);
+                            f[8 * j + 2 * e + 0] += r2.x;
+                            f[8 * j + 2 * e + 1] += r2.y;
+                        }
+                    }
+                }
+
+                if (!p.out_fp32) {
+                    // bf16 output: every thread owns 32 consecutive channels (64 B) of its pixel
+                    if (row_ok) {
+                        uint4 o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 h2[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                h2[e] = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+                            o[j] = *reinterpret_cast<uint4*>(h2);
+                        }
+                        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+                        const int reps = p.upsample ? 4 : 1;
+                        for (int rep = 0; rep < reps; ++rep) {
+                            const long long pix = opix + (rep >> 1) * up_row + (rep & 1);
+                            uint4* op = reinterpret_cast<uint4*>(ob + pix * p.out_stride + ncol);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) op[j] = o[j];
+                        }
+                    }
+                } else {
+                    // fp32 output with an arbitrary (e.g. 255-float) pixel stride: transpose through shared memory so
+                    // each store instruction writes 32 consecutive floats of one pixel.
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = f[j];
+                    __syncwarp();
+                    float* of = reinterpret_cast<float*>(p.out);
+                    const int m_w = tm * kBlockM + q * 32;
+                    const bool col_ok = (ncol + lane) < p.cout;
+                    for (int r = 0; r < 32; ++r) {
+                        const int mr = m_w + r;
+                        if (mr < p.M && col_ok) of[(long long)mr * p.out_stride + ncol + lane] = xp[r * 33 + lane];
+                    }
+                    __syncwarp();
+                }
+            }
+            // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// Debug helper: fetch ONE A tile (128 pixels x BLOCK_K channels) through the same TMA path as the conv kernel and copy the
+// raw (still swizzled) shared-memory image to global memory, so tests can check the im2col/padding semantics in
+// isolation from the MMA.
+template <int SWZ>
+__global__ void tma_tile_dump_kernel(const __grid_constant__ CUtensorMap tmA, int a_im2col, int c0, int cw, int ch,
+                                     int cn, int off_w, int off_h, int m0, uint8_t* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    constexpr int BYTES = kBlockM * SWZ;
+    const uint32_t bar = smem_base + BYTES;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, BYTES);
+        if (a_im2col)
+            tma_load_im2col_4d(smem_base, &tmA, bar, c0, cw, ch, cn, (uint16_t)off_w, (uint16_t)off_h);
+        else
+            tma_load_2d(smem_base, &tmA, bar, c0, m0);
+    }
+    mbar_wait(bar, 0, 0x500);
+    for (int i = threadIdx.x; i < BYTES; i += blockDim.x) out[i] = smem_gen[i];
+}
+
+}  // namespace y3

@@ -1,0 +1,181 @@
+// YOLO decode: the elementwise stage of reference core/yolo_decode_layer.py:4-36 as ONE memory-bound kernel.
+//
+// Input : 3 grids  t[s] = [B, gh_s, gw_s, 3, 5+C] fp32  (model outputs, reference core/parse_model.py:209-210)
+// Output: bboxes [B, N, 4] (xmin, ymin, xmax, ymax; image fractions, unclipped), confidence [B, N, 1],
+//         class_probs [B, N, C];  N = 3 * sum_s gh_s*gw_s, scales concatenated in model-output order,
+//         flat index n = off_s + (i*gw + j)*3 + a.
+// Optional fused tail (reference core/yolo_nms.py:18-24): scores[B,N] = conf * max_c prob, class_idx[B,N] = argmax_c
+// (first max wins, int64) so the NMS stage does not have to re-read class_probs.
+//
+// Each CTA stages a contiguous run of records in shared memory with one 1-D bulk-TMA copy, then
+//   (1) one thread per record does the box / objectness math (and the class max if requested),
+//   (2) all threads stream sigmoid(class logits) back out with 16-byte stores (C % 4 == 0) or scalar stores.
+#pragma once
+#include "ptx.cuh"
+
+namespace y3 {
+
+constexpr int kDecodeThreads = 256;
+constexpr int kDecodeRecs = 64;   // records per CTA (multiple of 4 keeps every chunk start 16-byte aligned)
+
+struct DecodeArgs {
+    const float* in[3];
+    int gh[3], gw[3];
+    int rec_off[3];        // first record of scale s inside one image
+    int chunk_begin[4];    // prefix sum of per-scale chunk counts
+    float anchors[18];     // [3 scales][3 anchors][w, h]
+    int B, C, N;
+    float* bboxes;
+    float* conf;
+    float* probs;
+    float* scores;         // optional
+    long long* cls;        // optional
+};
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs a) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const int F = 5 + a.C;
+    float* rec = reinterpret_cast<float*>(dsm);                         // [kDecodeRecs * F]
+    int* out_rec = reinterpret_cast<int*>(rec + ((kDecodeRecs * F + 3) & ~3));   // [kDecodeRecs] global record index
+    __shared__ __align__(8) uint64_t bar;
+
+    int s = 0;
+    if ((int)blockIdx.x >= a.chunk_begin[1]) s = 1;
+    if ((int)blockIdx.x >= a.chunk_begin[2]) s = 2;
+    const int chunk = blockIdx.x - a.chunk_begin[s];
+    const int per_img = a.gh[s] * a.gw[s] * 3;
+    const long long total = (long long)a.B * per_img;
+    const long long r0 = (long long)chunk * kDecodeRecs;
+    const int nrec = (int)min((long long)kDecodeRecs, total - r0);
+    const float* src = a.in[s] + r0 * F;
+    const int nfl = nrec * F;
+    const uint32_t bulk_bytes = ((uint32_t)nfl * 4u) & ~15u;
+
+    const uint32_t bar_s = smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar_s, bulk_bytes);
+        if (bulk_bytes) bulk_load_1d(smem_u32(rec), src, bulk_bytes, bar_s);
+    }
+    // the (at most 3) floats past the last 16-byte multiple
+    for (int i = (int)(bulk_bytes >> 2) + threadIdx.x; i < nfl; i += kDecodeThreads) rec[i] = src[i];
+    mbar_wait(bar_s, 0, 0x600);
+    __syncthreads();
+
+    // ---- (1) per-record box / objectness (+ class max) ----
+    if ((int)threadIdx.x < nrec) {
+        const int t = threadIdx.x;
+        const long long fr = r0 + t;
+        const int b = (int)(fr / per_img);
+        const int local = (int)(fr - (long long)b * per_img);
+        const int cell = local / 3;
+        const int anc = local - cell * 3;
+        const int gi = cell / a.gw[s];
+        const int gj = cell - gi * a.gw[s];
+        const long long orec = (long long)b * a.N + a.rec_off[s] + local;
+        out_rec[t] = (int)orec;
+        const float* r = rec + t * F;
+        const float sx = sigmoidf_acc(r[0]);
+        const float sy = sigmoidf_acc(r[1]);
+        const float w = expf(r[2]) * a.anchors[(s * 3 + anc) * 2 + 0];
+        const float h = expf(r[3]) * a.anchors[(s * 3 + anc) * 2 + 1];
+        const float obj = sigmoidf_acc(r[4]);
+        const float cx = __fdiv_rn(__fadd_rn(sx, (float)gj), (float)a.gw[s]);
+        const float cy = __fdiv_rn(__fadd_rn(sy, (float)gi), (float)a.gh[s]);
+        const float hw = w * 0.5f, hh = h * 0.5f;
+        float4 box;
+        box.x = __fsub_rn(cx, hw);
+        box.y = __fsub_rn(cy, hh);
+        box.z = __fadd_rn(cx, hw);
+        box.w = __fadd_rn(cy, hh);
+        reinterpret_cast<float4*>(a.bboxes)[orec] = box;
+        a.conf[orec] = obj;
+        rec[t * F + 4] = obj;   // kept for the fused score in phase (3)
+    }
+    __syncthreads();
+
+    // ---- (2) class probabilities ----
+    const int C = a.C;
+    if ((C & 3) == 0) {
+        const int c4 = C >> 2;
+        const int n4 = nrec * c4;
+        for (int e = threadIdx.x; e < n4; e += kDecodeThreads) {
+            const int ri = e / c4;
+            const int c = (e - ri * c4) << 2;
+            const float* r = rec + ri * F + 5 + c;
+            float4 o;
+            o.x = sigmoidf_acc(r[0]);
+            o.y = sigmoidf_acc(r[1]);
+            o.z = sigmoidf_acc(r[2]);
+            o.w = sigmoidf_acc(r[3]);
+            *reinterpret_cast<float4*>(a.probs + (long long)out_rec[ri] * C + c) = o;
+            float* w = rec + ri * F + 5 + c;
+            w[0] = o.x; w[1] = o.y; w[2] = o.z; w[3] = o.w;
+        }
+    } else {
+        const int n1 = nrec * C;
+        for (int e = threadIdx.x; e < n1; e += kDecodeThreads) {
+            const int ri = e / C;
+            const int c = e - ri * C;
+            const float pc = sigmoidf_acc(rec[ri * F + 5 + c]);
+            a.probs[(long long)out_rec[ri] * C + c] = pc;
+            rec[ri * F + 5 + c] = pc;
+        }
+    }
+
+    // ---- (3) fused class max: score = conf * max_c prob, class = first arg-max (reference core/yolo_nms.py:18-24) ----
+    if (a.scores != nullptr) {
+        __syncthreads();
+        if ((int)threadIdx.x < nrec) {
+            const float* r = rec + threadIdx.x * F;
+            float best = r[5];
+            int bi = 0;
+            for (int c = 1; c < C; ++c) {
+                const float pc = r[5 + c];
+                if (pc > best) { best = pc; bi = c; }
+            }
+            const long long orec = out_rec[threadIdx.x];
+            a.scores[orec] = __fmul_rn(r[4], best);
+            a.cls[orec] = (long long)bi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Class reduce for the stand-alone yolo_nms entry point (reference core/yolo_nms.py:18-24):
+// class_idx = argmax_c probs (first max wins), score = conf * max_c probs.  One warp per record, coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) class_reduce_kernel(const float* __restrict__ probs,
+                                                           const float* __restrict__ conf, long long nrec, int C,
+                                                           float* __restrict__ scores, long long* __restrict__ cls) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < nrec; r += nwarps) {
+        const float* p = probs + r * C;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float v = __ldg(p + c);
+            if (v > best) { best = v; bi = c; }   // strictly greater: earlier index wins inside a lane
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+            scores[r] = __fmul_rn(__ldg(conf + r), best);
+            cls[r] = (long long)(bi == 0x7fffffff ? 0 : bi);
+        }
+    }
+}
+
+}  // namespace y3

@@ -1,0 +1,290 @@
+// Class-agnostic padded NMS with the semantics of tf.image.non_max_suppression_padded(pad_to_max_output_size=True)
+// as called by reference core/yolo_nms.py:26-33 (restated in oracle/nms_oracle.py):
+//   1. masked score = score > score_thr ? score : 0 ; filtered boxes become all-zero boxes
+//   2. stable descending sort by masked score (ties: lower index first)
+//   3. greedy suppression in sorted order, a box is suppressed by an earlier surviving box when
+//      iou >= iou_thr, iou = inter / (area_a + area_b - inter + 1e-8) in fp32 with separately rounded operations
+//   4. selected = first max_boxes surviving boxes that have ANY coordinate > 0, mapped back to input indices,
+//      zero padded; num_valid = their count.
+//
+// One CTA (1024 threads) per image:
+//   sort    : (score key, index) pairs in shared memory, bitonic network with a (key desc, index asc) comparator
+//   suppress: candidates are consumed in sorted order in chunks of 256:
+//             A  every candidate of the chunk is tested against the boxes kept so far (all threads),
+//             B  256x256 upper-triangular IoU bitmask of the chunk built in shared memory (all threads),
+//             C  one warp resolves the chunk sequentially with word-wide bit operations, visiting only survivors,
+//             D  survivors are appended to the kept list / output (ballot + popc compaction).
+//   The loop stops as soon as max_boxes valid boxes are selected.
+#pragma once
+#include "ptx.cuh"
+
+namespace y3 {
+
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsChunk = 256;
+constexpr int kNmsKeptCap = 1024;
+constexpr int kNmsMaxN = 32768;
+
+struct NmsArgs {
+    const float* boxes;      // [B, N, 4]
+    const float* scores;     // [B, N]
+    int B, N, NP;            // NP = power of two >= N
+    int max_boxes;
+    float iou_thr, score_thr;
+    int* selected;           // [B, max_boxes] int32, zero padded
+    int* num_valid;          // [B]
+    int* status;             // [B] 0 ok, 1 kept-list overflow (pathological input)
+};
+
+__device__ __forceinline__ uint32_t score_key(float s) {
+    uint32_t u = __float_as_uint(s);
+    if (u == 0x80000000u) u = 0u;   // -0 == +0 for ordering
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// IoU exactly as TF's _bbox_overlap: every operation separately rounded (no FMA contraction), IEEE division.
+__device__ __forceinline__ float iou_tf(const float4 a, const float4 b) {
+    const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
+    const float ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
+    const float iw = fmaxf(__fsub_rn(ix2, ix1), 0.0f);
+    const float ih = fmaxf(__fsub_rn(iy2, iy1), 0.0f);
+    const float inter = __fmul_rn(iw, ih);
+    const float area_a = __fmul_rn(__fsub_rn(a.w, a.y), __fsub_rn(a.z, a.x));
+    const float area_b = __fmul_rn(__fsub_rn(b.w, b.y), __fsub_rn(b.z, b.x));
+    const float uni = __fadd_rn(__fsub_rn(__fadd_rn(area_a, area_b), inter), 1e-8f);
+    return __fdiv_rn(inter, uni);
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
+    extern __shared__ __align__(16) uint8_t nsm[];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(nsm);                       // [NP]
+    uint16_t* idxs = reinterpret_cast<uint16_t*>(nsm + (size_t)a.NP * 4);    // [NP]
+    uint8_t* tail = nsm + (size_t)a.NP * 6;
+    float4* kept = reinterpret_cast<float4*>(tail);                          // [kNmsKeptCap]
+    float4* cbox = kept + kNmsKeptCap;                                       // [kNmsChunk]
+    uint32_t* mask = reinterpret_cast<uint32_t*>(cbox + kNmsChunk);          // [kNmsChunk][8]
+    uint32_t* dead = mask + kNmsChunk * 8;                                   // [8] chunk-level dead bits
+    __shared__ int s_ncand, s_nkept, s_nsel, s_overflow;
+    __shared__ int s_warp_cnt[kNmsThreads / 32];
+
+    const int img = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
+    const float* sc = a.scores + (long long)img * a.N;
+    const float4* bx = reinterpret_cast<const float4*>(a.boxes) + (long long)img * a.N;
+    int* sel = a.selected + (long long)img * a.max_boxes;
+
+    // With score_thr >= 0 and iou_thr > 0 the filtered (all-zero) boxes sort after every passing box, never suppress
+    // and are never selected, so only passing boxes need to be sorted/visited.  Otherwise keep all N candidates.
+    const bool compact = (a.score_thr >= 0.0f) && (a.iou_thr > 0.0f);
+
+    if (tid == 0) { s_ncand = 0; s_nkept = 0; s_nsel = 0; s_overflow = 0; }
+    for (int i = tid; i < a.max_boxes; i += kNmsThreads) sel[i] = 0;
+    __syncthreads();
+
+    // ---------------- candidate list (index order) ----------------
+    int ncand;
+    if (compact) {
+        // ordered compaction, one pass of 1024-wide tiles: ballot inside warps, running base across tiles
+        int base = 0;
+        for (int t0 = 0; t0 < a.N; t0 += kNmsThreads) {
+            const int i = t0 + tid;
+            const float s = (i < a.N) ? sc[i] : 0.0f;
+            const bool pass = (i < a.N) && (s > a.score_thr);
+            const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) s_warp_cnt[wid] = __popc(bal);
+            __syncthreads();
+            int woff = 0, tot = 0;
+            for (int w = 0; w < kNmsThreads / 32; ++w) {
+                const int c = s_warp_cnt[w];
+                if (w < wid) woff += c;
+                tot += c;
+            }
+            if (pass) {
+                const int pos = base + woff + __popc(bal & ((1u << lane) - 1u));
+                keys[pos] = score_key(s);
+                idxs[pos] = (uint16_t)i;
+            }
+            base += tot;
+            __syncthreads();
+        }
+        ncand = base;
+    } else {
+        for (int i = tid; i < a.N; i += kNmsThreads) {
+            const float s = sc[i];
+            const float ms = (s > a.score_thr) ? s : 0.0f;
+            keys[i] = score_key(ms);
+            idxs[i] = (uint16_t)i;
+        }
+        ncand = a.N;
+    }
+    // pad to a power of two with entries that sort last
+    int np = 32;
+    while (np < ncand) np <<= 1;
+    for (int i = ncand + tid; i < np; i += kNmsThreads) { keys[i] = 0u; idxs[i] = 0xFFFFu; }
+    __syncthreads();
+
+    // ---------------- bitonic sort: descending key, ascending index on ties ----------------
+    for (int k = 2; k <= np; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (np >> 1); t += kNmsThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+                const int l = i | j;
+                const uint32_t ki = keys[i], kl = keys[l];
+                const uint16_t xi = idxs[i], xl = idxs[l];
+                const bool i_first = (ki > kl) || (ki == kl && xi < xl);   // "i sorts before l"
+                const bool want_first = ((i & k) == 0);                    // this sub-sequence is in final order
+                if (i_first != want_first) {
+                    keys[i] = kl; keys[l] = ki;
+                    idxs[i] = xl; idxs[l] = xi;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---------------- greedy suppression over sorted candidates ----------------
+    for (int c0 = 0; c0 < ncand; c0 += kNmsChunk) {
+        const int nc = min(kNmsChunk, ncand - c0);
+        const int nkept = s_nkept;
+        // load chunk boxes (masked), clear dead bits
+        if (tid < kNmsChunk) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < nc) {
+                const int oi = idxs[c0 + tid];
+                const bool pass = sc[oi] > a.score_thr;
+                if (pass) b = bx[oi];
+            }
+            cbox[tid] = b;
+        }
+        if (tid < 8) dead[tid] = 0u;
+        __syncthreads();
+
+        // A: chunk candidates vs kept boxes.  thread -> (candidate = tid % 256, kept subset = tid / 256)
+        {
+            const int ci = tid & (kNmsChunk - 1);
+            if (ci < nc) {
+                const float4 b = cbox[ci];
+                bool d = false;
+                for (int k = tid >> 8; k < nkept && !d; k += kNmsThreads / kNmsChunk)
+                    d = iou_tf(kept[k], b) >= a.iou_thr;
+                if (d) atomicOr(&dead[ci >> 5], 1u << (ci & 31));
+            }
+        }
+        __syncthreads();
+
+        // B: intra-chunk bitmask. thread -> (row i = tid / 4, two 32-column words w = (tid % 4) * 2 + {0,1})
+        {
+            const int i = tid >> 2;
+            const bool row_alive = (i < nc) && !((dead[i >> 5] >> (i & 31)) & 1u);
+            const float4 bi = cbox[i];
+#pragma unroll
+            for (int ww = 0; ww < 2; ++ww) {
+                const int w = ((tid & 3) << 1) + ww;
+                uint32_t bits = 0u;
+                if (row_alive && (w * 32 + 31) > i) {
+                    const int jlo = max(w * 32, i + 1);
+                    const int jhi = min(w * 32 + 32, nc);
+                    for (int j = jlo; j < jhi; ++j)
+                        if (iou_tf(bi, cbox[j]) >= a.iou_thr) bits |= 1u << (j & 31);
+                }
+                mask[i * 8 + w] = bits;
+            }
+        }
+        __syncthreads();
+
+        // C: sequential resolution by warp 0; lane w (< 8) owns dead word w.  Only surviving rows are visited.
+        if (wid == 0) {
+            uint32_t dw = (lane < 8) ? dead[lane] : 0xffffffffu;
+            // bits beyond nc are dead
+            if (lane < 8) {
+                const int lo = lane * 32;
+                if (nc <= lo) dw = 0xffffffffu;
+                else if (nc < lo + 32) dw |= ~((1u << (nc - lo)) - 1u);
+            }
+            int i = 0;
+            while (true) {
+                // next alive index >= i
+                const uint32_t alive_w = (lane < 8) ? ~dw : 0u;
+                uint32_t cand = alive_w;
+                const int wi = i >> 5;
+                if (lane < wi) cand = 0u;
+                else if (lane == wi) cand &= ~((1u << (i & 31)) - 1u);
+                const uint32_t has = __ballot_sync(0xffffffffu, cand != 0u);
+                if (has == 0u) break;
+                const int fw = __ffs(has) - 1;
+                const uint32_t wbits = __shfl_sync(0xffffffffu, cand, fw);
+                const int row = fw * 32 + (__ffs(wbits) - 1);
+                if (lane < 8) dw |= mask[row * 8 + lane];
+                i = row + 1;
+                if (i >= nc) break;
+            }
+            if (lane < 8) dead[lane] = dw;
+        }
+        __syncthreads();
+
+        // D: append survivors in order (first kNmsChunk threads = 8 warps), count the valid ones
+        if (tid < kNmsChunk) {
+            const bool alive = !((dead[tid >> 5] >> (tid & 31)) & 1u);
+            const float4 b = cbox[tid];
+            const bool is_zero = (b.x == 0.f && b.y == 0.f && b.z == 0.f && b.w == 0.f);
+            // all-zero boxes can only matter as suppressors when iou_thr <= 0
+            const bool keep = alive && !(compact && is_zero);
+            const bool valid = alive && (b.x > 0.f || b.y > 0.f || b.z > 0.f || b.w > 0.f);
+            const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+            const uint32_t vb = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) { s_warp_cnt[wid] = __popc(kb); s_warp_cnt[8 + wid] = __popc(vb); }
+            // named barrier over the 256 participating threads
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            int koff = s_nkept, voff = s_nsel;
+            for (int w = 0; w < wid; ++w) { koff += s_warp_cnt[w]; voff += s_warp_cnt[8 + w]; }
+            const uint32_t lm = (1u << lane) - 1u;
+            if (keep) {
+                const int kp = koff + __popc(kb & lm);
+                if (kp < kNmsKeptCap) kept[kp] = b; else s_overflow = 1;
+            }
+            if (valid) {
+                const int vp = voff + __popc(vb & lm);
+                if (vp < a.max_boxes) sel[vp] = (int)idxs[c0 + tid];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid == 0) {
+                int kt = 0, vt = 0;
+                for (int w = 0; w < 8; ++w) { kt += s_warp_cnt[w]; vt += s_warp_cnt[8 + w]; }
+                s_nkept = min(s_nkept + kt, kNmsKeptCap);
+                s_nsel = s_nsel + vt;
+            }
+        }
+        __syncthreads();
+        if (s_nsel >= a.max_boxes || s_overflow) break;
+    }
+    if (tid == 0) {
+        a.num_valid[img] = min(s_nsel, a.max_boxes);
+        a.status[img] = s_overflow;
+    }
+}
+
+// gather_valid_detections_results of reference inference.py:21-28, batched and zero padded to max_boxes rows.
+__global__ void gather_detections_kernel(const float* __restrict__ boxes, const long long* __restrict__ cls,
+                                         const float* __restrict__ scores, const int* __restrict__ selected,
+                                         const int* __restrict__ num_valid, int B, int N, int max_boxes,
+                                         float* __restrict__ out_boxes, long long* __restrict__ out_cls,
+                                         float* __restrict__ out_scores) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * max_boxes) return;
+    const int b = t / max_boxes, k = t - b * max_boxes;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long c = 0;
+    float s = 0.f;
+    if (k < num_valid[b]) {
+        const long long src = (long long)b * N + selected[t];
+        bb = reinterpret_cast<const float4*>(boxes)[src];
+        c = cls[src];
+        s = scores[src];
+    }
+    reinterpret_cast<float4*>(out_boxes)[t] = bb;
+    out_cls[t] = c;
+    out_scores[t] = s;
+}
+
+}  // namespace y3

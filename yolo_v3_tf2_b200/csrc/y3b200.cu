@@ -1,0 +1,1007 @@
+// liby3b200.so -- C ABI (include/y3b200.h) over the sm_100a kernels in this directory.
+// Host side: tensor-map construction, the graph planner (fusion of add / upsample / concat into conv epilogues,
+// activation-arena layout) and the per-layer launcher.  No CPU compute path exists: without a GPU context every
+// compute entry point returns an error.
+#include "../../include/y3b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "conv_first.cuh"
+#include "conv_tc.cuh"
+#include "decode.cuh"
+#include "nms.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define Y3_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(Y3_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// driver entry points (resolved at run time so the library loads on machines without libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Driver {
+    EncodeTiledFn tiled = nullptr;
+    EncodeIm2colFn im2col = nullptr;
+    int version = 0;
+};
+
+int load_driver(Driver& d) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    Y3_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    d.tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    fn = nullptr;
+    Y3_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeIm2col not available");
+    d.im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+    Y3_CUDA(cudaDriverGetVersion(&d.version));
+    return Y3_OK;
+}
+
+CUtensorMapSwizzle swz_enum(int swz) {
+    return swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 2-D bf16 matrix [rows][cols] with a row pitch of row_stride elements; box = box_rows x (swz/2) columns.
+int make_map_2d(const Driver& d, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
+                uint32_t box_rows, int swz, bool weights) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride * 2};
+    cuuint32_t box[2] = {(cuuint32_t)(swz / 2), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = d.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(swz),
+                         weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return Y3_OK;
+}
+
+// NHWC bf16 activation seen as (C, W, H, N) for the im2col load of a k x k conv with the reference's padding rule:
+//   stride 1 ('same'):                      pad_lo = pad_hi = (k-1)/2
+//   stride 2 (ZeroPadding2D((1,0),(1,0)) + 'valid'):  pad_lo = 1, pad_hi = 0        (core/parse_model.py:31-43)
+// lower corner = -pad_lo, upper corner = pad_hi - (k-1).
+int make_map_im2col(const Driver& d, CUtensorMap* tm, const void* base, int N, int H, int W, int C,
+                    uint64_t pix_stride, int ksize, int stride, int pad_lo, int pad_hi, int swz) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {pix_stride * 2, pix_stride * 2 * (uint64_t)W, pix_stride * 2 * (uint64_t)W * (uint64_t)H};
+    int lower[2] = {-pad_lo, -pad_lo};
+    int upper[2] = {pad_hi - (ksize - 1), pad_hi - (ksize - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = d.im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                          upper, (cuuint32_t)(swz / 2), (cuuint32_t)y3::kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swz_enum(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeIm2col failed: " + std::to_string((int)r));
+    // Driver <= 13.1 mis-encodes im2col maps of tensors smaller than 128 KiB (bit 21 of the second descriptor word);
+    // the same correction is applied by NVIDIA's open-source CUTLASS im2col descriptor builder.
+    const uint64_t bytes = pix_stride * 2 * (uint64_t)W * (uint64_t)H * (uint64_t)N;
+    if (d.version <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+    return Y3_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv tile configuration + launch
+// ------------------------------------------------------------------------------------------------
+struct ConvCfg {
+    int block_n, swz, stages;
+};
+
+int pick_block_n(int cout) {
+    if (cout <= 32) return 32;
+    if (cout <= 64) return 64;
+    if (cout <= 128) return 128;
+    return 256;
+}
+
+bool pick_cfg(int cin, int cout, ConvCfg& c) {
+    if (cin % 64 == 0) c.swz = 128;
+    else if (cin % 32 == 0) c.swz = 64;
+    else return false;
+    c.block_n = pick_block_n(cout);
+    if (c.swz == 128) c.stages = (c.block_n == 256) ? 4 : (c.block_n == 128 ? 6 : 8);
+    else c.stages = 8;
+    return true;
+}
+
+template <int BN, int SWZ, int ST>
+cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& args, int sms,
+                          cudaStream_t st) {
+    using S = y3::ConvSmem<BN, SWZ, ST>;
+    static_assert(S::TOTAL <= 232448, "shared memory budget");
+    auto kern = y3::conv_tc_kernel<BN, SWZ, ST>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = args.tiles_m * args.tiles_n;
+    const int grid = std::max(1, std::min(tiles, sms));
+    kern<<<grid, y3::kConvThreads, S::TOTAL, st>>>(ta, tb, args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv(const ConvCfg& c, const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& a, int sms,
+                        cudaStream_t st) {
+    if (c.swz == 128) {
+        switch (c.block_n) {
+            case 32: return launch_conv_t<32, 128, 8>(ta, tb, a, sms, st);
+            case 64: return launch_conv_t<64, 128, 8>(ta, tb, a, sms, st);
+            case 128: return launch_conv_t<128, 128, 6>(ta, tb, a, sms, st);
+            case 256: return launch_conv_t<256, 128, 4>(ta, tb, a, sms, st);
+        }
+    } else {
+        switch (c.block_n) {
+            case 32: return launch_conv_t<32, 64, 8>(ta, tb, a, sms, st);
+            case 64: return launch_conv_t<64, 64, 8>(ta, tb, a, sms, st);
+            case 128: return launch_conv_t<128, 64, 8>(ta, tb, a, sms, st);
+            case 256: return launch_conv_t<256, 64, 8>(ta, tb, a, sms, st);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+// reference padding rule (core/parse_model.py:29-43)
+void conv_geometry(int H, int W, int k, int stride, int pad, int& Ho, int& Wo, int& pad_lo, int& pad_hi) {
+    if (stride > 1) {
+        pad_lo = 1;
+        pad_hi = 0;
+    } else if (pad == 1) {
+        pad_lo = (k - 1) / 2;
+        pad_hi = (k - 1) - pad_lo;
+    } else {
+        pad_lo = pad_hi = 0;
+    }
+    Ho = (H + pad_lo + pad_hi - k) / stride + 1;
+    Wo = (W + pad_lo + pad_hi - k) / stride + 1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context / net objects
+// ------------------------------------------------------------------------------------------------
+struct y3_ctx {
+    int device = -1;
+    int sms = 148;
+    Driver drv;
+};
+
+namespace {
+
+struct TensorInfo {
+    int H = 0, W = 0, C = 0;
+    int producer = -1;            // layer index, -1 for the input image
+    std::vector<int> consumers;   // layer indices
+    bool materialized = false;    // some kernel writes it to memory
+    bool fp32_output = false;     // network output written by a head conv
+    int out_index = -1;
+    int buffer = -1, chan_off = 0, pix_stride = 0;
+};
+
+struct BufferInfo {
+    int H = 0, W = 0, C = 0;
+    int64_t bytes = 0;
+    int first = 1 << 30, last = -1;
+    int64_t offset = 0;
+};
+
+struct ConvWeights {
+    int cin = 0, cout = 0, k = 0, cout_pad = 0;
+    bool direct = false;
+    void* w = nullptr;     // bf16 [cout_pad][k*k*cin]  or fp32 [k*k*cin][cout] for the direct kernel
+    float* bias = nullptr; // fp32 [cout_pad]
+    bool loaded = false;
+};
+
+struct Step {
+    int kind = 0;          // 1 tc conv, 2 direct conv, 3 add, 4 upsample, 5 copy
+    int layer = -1;
+    int conv_idx = -1;
+    int src = -1, src2 = -1, dst = -1;   // tensor ids
+    int dst_chan_extra = 0;              // copy: extra channel offset inside dst
+    ConvCfg cfg{};
+    int Ho = 0, Wo = 0, pad_lo = 0, pad_hi = 0;
+    int fused_up = 0;
+    CUtensorMap tmA, tmB;
+};
+
+}  // namespace
+
+struct y3_net {
+    y3_ctx* ctx = nullptr;
+    int H = 0, W = 0, max_batch = 0, nclasses = 0;
+    std::vector<y3_layer_desc> layers;
+    std::vector<TensorInfo> tensors;   // tensor 0 = input
+    std::vector<BufferInfo> buffers;
+    std::vector<y3_layer_plan> plans;
+    std::vector<Step> steps;
+    std::vector<ConvWeights> convs;
+    std::vector<int> conv_layer;       // conv idx -> layer
+    std::vector<int> outputs;          // tensor ids of network outputs, model order
+    int64_t arena_bytes = 0;
+    uint8_t* arena = nullptr;
+    bool maps_built = false;
+};
+
+namespace {
+
+int plan_net(y3_net& n) {
+    const int L = (int)n.layers.size();
+    n.tensors.assign(L + 1, TensorInfo{});
+    n.plans.assign(L, y3_layer_plan{});
+    n.tensors[0].H = n.H;
+    n.tensors[0].W = n.W;
+    n.tensors[0].C = 3;
+    n.tensors[0].materialized = true;
+
+    // ---- shapes + validation ----
+    for (int i = 0; i < L; ++i) {
+        const y3_layer_desc& d = n.layers[i];
+        TensorInfo& t = n.tensors[i + 1];
+        t.producer = i;
+        auto check_src = [&](int s) { return s >= 0 && s <= i; };
+        if (!check_src(d.src0)) return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": bad src0");
+        const TensorInfo& a = n.tensors[d.src0];
+        switch (d.op) {
+            case Y3_OP_CONV: {
+                if (d.ksize != 1 && d.ksize != 3)
+                    return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": conv size must be 1 or 3");
+                if (d.stride != 1 && d.stride != 2)
+                    return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": conv stride must be 1 or 2");
+                if (d.filters <= 0) return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": filters <= 0");
+                if (d.activation != 0 && d.activation != 1)
+                    return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": Invalid activation");
+                int Ho, Wo, pl, ph;
+                conv_geometry(a.H, a.W, d.ksize, d.stride, d.pad, Ho, Wo, pl, ph);
+                if (Ho <= 0 || Wo <= 0) return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": empty output");
+                t.H = Ho; t.W = Wo; t.C = d.filters;
+                n.conv_layer.push_back(i);
+                break;
+            }
+            case Y3_OP_SHORTCUT: {
+                if (!check_src(d.src1)) return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": bad 'from'");
+                const TensorInfo& b = n.tensors[d.src1];
+                if (a.H != b.H || a.W != b.W || a.C != b.C)
+                    return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": shortcut shape mismatch");
+                t.H = a.H; t.W = a.W; t.C = a.C;
+                break;
+            }
+            case Y3_OP_UPSAMPLE:
+                if (d.stride != 2) return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": upsample stride must be 2");
+                t.H = a.H * 2; t.W = a.W * 2; t.C = a.C;
+                break;
+            case Y3_OP_CONCAT: {
+                if (!check_src(d.src1)) return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": bad concat source");
+                const TensorInfo& b = n.tensors[d.src1];
+                if (a.H != b.H || a.W != b.W)
+                    return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": concat shape mismatch");
+                t.H = a.H; t.W = a.W; t.C = a.C + b.C;
+                break;
+            }
+            case Y3_OP_YOLO:
+                if (a.C != 3 * (5 + n.nclasses))
+                    return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": yolo input channels " +
+                                                    std::to_string(a.C) + " != 3*(5+nclasses)");
+                t.H = a.H; t.W = a.W; t.C = a.C;
+                break;
+            case Y3_OP_MAXPOOL:
+                return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": maxpool (yolov3-tiny) is not on this path yet");
+            default:
+                return fail(Y3_ERR_INVALID, std::to_string(d.op) + " not recognized as layer_conf type");
+        }
+        n.tensors[d.src0].consumers.push_back(i);
+        if (d.op == Y3_OP_SHORTCUT || d.op == Y3_OP_CONCAT) n.tensors[d.src1].consumers.push_back(i);
+        n.plans[i].H = t.H; n.plans[i].W = t.W; n.plans[i].C = t.C;
+        n.plans[i].fused_add = -1;
+        n.plans[i].buffer = -1;
+    }
+
+    // ---- fusion: conv (+shortcut) (+upsample) (+yolo output) ----
+    std::vector<int> writes(L, -1);        // conv layer -> tensor id it materializes
+    std::vector<int> residual(L, -1);
+    std::vector<int> fused_up(L, 0);
+    std::vector<char> layer_fused(L, 0);   // shortcut / upsample / yolo absorbed into a conv
+    for (int i = 0; i < L; ++i) {
+        if (n.layers[i].op != Y3_OP_CONV) continue;
+        int r = i + 1;
+        {
+            const auto& cons = n.tensors[r].consumers;
+            if (cons.size() == 1 && n.layers[cons[0]].op == Y3_OP_SHORTCUT) {
+                const y3_layer_desc& s = n.layers[cons[0]];
+                const int other = (s.src0 == r) ? s.src1 : s.src0;
+                if (other != r && other != 0 && n.tensors[r].C % 32 == 0) {
+                    residual[i] = other;
+                    layer_fused[cons[0]] = 1;
+                    r = cons[0] + 1;
+                }
+            }
+        }
+        {
+            const auto& cons = n.tensors[r].consumers;
+            if (cons.size() == 1 && n.layers[cons[0]].op == Y3_OP_UPSAMPLE && n.tensors[r].C % 32 == 0) {
+                fused_up[i] = 1;
+                layer_fused[cons[0]] = 1;
+                r = cons[0] + 1;
+            }
+        }
+        {
+            const auto& cons = n.tensors[r].consumers;
+            if (cons.size() == 1 && n.layers[cons[0]].op == Y3_OP_YOLO && !fused_up[i]) {
+                layer_fused[cons[0]] = 1;
+                r = cons[0] + 1;
+                n.tensors[r].fp32_output = true;
+            }
+        }
+        writes[i] = r;
+        n.tensors[r].materialized = true;
+    }
+    for (int i = 0; i < L; ++i) {
+        const int op = n.layers[i].op;
+        if (op == Y3_OP_YOLO) {
+            if (!layer_fused[i])
+                return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": yolo layer must directly follow a conv");
+            n.tensors[i + 1].out_index = (int)n.outputs.size();
+            n.outputs.push_back(i + 1);
+            if (!n.tensors[i + 1].consumers.empty())
+                return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": yolo output consumed by another layer");
+        } else if ((op == Y3_OP_SHORTCUT || op == Y3_OP_UPSAMPLE) && !layer_fused[i]) {
+            n.tensors[i + 1].materialized = true;
+        } else if (op == Y3_OP_CONCAT) {
+            n.tensors[i + 1].materialized = true;
+        }
+    }
+    if (n.outputs.empty()) return fail(Y3_ERR_INVALID, "network has no yolo output");
+
+    // every non-input bf16 tensor must have C % 8 == 0 (16-byte vector stores / TMA strides)
+    for (int t = 1; t <= L; ++t)
+        if (n.tensors[t].materialized && !n.tensors[t].fp32_output && n.tensors[t].C % 8 != 0)
+            return fail(Y3_ERR_UNSUPPORTED, "tensor " + std::to_string(t) + ": channel count must be a multiple of 8");
+
+    // ---- concat placement: operands are produced directly inside the concat buffer when possible ----
+    auto new_buffer = [&](int H, int W, int C) {
+        BufferInfo b;
+        b.H = H; b.W = W; b.C = C;
+        b.bytes = (int64_t)n.max_batch * H * W * C * 2;
+        n.buffers.push_back(b);
+        return (int)n.buffers.size() - 1;
+    };
+    std::vector<std::pair<int, int>> copies;   // (concat layer, operand index) that need a copy kernel
+    for (int i = 0; i < L; ++i) {
+        if (n.layers[i].op != Y3_OP_CONCAT) continue;
+        TensorInfo& tc = n.tensors[i + 1];
+        tc.buffer = new_buffer(tc.H, tc.W, tc.C);
+        tc.chan_off = 0;
+        tc.pix_stride = tc.C;
+        const int ops[2] = {n.layers[i].src0, n.layers[i].src1};
+        int off = 0;
+        for (int k = 0; k < 2; ++k) {
+            TensorInfo& o = n.tensors[ops[k]];
+            const bool placeable = ops[k] != 0 && o.materialized && o.buffer < 0 && !o.fp32_output &&
+                                   n.layers[o.producer].op != Y3_OP_CONCAT && (off % 8 == 0) &&
+                                   !(k == 1 && ops[0] == ops[1]);
+            if (placeable) {
+                o.buffer = tc.buffer;
+                o.chan_off = off;
+                o.pix_stride = tc.C;
+            } else {
+                copies.push_back({i, k});
+            }
+            off += o.C;
+        }
+    }
+    for (int t = 1; t <= L; ++t) {
+        TensorInfo& ti = n.tensors[t];
+        if (ti.materialized && !ti.fp32_output && ti.buffer < 0) {
+            ti.buffer = new_buffer(ti.H, ti.W, ti.C);
+            ti.chan_off = 0;
+            ti.pix_stride = ti.C;
+        }
+    }
+
+    // ---- steps ----
+    int conv_counter = 0;
+    n.convs.assign(n.conv_layer.size(), ConvWeights{});
+    auto touch = [&](int tensor, int step) {
+        if (tensor <= 0) return;
+        const TensorInfo& ti = n.tensors[tensor];
+        if (ti.buffer < 0) return;
+        BufferInfo& b = n.buffers[ti.buffer];
+        b.first = std::min(b.first, step);
+        b.last = std::max(b.last, step);
+    };
+    for (int i = 0; i < L; ++i) {
+        const y3_layer_desc& d = n.layers[i];
+        y3_layer_plan& pl = n.plans[i];
+        if (d.op == Y3_OP_CONV) {
+            Step s;
+            s.layer = i;
+            s.conv_idx = conv_counter++;
+            s.src = d.src0;
+            s.src2 = residual[i];
+            s.dst = writes[i];
+            s.fused_up = fused_up[i];
+            const TensorInfo& a = n.tensors[d.src0];
+            conv_geometry(a.H, a.W, d.ksize, d.stride, d.pad, s.Ho, s.Wo, s.pad_lo, s.pad_hi);
+            ConvWeights& w = n.convs[s.conv_idx];
+            w.cin = a.C; w.cout = d.filters; w.k = d.ksize;
+            const bool tc_ok = pick_cfg(a.C, d.filters, s.cfg) && d.src0 != 0;
+            if (tc_ok) {
+                if (!n.tensors[writes[i]].fp32_output && d.filters % 32 != 0)
+                    return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": bf16 conv outputs need filters % 32 == 0");
+                s.kind = 1;
+                w.cout_pad = ((d.filters + s.cfg.block_n - 1) / s.cfg.block_n) * s.cfg.block_n;
+                pl.block_n = s.cfg.block_n; pl.swizzle = s.cfg.swz; pl.stages = s.cfg.stages;
+            } else {
+                // direct CUDA-core conv: fp32 NHWC network input with 3 channels, bf16 output, no fusion
+                if (d.src0 != 0 || a.C != 3 || (d.filters != 32 && d.filters != 16) || residual[i] >= 0 || fused_up[i] ||
+                    n.tensors[writes[i]].fp32_output)
+                    return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": conv with Cin=" + std::to_string(a.C) +
+                                                        " is only supported as the 3-channel stem (16/32 filters)");
+                s.kind = 2;
+                w.direct = true;
+                w.cout_pad = d.filters;
+            }
+            pl.kernel = s.kind;
+            pl.fused_add = residual[i];
+            pl.fused_upsample = fused_up[i];
+            const int step_id = (int)n.steps.size();
+            touch(s.src, step_id); touch(s.src2, step_id); touch(s.dst, step_id);
+            n.steps.push_back(s);
+        } else if ((d.op == Y3_OP_SHORTCUT || d.op == Y3_OP_UPSAMPLE) && !layer_fused[i]) {
+            if (d.src0 == 0 || (d.op == Y3_OP_SHORTCUT && d.src1 == 0))
+                return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": op on the raw input image");
+            Step s;
+            s.kind = d.op == Y3_OP_SHORTCUT ? 3 : 4;
+            s.layer = i;
+            s.src = d.src0;
+            s.src2 = d.op == Y3_OP_SHORTCUT ? d.src1 : -1;
+            s.dst = i + 1;
+            pl.kernel = s.kind;
+            const int step_id = (int)n.steps.size();
+            touch(s.src, step_id); touch(s.src2, step_id); touch(s.dst, step_id);
+            n.steps.push_back(s);
+        } else if (d.op == Y3_OP_CONCAT) {
+            int off = 0;
+            const int ops[2] = {d.src0, d.src1};
+            for (int k = 0; k < 2; ++k) {
+                bool need_copy = false;
+                for (auto& c : copies) need_copy |= (c.first == i && c.second == k);
+                if (need_copy) {
+                    if (ops[k] == 0) return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": concat of the raw input image");
+                    Step s;
+                    s.kind = 5;
+                    s.layer = i;
+                    s.src = ops[k];
+                    s.dst = i + 1;
+                    s.dst_chan_extra = off;
+                    pl.kernel = 5;
+                    const int step_id = (int)n.steps.size();
+                    touch(s.src, step_id); touch(s.dst, step_id);
+                    n.steps.push_back(s);
+                }
+                off += n.tensors[ops[k]].C;
+            }
+        }
+    }
+    // a buffer must stay alive until the last reader of ANY tensor placed in it (handled by touch() on reads);
+    // buffers never read (dead layers) still need first<=last
+    for (auto& b : n.buffers)
+        if (b.last < b.first) { b.first = 0; b.last = (int)n.steps.size(); }
+
+    // ---- arena layout: first-fit over live intervals ----
+    struct Live { int64_t off, bytes; int last; };
+    std::vector<Live> live;
+    std::vector<int> order(n.buffers.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return n.buffers[x].first < n.buffers[y].first; });
+    int64_t top = 0;
+    for (int bi : order) {
+        BufferInfo& b = n.buffers[bi];
+        live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last < b.first; }), live.end());
+        std::sort(live.begin(), live.end(), [](const Live& x, const Live& y) { return x.off < y.off; });
+        const int64_t need = (b.bytes + 1023) & ~1023LL;
+        int64_t off = 0;
+        for (const Live& l : live) {
+            if (off + need <= l.off) break;
+            off = std::max(off, l.off + l.bytes);
+        }
+        b.offset = off;
+        live.push_back({off, need, b.last});
+        top = std::max(top, off + need);
+    }
+    n.arena_bytes = top;
+
+    for (int i = 0; i < L; ++i) {
+        const TensorInfo& t = n.tensors[i + 1];
+        y3_layer_plan& pl = n.plans[i];
+        pl.buffer = t.materialized ? t.buffer : -1;
+        pl.chan_offset = t.chan_off;
+        pl.pix_stride = t.pix_stride;
+        pl.arena_offset = (t.materialized && t.buffer >= 0) ? n.buffers[t.buffer].offset : -1;
+    }
+    return Y3_OK;
+}
+
+__nv_bfloat16* tensor_ptr(const y3_net& n, int t) {
+    const TensorInfo& ti = n.tensors[t];
+    return reinterpret_cast<__nv_bfloat16*>(n.arena + n.buffers[ti.buffer].offset) + ti.chan_off;
+}
+
+int build_maps(y3_net& n) {
+    for (Step& s : n.steps) {
+        if (s.kind != 1) continue;
+        const y3_layer_desc& d = n.layers[s.layer];
+        const TensorInfo& a = n.tensors[s.src];
+        const ConvWeights& w = n.convs[s.conv_idx];
+        const __nv_bfloat16* ap = tensor_ptr(n, s.src);
+        int rc;
+        if (d.ksize == 1 && d.stride == 1) {
+            rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * a.H * a.W, a.C, a.pix_stride, y3::kBlockM,
+                             s.cfg.swz, false);
+        } else {
+            rc = make_map_im2col(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, a.C, a.pix_stride, d.ksize, d.stride,
+                                 s.pad_lo, s.pad_hi, s.cfg.swz);
+        }
+        if (rc) return rc;
+        const uint64_t K = (uint64_t)d.ksize * d.ksize * a.C;
+        rc = make_map_2d(n.ctx->drv, &s.tmB, w.w, w.cout_pad, K, K, s.cfg.block_n, s.cfg.swz, true);
+        if (rc) return rc;
+    }
+    n.maps_built = true;
+    return Y3_OK;
+}
+
+y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
+    y3::ConvArgs a{};
+    a.M = B * s.Ho * s.Wo;
+    a.Ho = s.Ho; a.Wo = s.Wo;
+    a.stride = d.stride;
+    a.lower = -s.pad_lo;
+    a.a_im2col = !(d.ksize == 1 && d.stride == 1);
+    a.ksize = d.ksize;
+    a.kblocks_per_tap = cin / (s.cfg.swz / 2);
+    a.num_k_blocks = d.ksize * d.ksize * a.kblocks_per_tap;
+    a.tiles_m = (a.M + y3::kBlockM - 1) / y3::kBlockM;
+    a.tiles_n = (d.filters + s.cfg.block_n - 1) / s.cfg.block_n;
+    a.cout = d.filters;
+    a.leaky = d.activation;
+    a.upsample = s.fused_up;
+    return a;
+}
+
+unsigned grid_for(long long work, int threads, int sms) {
+    long long blocks = (work + threads - 1) / threads;
+    return (unsigned)std::max(1LL, std::min(blocks, (long long)sms * 16));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* y3_last_error(void) { return g_err.c_str(); }
+int y3_version(void) { return 100; }
+
+int y3_ctx_create(int device, y3_ctx** out) {
+    if (!out) return fail(Y3_ERR_INVALID, "out is null");
+    y3_ctx* c = new y3_ctx();
+    c->device = device;
+    if (device >= 0) {
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) {
+            delete c;
+            return fail(Y3_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        }
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) {
+            delete c;
+            return fail(Y3_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+        }
+        if (prop.major != 10) {
+            delete c;
+            return fail(Y3_ERR_UNSUPPORTED, "this library only runs on sm_100 (B200) GPUs, found sm_" +
+                                                std::to_string(prop.major) + std::to_string(prop.minor));
+        }
+        c->sms = prop.multiProcessorCount;
+        int rc = load_driver(c->drv);
+        if (rc) {
+            delete c;
+            return rc;
+        }
+    }
+    *out = c;
+    return Y3_OK;
+}
+
+void y3_ctx_destroy(y3_ctx* ctx) { delete ctx; }
+int y3_ctx_sm_count(y3_ctx* ctx) { return ctx ? ctx->sms : 0; }
+
+int y3_watchdog_code(y3_ctx* ctx) {
+    if (!ctx || ctx->device < 0) return 0;
+    unsigned v = 0;
+    if (cudaMemcpyFromSymbol(&v, y3::g_watchdog_flag, sizeof(v)) != cudaSuccess) return -1;
+    return (int)v;
+}
+
+int y3_net_create(y3_ctx* ctx, const y3_layer_desc* layers, int n_layers, int H, int W, int max_batch, int nclasses,
+                  y3_net** out) {
+    if (!ctx || !layers || !out || n_layers <= 0) return fail(Y3_ERR_INVALID, "null argument");
+    if (H <= 0 || W <= 0 || max_batch <= 0 || nclasses <= 0) return fail(Y3_ERR_INVALID, "bad H/W/max_batch/nclasses");
+    if (H % 32 != 0 || W % 32 != 0) return fail(Y3_ERR_INVALID, "image size must be a multiple of 32");
+    y3_net* n = new y3_net();
+    n->ctx = ctx;
+    n->H = H; n->W = W; n->max_batch = max_batch; n->nclasses = nclasses;
+    n->layers.assign(layers, layers + n_layers);
+    int rc = plan_net(*n);
+    if (rc) {
+        delete n;
+        return rc;
+    }
+    if (ctx->device >= 0) {
+        cudaError_t e = cudaMalloc(&n->arena, (size_t)std::max<int64_t>(n->arena_bytes, 1024));
+        if (e != cudaSuccess) {
+            delete n;
+            return fail(Y3_ERR_CUDA, std::string("cudaMalloc(arena): ") + cudaGetErrorString(e));
+        }
+        cudaMemset(n->arena, 0, (size_t)n->arena_bytes);
+        for (ConvWeights& w : n->convs) {
+            const size_t K = (size_t)w.k * w.k * w.cin;
+            const size_t wbytes = w.direct ? K * w.cout * 4 : (size_t)w.cout_pad * K * 2;
+            if (cudaMalloc(&w.w, wbytes) != cudaSuccess || cudaMalloc(&w.bias, (size_t)w.cout_pad * 4) != cudaSuccess) {
+                y3_net_destroy(n);
+                return fail(Y3_ERR_CUDA, "cudaMalloc(weights) failed");
+            }
+        }
+        rc = build_maps(*n);
+        if (rc) {
+            y3_net_destroy(n);
+            return rc;
+        }
+    }
+    *out = n;
+    return Y3_OK;
+}
+
+void y3_net_destroy(y3_net* net) {
+    if (!net) return;
+    if (net->arena) cudaFree(net->arena);
+    for (ConvWeights& w : net->convs) {
+        if (w.w) cudaFree(w.w);
+        if (w.bias) cudaFree(w.bias);
+    }
+    delete net;
+}
+
+int y3_net_num_convs(y3_net* net) { return net ? (int)net->convs.size() : 0; }
+int y3_net_num_outputs(y3_net* net) { return net ? (int)net->outputs.size() : 0; }
+int64_t y3_net_arena_bytes(y3_net* net) { return net ? net->arena_bytes : 0; }
+
+int y3_net_get_plan(y3_net* net, y3_layer_plan* plans_host, int n_layers) {
+    if (!net || !plans_host || n_layers != (int)net->plans.size()) return fail(Y3_ERR_INVALID, "bad plan query");
+    std::memcpy(plans_host, net->plans.data(), sizeof(y3_layer_plan) * net->plans.size());
+    return Y3_OK;
+}
+
+int y3_net_output_shape(y3_net* net, int k, int* gh, int* gw, int* ch) {
+    if (!net || k < 0 || k >= (int)net->outputs.size()) return fail(Y3_ERR_INVALID, "bad output index");
+    const TensorInfo& t = net->tensors[net->outputs[k]];
+    if (gh) *gh = t.H;
+    if (gw) *gw = t.W;
+    if (ch) *ch = t.C;
+    return Y3_OK;
+}
+
+int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float* bias, const float* gamma,
+                     const float* beta, const float* mean, const float* var, float eps) {
+    if (!net || !kernel) return fail(Y3_ERR_INVALID, "null argument");
+    if (conv_idx < 0 || conv_idx >= (int)net->convs.size()) return fail(Y3_ERR_INVALID, "conv index out of range");
+    if (net->ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context has no weights");
+    ConvWeights& w = net->convs[conv_idx];
+    const y3_layer_desc& d = net->layers[net->conv_layer[conv_idx]];
+    const bool bn = d.batch_normalize != 0;
+    if (bn && !(gamma && beta && mean && var)) return fail(Y3_ERR_INVALID, "conv has batch_normalize: BN vectors required");
+    if (!bn && !bias) return fail(Y3_ERR_INVALID, "conv without batch_normalize: bias required");
+    const int k = w.k, cin = w.cin, cout = w.cout;
+    const size_t K = (size_t)k * k * cin;
+    std::vector<float> scale(cout, 1.0f), shift(w.cout_pad, 0.0f);
+    for (int o = 0; o < cout; ++o) {
+        if (bn) {
+            // Keras inference BN: gamma * (x - mean) / sqrt(var + eps) + beta   (eps = 1e-3 by default)
+            const double sc = (double)gamma[o] / std::sqrt((double)var[o] + (double)eps);
+            scale[o] = (float)sc;
+            shift[o] = (float)((double)beta[o] - (double)mean[o] * sc);
+        } else {
+            shift[o] = bias[o];
+        }
+    }
+    if (w.direct) {
+        std::vector<float> packed(K * cout);
+        for (size_t kk = 0; kk < K; ++kk)
+            for (int o = 0; o < cout; ++o) packed[kk * cout + o] = kernel[kk * cout + o] * scale[o];   // HWIO is already [K][Cout]
+        Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * K, __float2bfloat16(0.0f));
+        for (size_t kk = 0; kk < K; ++kk)
+            for (int o = 0; o < cout; ++o) packed[(size_t)o * K + kk] = __float2bfloat16(kernel[kk * cout + o] * scale[o]);
+        Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    }
+    Y3_CUDA(cudaMemcpy(w.bias, shift.data(), shift.size() * 4, cudaMemcpyHostToDevice));
+    w.loaded = true;
+    return Y3_OK;
+}
+
+int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream) {
+    if (!net || !x || !outs) return fail(Y3_ERR_INVALID, "null argument");
+    if (net->ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (B <= 0 || B > net->max_batch) return fail(Y3_ERR_INVALID, "batch " + std::to_string(B) + " exceeds max_batch");
+    if (n_outs != (int)net->outputs.size()) return fail(Y3_ERR_INVALID, "wrong number of outputs");
+    for (const ConvWeights& w : net->convs)
+        if (!w.loaded) return fail(Y3_ERR_STATE, "weights not loaded for every conv");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int sms = net->ctx->sms;
+    for (const Step& s : net->steps) {
+        const y3_layer_desc& d = net->layers[s.layer];
+        if (s.kind == 1) {
+            const TensorInfo& a = net->tensors[s.src];
+            const TensorInfo& o = net->tensors[s.dst];
+            const ConvWeights& w = net->convs[s.conv_idx];
+            y3::ConvArgs ca = conv_args(s, d, a.C, B);
+            ca.bias = w.bias;
+            if (s.src2 >= 0) {
+                ca.residual = tensor_ptr(*net, s.src2);
+                ca.res_stride = net->tensors[s.src2].pix_stride;
+            }
+            if (o.fp32_output) {
+                ca.out = outs[o.out_index];
+                ca.out_stride = o.C;
+                ca.out_fp32 = 1;
+            } else {
+                ca.out = tensor_ptr(*net, s.dst);
+                ca.out_stride = o.pix_stride;
+            }
+            Y3_CUDA(launch_conv(s.cfg, s.tmA, s.tmB, ca, sms, st));
+        } else if (s.kind == 2) {
+            const TensorInfo& a = net->tensors[s.src];
+            const TensorInfo& o = net->tensors[s.dst];
+            const ConvWeights& w = net->convs[s.conv_idx];
+            y3::ConvFirstArgs fa{};
+            fa.x = x;
+            fa.w = reinterpret_cast<const float*>(w.w);
+            fa.bias = w.bias;
+            fa.out = tensor_ptr(*net, s.dst);
+            fa.out_stride = o.pix_stride;
+            fa.B = B; fa.H = a.H; fa.W = a.W; fa.Ho = s.Ho; fa.Wo = s.Wo;
+            fa.ksize = d.ksize; fa.stride = d.stride; fa.pad_lo = s.pad_lo;
+            fa.leaky = d.activation;
+            const size_t smem = ((size_t)d.ksize * d.ksize * 3 * d.filters + d.filters) * 4;
+            const unsigned grid = grid_for((long long)B * s.Ho * s.Wo, 128, sms);
+            if (d.filters == 32) y3::conv_first_kernel<3, 32><<<grid, 128, smem, st>>>(fa);
+            else y3::conv_first_kernel<3, 16><<<grid, 128, smem, st>>>(fa);
+            Y3_CUDA(cudaGetLastError());
+        } else {
+            const TensorInfo& a = net->tensors[s.src];
+            const TensorInfo& o = net->tensors[s.dst];
+            y3::ViewArgs v{};
+            v.a = tensor_ptr(*net, s.src);
+            v.a_stride = a.pix_stride;
+            v.out = tensor_ptr(*net, s.dst) + s.dst_chan_extra;
+            v.out_stride = o.pix_stride;
+            v.C = a.C;
+            v.Ho = o.H; v.Wo = o.W;
+            v.npix = (long long)B * o.H * o.W;
+            const unsigned grid = grid_for(v.npix * (v.C / 8), 256, sms);
+            if (s.kind == 3) {
+                v.b = tensor_ptr(*net, s.src2);
+                v.b_stride = net->tensors[s.src2].pix_stride;
+                y3::add_views_kernel<<<grid, 256, 0, st>>>(v);
+            } else if (s.kind == 4) {
+                y3::upsample2_view_kernel<<<grid, 256, 0, st>>>(v);
+            } else {
+                y3::copy_view_kernel<<<grid, 256, 0, st>>>(v);
+            }
+            Y3_CUDA(cudaGetLastError());
+        }
+    }
+    return Y3_OK;
+}
+
+int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, int n_scales,
+              const float* anchors_host, int B, int nclasses, float* bboxes, float* conf, float* probs, float* scores,
+              int64_t* class_idx, void* stream) {
+    if (!ctx || !grids || !gh || !gw || !anchors_host || !bboxes || !conf || !probs) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (n_scales < 1 || n_scales > 3) return fail(Y3_ERR_UNSUPPORTED, "1..3 scales supported");
+    if (B <= 0 || nclasses <= 0) return fail(Y3_ERR_INVALID, "bad B / nclasses");
+    if ((scores == nullptr) != (class_idx == nullptr)) return fail(Y3_ERR_INVALID, "scores and class_idx go together");
+    y3::DecodeArgs a{};
+    int off = 0, chunks = 0;
+    for (int s = 0; s < 3; ++s) {
+        a.chunk_begin[s] = chunks;
+        if (s < n_scales) {
+            if (!grids[s] || gh[s] <= 0 || gw[s] <= 0) return fail(Y3_ERR_INVALID, "bad grid");
+            if ((reinterpret_cast<uintptr_t>(grids[s]) & 15) != 0) return fail(Y3_ERR_INVALID, "grid pointers must be 16-byte aligned");
+            a.in[s] = grids[s];
+            a.gh[s] = gh[s]; a.gw[s] = gw[s];
+            a.rec_off[s] = off;
+            const long long recs = (long long)B * gh[s] * gw[s] * 3;
+            off += gh[s] * gw[s] * 3;
+            chunks += (int)((recs + y3::kDecodeRecs - 1) / y3::kDecodeRecs);
+        } else {
+            a.in[s] = nullptr; a.gh[s] = 1; a.gw[s] = 1; a.rec_off[s] = off;
+        }
+    }
+    a.chunk_begin[3] = chunks;
+    // scales that are absent must never be selected by the block->scale search
+    for (int s = n_scales; s < 3; ++s) a.chunk_begin[s] = 0x7fffffff;
+    std::memcpy(a.anchors, anchors_host, sizeof(float) * 6 * n_scales);
+    a.B = B; a.C = nclasses; a.N = off;
+    if ((long long)B * off > 0x7fffffffLL) return fail(Y3_ERR_UNSUPPORTED, "B*N exceeds int32 record indexing");
+    a.bboxes = bboxes; a.conf = conf; a.probs = probs; a.scores = scores;
+    a.cls = reinterpret_cast<long long*>(class_idx);
+    const int F = 5 + nclasses;
+    const size_t smem = (size_t)((y3::kDecodeRecs * F + 3) & ~3) * 4 + y3::kDecodeRecs * 4;
+    if (smem > 200 * 1024) return fail(Y3_ERR_UNSUPPORTED, "nclasses too large for the decode tile");
+    static bool configured = false;
+    if (!configured) {
+        Y3_CUDA(cudaFuncSetAttribute(y3::decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    y3::decode_kernel<<<chunks, y3::kDecodeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    Y3_CUDA(cudaGetLastError());
+    return Y3_OK;
+}
+
+int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, int N, int nclasses, float* scores,
+                    int64_t* class_idx, void* stream) {
+    if (!ctx || !probs || !conf || !scores || !class_idx) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (B <= 0 || N <= 0 || nclasses <= 0) return fail(Y3_ERR_INVALID, "bad shape");
+    const long long nrec = (long long)B * N;
+    const unsigned grid = grid_for(nrec * 32, 256, ctx->sms);
+    y3::class_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        probs, conf, nrec, nclasses, scores, reinterpret_cast<long long*>(class_idx));
+    Y3_CUDA(cudaGetLastError());
+    return Y3_OK;
+}
+
+int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, int max_boxes, float iou_thr,
+           float score_thr, int32_t* selected, int32_t* num_valid, int32_t* status, void* stream) {
+    if (!ctx || !bboxes || !scores || !selected || !num_valid || !status) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (B <= 0 || N <= 0 || max_boxes <= 0) return fail(Y3_ERR_INVALID, "bad shape");
+    if (N > y3::kNmsMaxN) return fail(Y3_ERR_UNSUPPORTED, "N > 32768 boxes per image is not supported");
+    if ((reinterpret_cast<uintptr_t>(bboxes) & 15) != 0) return fail(Y3_ERR_INVALID, "bboxes must be 16-byte aligned");
+    y3::NmsArgs a{};
+    a.boxes = bboxes; a.scores = scores;
+    a.B = B; a.N = N;
+    int np = 32;
+    while (np < N) np <<= 1;
+    a.NP = np;
+    a.max_boxes = max_boxes;
+    a.iou_thr = iou_thr; a.score_thr = score_thr;
+    a.selected = selected; a.num_valid = num_valid; a.status = status;
+    const size_t smem = (size_t)np * 6 + (size_t)(y3::kNmsKeptCap + y3::kNmsChunk) * 16 + (size_t)y3::kNmsChunk * 8 * 4 + 32;
+    static bool configured = false;
+    if (!configured) {
+        Y3_CUDA(cudaFuncSetAttribute(y3::nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    y3::nms_kernel<<<B, y3::kNmsThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    Y3_CUDA(cudaGetLastError());
+    return Y3_OK;
+}
+
+int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_idx, const float* scores,
+                         const int32_t* selected, const int32_t* num_valid, int B, int N, int max_boxes,
+                         float* out_boxes, int64_t* out_classes, float* out_scores, void* stream) {
+    if (!ctx || !bboxes || !class_idx || !scores || !selected || !num_valid || !out_boxes || !out_classes || !out_scores)
+        return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    const int total = B * max_boxes;
+    y3::gather_detections_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        bboxes, reinterpret_cast<const long long*>(class_idx), scores, selected, num_valid, B, N, max_boxes, out_boxes,
+        reinterpret_cast<long long*>(out_classes), out_scores);
+    Y3_CUDA(cudaGetLastError());
+    return Y3_OK;
+}
+
+int y3_conv_block_n(int cin, int cout) {
+    ConvCfg c;
+    if (!pick_cfg(cin, cout, c)) return 0;
+    return c.block_n;
+}
+
+int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, const void* w_packed,
+                   const float* bias, int ksize, int stride, int Cout, int leaky, const void* residual,
+                   int64_t res_stride, void* out, int64_t out_stride, int out_fp32, int upsample, void* stream) {
+    if (!ctx || !x || !w_packed || !bias || !out) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    ConvCfg cfg;
+    if (!pick_cfg(Cin, Cout, cfg)) return fail(Y3_ERR_UNSUPPORTED, "Cin must be a multiple of 32");
+    if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return fail(Y3_ERR_UNSUPPORTED, "k in {1,3}, stride in {1,2}");
+    if (!out_fp32 && Cout % 32 != 0) return fail(Y3_ERR_UNSUPPORTED, "bf16 conv outputs need Cout % 32 == 0");
+    Step s;
+    s.cfg = cfg;
+    s.fused_up = upsample;
+    conv_geometry(H, W, ksize, stride, stride == 1 ? 1 : 0, s.Ho, s.Wo, s.pad_lo, s.pad_hi);
+    y3_layer_desc d{};
+    d.ksize = ksize; d.stride = stride; d.filters = Cout; d.activation = leaky;
+    int rc;
+    if (ksize == 1 && stride == 1)
+        rc = make_map_2d(ctx->drv, &s.tmA, x, (uint64_t)B * H * W, Cin, x_stride, y3::kBlockM, cfg.swz, false);
+    else
+        rc = make_map_im2col(ctx->drv, &s.tmA, x, B, H, W, Cin, x_stride, ksize, stride, s.pad_lo, s.pad_hi, cfg.swz);
+    if (rc) return rc;
+    const int cout_pad = ((Cout + cfg.block_n - 1) / cfg.block_n) * cfg.block_n;
+    const uint64_t K = (uint64_t)ksize * ksize * Cin;
+    rc = make_map_2d(ctx->drv, &s.tmB, w_packed, cout_pad, K, K, cfg.block_n, cfg.swz, true);
+    if (rc) return rc;
+    y3::ConvArgs ca = conv_args(s, d, Cin, B);
+    ca.bias = bias;
+    ca.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    ca.res_stride = res_stride;
+    ca.out = out;
+    ca.out_stride = out_stride;
+    ca.out_fp32 = out_fp32;
+    Y3_CUDA(launch_conv(cfg, s.tmA, s.tmB, ca, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
+    return Y3_OK;
+}
+
+int y3_dbg_tma_tile(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, int ksize, int stride,
+                    int swizzle, int tap_r, int tap_s, int c0, int m0, void* out_bytes, void* stream) {
+    if (!ctx || !x || !out_bytes) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (swizzle != 128 && swizzle != 64) return fail(Y3_ERR_INVALID, "swizzle must be 64 or 128");
+    int Ho, Wo, pl, ph;
+    conv_geometry(H, W, ksize, stride, stride == 1 ? 1 : 0, Ho, Wo, pl, ph);
+    CUtensorMap tm;
+    const int im2col = !(ksize == 1 && stride == 1);
+    int rc;
+    if (!im2col) rc = make_map_2d(ctx->drv, &tm, x, (uint64_t)B * H * W, Cin, x_stride, y3::kBlockM, swizzle, false);
+    else rc = make_map_im2col(ctx->drv, &tm, x, B, H, W, Cin, x_stride, ksize, stride, pl, ph, swizzle);
+    if (rc) return rc;
+    const int hw = Ho * Wo;
+    const int cn = m0 / hw, rem = m0 % hw, po = rem / Wo, qo = rem % Wo;
+    const size_t smem = 1024 + (size_t)y3::kBlockM * swizzle + 16;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (swizzle == 128)
+        y3::tma_tile_dump_kernel<128><<<1, 128, smem, st>>>(tm, im2col, c0, qo * stride - pl, po * stride - pl, cn, tap_s,
+                                                            tap_r, m0, reinterpret_cast<uint8_t*>(out_bytes));
+    else
+        y3::tma_tile_dump_kernel<64><<<1, 128, smem, st>>>(tm, im2col, c0, qo * stride - pl, po * stride - pl, cn, tap_s,
+                                                           tap_r, m0, reinterpret_cast<uint8_t*>(out_bytes));
+    Y3_CUDA(cudaGetLastError());
+    return Y3_OK;
+}
+
+}  // extern "C"
