@@ -1,0 +1,195 @@
+"""Host logic (no GPU): yaml -> flat graph, reference error behaviour, planner decisions through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+REF = "/root/reference"
+has_ref = os.path.isdir(os.path.join(REF, "config"))
+
+
+def _strip(g):
+    return [(l.op, l.src0, l.src1, l.ksize, l.stride, l.filters, l.pad, l.batch_normalize, l.activation) for l in g.layers]
+
+
+def test_builtin_yolov3_structure():
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import _lib
+    m = y3.ParseModel.builtin_yolov3(80)
+    g = m.graph
+    assert len(m.conv_shapes) == 75
+    assert sum(k * k * ci * co for k, ci, co, _ in m.conv_shapes) == 61_895_776
+    assert sum(1 for l in g.layers if l.op == _lib.OP_SHORTCUT) == 23
+    assert sum(1 for l in g.layers if l.op == _lib.OP_CONCAT) == 2
+    assert sum(1 for l in g.layers if l.op == _lib.OP_UPSAMPLE) == 2
+    assert len(g.outputs) == 3
+    # only the three head 1x1 convs carry a bias; they have 3*(5+C) filters
+    nobn = [(k, co) for k, ci, co, bn in m.conv_shapes if not bn]
+    assert nobn == [(1, 255)] * 3
+    # concat order is [upsampled, skip] (parse_model.py:116-126): 256+512 and 128+256
+    cats = [l for l in g.layers if l.op == _lib.OP_CONCAT]
+    assert [(g.channels(c.src0), g.channels(c.src1)) for c in cats] == [(256, 512), (128, 256)]
+    # algorithmic FLOPs at 416 (65.864 GFLOP)
+    p = m.plan(416, 416, 1)
+    flops = 0
+    ci = 0
+    for l, pl in zip(g.layers, p["layers"]):
+        if l.op == _lib.OP_CONV:
+            k, cin, cout, _ = m.conv_shapes[ci]
+            ci += 1
+            flops += 2 * pl["H"] * pl["W"] * cout * k * k * cin
+    assert abs(flops / 1e9 - 65.864) < 0.01
+
+
+@pytest.mark.parametrize("nclasses,filters", [(80, 255), (38, 129), (37, 126), (3, 24)])
+def test_head_filters_expression(nclasses, filters):
+    import yolo_v3_tf2_b200 as y3
+    m = y3.ParseModel.builtin_yolov3(nclasses)
+    assert [co for k, ci, co, bn in m.conv_shapes if not bn] == [filters] * 3
+
+
+@pytest.mark.skipif(not has_ref, reason="reference checkout not present")
+def test_reference_yamls_load_unchanged_and_match_builtin(monkeypatch):
+    """The reference's own files are accepted as-is: current schema, legacy monolithic schema and the built-in
+    description all flatten to the same graph."""
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import graph
+    builtin = y3.ParseModel.builtin_yolov3(80).graph
+    g_cur = graph.load_model_config(os.path.join(REF, "config/models/yolov3/model.yaml"), 80)
+    g_old = graph.load_model_config(os.path.join(REF, "config/yolov3_model.yaml"), 80)
+    assert _strip(g_cur) == _strip(builtin)
+    assert _strip(g_old) == _strip(builtin)
+    assert g_cur.outputs == g_old.outputs == builtin.outputs
+    # same call sequence as inference.py:87-96, from the reference repo root as CWD
+    monkeypatch.chdir(REF)
+    with open("config/models/yolov3/model.yaml") as f:
+        cfg = yaml.safe_load(f)
+    model = y3.ParseModel().build_model(None, cfg["sub_models_configs"], cfg["output_stage"], nclasses=80)
+    assert _strip(model.graph) == _strip(builtin)
+    m2 = y3.ParseModel().create_model(80, "config/yolov3_model.yaml")
+    assert _strip(m2.graph) == _strip(builtin)
+    # the empty decode-layer cfg is accepted (nothing to parse)
+    assert os.path.getsize("config/yolov3_decode_layer.cfg") == 0
+
+
+@pytest.mark.skipif(not has_ref, reason="reference checkout not present")
+def test_reference_anchors_and_names():
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    from yolo_v3_tf2_b200.core.utils import count_file_lines
+    a = y3.get_anchors(os.path.join(REF, "datasets/coco2012/anchors.txt"))
+    assert a.shape == (3, 3, 2)
+    np.testing.assert_allclose(a.astype(np.float32), configs.coco_anchors(), rtol=0, atol=1e-7)
+    assert count_file_lines(os.path.join(REF, "datasets/coco2012/coco.names")) == 80
+    assert count_file_lines(os.path.join(REF, "datasets/pets_breed.names")) == 38   # SURVEY.md header note 3
+
+
+def _mini(layers_by_file, subs, nclasses=2, output_stage="head"):
+    import yolo_v3_tf2_b200 as y3
+    return y3.ParseModel().build_model(None, subs, output_stage, nclasses=nclasses, layer_lists=layers_by_file)
+
+
+def _conv(f, size=1, stride=1, bn=True, act="leaky"):
+    d = {"type": "convolutional", "filters": f, "size": size, "stride": stride, "pad": 1, "activation": act}
+    if bn:
+        d["batch_normalize"] = 1
+    return d
+
+
+def test_reference_error_behaviour():
+    """Same exception types as the reference for the same config mistakes (parse_model.py:48,140,157,227,277)."""
+    subs = [{"name": "head", "layers_config_file": "a", "outputs_layers": [-1]}]
+    with pytest.raises(ValueError, match="not recognized as layer_conf type"):
+        _mini({"a": [{"type": "dropout"}]}, subs)
+    with pytest.raises(AssertionError, match="Invalid activation"):
+        _mini({"a": [_conv(32, act="relu")]}, subs)
+    with pytest.raises(AssertionError, match="Invalid activation"):
+        _mini({"a": [_conv(32), _conv(32), _conv(32), {"type": "shortcut", "from": -3, "activation": "leaky"}]}, subs)
+    with pytest.raises(ValueError, match="Invalid number of layers"):
+        _mini({"a": [_conv(32), _conv(32), _conv(32), {"type": "route", "source": {"layers": [0, 1, 2]}}]}, subs)
+    with pytest.raises(IndexError):
+        _mini({"a": [_conv(32)]}, [{"name": "head", "inputs": {"source": [{"name": "nope"}]}, "layers_config_file": "a",
+                                    "outputs_layers": [-1]}])
+    with pytest.raises(KeyError):
+        _mini({"a": [{"type": "convolutional", "filters": 8, "activation": "linear"}]}, subs)
+
+
+def test_planner_through_c_abi():
+    """Fusion + arena decisions for the real network, on a planning-only context (no GPU needed)."""
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import _lib
+    m = y3.ParseModel.builtin_yolov3(80)
+    g = m.graph
+    p = m.plan(416, 416, 8)
+    L = p["layers"]
+    assert p["num_convs"] == 75
+    kinds = [l["kernel"] for l in L]
+    assert kinds.count(2) == 1 and kinds.count(1) == 74          # stem on CUDA cores, 74 tcgen05 convs
+    assert kinds.count(3) == kinds.count(4) == kinds.count(5) == 0   # every add / upsample / concat is fused
+    assert sum(1 for l in L if l["fused_add"] >= 0) == 23
+    assert sum(1 for l in L if l["fused_upsample"]) == 2
+    # concat operands live inside the concat buffer: same buffer id, channel offsets 0 and Ca, pixel stride Ca+Cb
+    for i, l in enumerate(g.layers):
+        if l.op == _lib.OP_CONCAT:
+            cat, a, b = L[i], L[l.src0 - 1], L[l.src1 - 1]
+            assert a["buffer"] == b["buffer"] == cat["buffer"]
+            assert (a["chan_offset"], b["chan_offset"]) == (0, a["C"])
+            assert a["pix_stride"] == b["pix_stride"] == cat["C"] == a["C"] + b["C"]
+    # live buffers never overlap in the arena: rebuild liveness from the graph
+    assert 0 < p["arena_bytes"] < 8 * 416 * 416 * 64 * 2 * 4
+    # shapes follow H/32, H/16, H/8 for any multiple of 32 (the reference's Reshape breaks at 608; ours must not)
+    p608 = m.plan(608, 608, 1)
+    outs = [p608["layers"][t - 1] for t in g.outputs]
+    assert [(o["H"], o["W"], o["C"]) for o in outs] == [(19, 19, 255), (38, 38, 255), (76, 76, 255)]
+    with pytest.raises(ValueError):
+        m.plan(400, 416, 1)
+
+
+def test_planner_arena_no_live_overlap():
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import _lib
+    m = y3.ParseModel.builtin_yolov3(80)
+    g = m.graph
+    B = 4
+    p = m.plan(256, 256, B)
+    L = p["layers"]
+    # materialised tensor -> (buffer, first write layer, last read layer)
+    bufs = {}
+    for i, (l, pl) in enumerate(zip(g.layers, L)):
+        if pl["buffer"] < 0:
+            continue
+        size = None
+        b = bufs.setdefault(pl["buffer"], {"off": pl["arena_offset"], "first": i, "last": i, "bytes": 0})
+        b["first"] = min(b["first"], i)
+        b["bytes"] = max(b["bytes"], B * pl["H"] * pl["W"] * pl["pix_stride"] * 2)
+        for j, l2 in enumerate(g.layers):
+            if l2.src0 == i + 1 or l2.src1 == i + 1:
+                b["last"] = max(b["last"], j)
+    items = list(bufs.values())
+    for x in range(len(items)):
+        for y in range(x + 1, len(items)):
+            a, b = items[x], items[y]
+            live_overlap = not (a["last"] < b["first"] or b["last"] < a["first"])
+            mem_overlap = not (a["off"] + a["bytes"] <= b["off"] or b["off"] + b["bytes"] <= a["off"])
+            assert not (live_overlap and mem_overlap)
+
+
+def test_unfusable_graphs_fall_back_to_standalone_kernels_or_reject():
+    """A shortcut whose conv output is also used elsewhere cannot be fused -> planner schedules an add kernel;
+    maxpool (yolov3-tiny) is rejected loudly -- there is no CPU fallback."""
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import _lib
+    layers = [_conv(32, 3), _conv(64, 3, 2), _conv(32, 1), _conv(64, 3),
+              {"type": "shortcut", "from": -3, "activation": "linear"},
+              {"type": "route", "source": {"layers": [-1, 3]}},      # conv3 output used twice -> add not fusable
+              _conv("3*(2+2+1+nclasses)", 1, bn=False, act="linear"), {"type": "yolo", "grid_size": 13}]
+    m = _mini({"a": layers}, [{"name": "head", "layers_config_file": "a", "outputs_layers": [-1]}])
+    p = m.plan(64, 64, 1)
+    kinds = [l["kernel"] for l in p["layers"]]
+    assert 3 in kinds                       # stand-alone add
+    tiny = [_conv(32, 3), {"type": "maxpool", "size_xy": [2, 2], "stride_xy": [2, 2], "padding": "same"},
+            _conv("3*(2+2+1+nclasses)", 1, bn=False, act="linear"), {"type": "yolo", "grid_size": 13}]
+    m2 = _mini({"a": tiny}, [{"name": "head", "layers_config_file": "a", "outputs_layers": [-1]}])
+    with pytest.raises(_lib.Y3Unsupported, match="maxpool"):
+        m2.plan(64, 64, 1)

@@ -1,0 +1,137 @@
+"""The oracle against its golden vectors and against itself (two NMS formulations + the C port; fp32 vs fp64 convs)."""
+import os
+
+import numpy as np
+import pytest
+
+from y3_test_util import cluster_boxes, synth_grids
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_decode_golden():
+    from oracle import decode_oracle, c_oracle
+    z = np.load(os.path.join(GOLD, "decode_small.npz"))
+    grids = [z["g0"], z["g1"], z["g2"]]
+    b, c, p = decode_oracle.yolo_decode(grids, z["anchors"], 6)
+    assert np.array_equal(b, z["bboxes"]) and np.array_equal(c, z["conf"]) and np.array_equal(p, z["probs"])
+    cls, sc = decode_oracle.class_reduce(c, p)
+    assert np.array_equal(cls, z["cls"]) and np.array_equal(sc, z["scores"])
+    # C port: same formulas, libm expf instead of numpy's -> a couple of ulp
+    cb, cc, cp = c_oracle.decode(grids, z["anchors"], 6)
+    np.testing.assert_allclose(cb, b, rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(cp, p, rtol=2e-6, atol=2e-6)
+    ccls, csc = c_oracle.class_reduce(c, p)
+    assert np.array_equal(ccls, cls) and np.array_equal(csc, sc)
+
+
+def test_decode_layout_properties():
+    """flat index n = off_s + (i*g + j)*3 + a ; box centre inside its cell ; scales concatenated 13 -> 26 -> 52."""
+    from oracle import decode_oracle
+    from yolo_v3_tf2_b200 import configs
+    grids = [np.zeros((1, g, g, 3, 7), np.float32) for g in (13, 26, 52)]
+    b, c, p = decode_oracle.yolo_decode(grids, configs.coco_anchors(), 2)
+    assert b.shape == (1, 10647, 4) and c.shape == (1, 10647, 1) and p.shape == (1, 10647, 2)
+    assert np.all(c == 0.5) and np.all(p == 0.5)
+    n = 507 + (5 * 26 + 7) * 3 + 1          # scale 1, row 5, col 7, anchor 1
+    cx, cy = (b[0, n, 0] + b[0, n, 2]) / 2, (b[0, n, 1] + b[0, n, 3]) / 2
+    assert abs(cx - 7.5 / 26) < 1e-6 and abs(cy - 5.5 / 26) < 1e-6
+    w = b[0, n, 2] - b[0, n, 0]
+    assert abs(w - configs.coco_anchors()[1, 1, 0]) < 1e-6
+
+
+def test_nms_golden_all_formulations():
+    from oracle import nms_oracle, c_oracle
+    z = np.load(os.path.join(GOLD, "nms_cases.npz"))
+    names = sorted({k.rsplit("_", 1)[0] for k in z.files if k.endswith("_boxes")})
+    assert len(names) >= 6
+    for n in names:
+        b, s = z[f"{n}_boxes"], z[f"{n}_scores"]
+        mx, iou, sthr = z[f"{n}_params"]
+        for f in (nms_oracle.nms_padded_tiled, nms_oracle.nms_padded_greedy):
+            sel, nv = f(b, s, int(mx), float(iou), float(sthr))
+            assert np.array_equal(sel, z[f"{n}_sel"]) and nv == z[f"{n}_nv"], n
+        sel, nv = c_oracle.nms(b[None], s[None], int(mx), float(iou), float(sthr))
+        assert np.array_equal(sel[0], z[f"{n}_sel"]) and nv[0] == z[f"{n}_nv"], n
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_nms_formulations_agree_random(seed):
+    from oracle import nms_oracle, c_oracle
+    rng = np.random.default_rng(seed)
+    b, s = cluster_boxes(int(rng.integers(600, 2500)), int(rng.integers(3, 60)), seed + 100)
+    s[:: int(rng.integers(3, 9))] = s[1]
+    for iou in (0.3, 0.5, 0.7):
+        for sthr in (0.004, 0.5):
+            t = nms_oracle.nms_padded_tiled(b, s, 100, iou, sthr)
+            g = nms_oracle.nms_padded_greedy(b, s, 100, iou, sthr)
+            c = c_oracle.nms(b[None], s[None], 100, iou, sthr)
+            assert np.array_equal(t[0], g[0]) and t[1] == g[1]
+            assert np.array_equal(c[0][0], t[0]) and c[1][0] == t[1]
+
+
+def test_nms_semantics_by_hand():
+    """Tiny hand-checkable cases for each rule in SURVEY.md row a14."""
+    from oracle import nms_oracle
+    b = np.array([[0, 0, .4, .4], [0, 0, .4, .41], [.5, .5, .9, .9], [0, 0, .4, .4]], np.float32)
+    s = np.array([.9, .8, .3, .9], np.float32)
+    sel, nv = nms_oracle.nms_padded_greedy(b, s, 5, 0.5, 0.1)
+    assert nv == 2 and sel.tolist() == [0, 2, 0, 0, 0]        # tie 0/3 -> lower index first; 1 and 3 suppressed
+    sel, nv = nms_oracle.nms_padded_greedy(b, s, 5, 0.5, 0.3)  # strict '>' score filter drops score == thr
+    assert nv == 1 and sel.tolist() == [0, 0, 0, 0, 0]
+    sel, nv = nms_oracle.nms_padded_greedy(b, s, 1, 0.5, 0.1)  # max_output_size caps
+    assert nv == 1
+    # all-coords <= 0 box survives (it suppresses) but is never selected
+    b2 = np.array([[-.5, -.5, -.1, -.1], [-.5, -.5, -.1, -.1001], [.1, .1, .2, .2]], np.float32)
+    sel, nv = nms_oracle.nms_padded_greedy(b2, np.array([.9, .8, .7], np.float32), 3, 0.5, 0.1)
+    assert nv == 1 and sel.tolist() == [2, 0, 0]
+    t = nms_oracle.nms_padded_tiled(b2, np.array([.9, .8, .7], np.float32), 3, 0.5, 0.1)
+    assert t[1] == 1 and t[0].tolist() == [2, 0, 0]
+
+
+@pytest.mark.parametrize("init", ["variance", "keras"])
+def test_net_golden(init):
+    import yolo_v3_tf2_b200 as y3
+    from oracle import net_oracle
+    z = np.load(os.path.join(GOLD, f"net64_{init}.npz"))
+    m = y3.ParseModel.builtin_yolov3(80).init_weights(init, seed=int(z["seed"]))
+    assert abs(m._params[0].kernel.astype(np.float64).sum() - float(z["w0_sum"])) < 1e-9      # generator is deterministic
+    assert abs(m._params[74].kernel.astype(np.float64).sum() - float(z["w74_sum"])) < 1e-9
+    outs = net_oracle.forward(m.graph.layers, m.graph.outputs, m._params, z["x"])
+    for o, k in zip(outs, ("g0", "g1", "g2")):
+        # conv summation order may differ between CPU kernels/thread counts: compare with a float32 tolerance
+        np.testing.assert_allclose(o, z[k], rtol=2e-4, atol=2e-4)
+
+
+def test_net_oracle_fp32_vs_fp64():
+    """Bounds the oracle's own float32 noise, so the bf16 tolerance of the GPU tests is stated against truth."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from oracle import net_oracle
+    m = y3.ParseModel.builtin_yolov3(80).init_weights("variance", seed=3)
+    x = np.random.default_rng(1).random((1, 64, 64, 3), dtype=np.float32)
+    a = net_oracle.forward(m.graph.layers, m.graph.outputs, m._params, x)
+    b = net_oracle.forward(m.graph.layers, m.graph.outputs, m._params, x, dtype=torch.float64)
+    for u, v in zip(a, b):
+        assert np.linalg.norm(u - v) / np.linalg.norm(v) < 1e-5
+
+
+def test_net_oracle_conv_semantics():
+    """Asymmetric stride-2 padding (top/left only), concat order and nearest upsample, by hand."""
+    from oracle import net_oracle
+    x = np.zeros((1, 4, 4, 1), np.float32)
+    x[0, 0, 0, 0] = 1.0
+    k = np.zeros((3, 3, 1, 1), np.float32)
+    k[0, 0, 0, 0] = 5.0     # top-left tap sees the padded zero row/col for output (0,0)
+    k[1, 1, 0, 0] = 1.0     # centre tap: output(0,0) reads input(0,0) when pad_top=pad_left=1
+    y = net_oracle.conv_layer(x, k, np.zeros(1, np.float32), 3, 2, False)
+    assert y.shape == (1, 2, 2, 1) and y[0, 0, 0, 0] == 1.0 and y.sum() == 1.0
+    k2 = np.zeros((3, 3, 1, 1), np.float32)
+    k2[2, 2, 0, 0] = 1.0    # bottom-right tap: output(1,1) reads input(3,3) -> no bottom/right padding needed
+    x2 = np.zeros((1, 4, 4, 1), np.float32)
+    x2[0, 3, 3, 0] = 2.0
+    y2 = net_oracle.conv_layer(x2, k2, np.zeros(1, np.float32), 3, 2, False)
+    assert y2[0, 1, 1, 0] == 2.0
+    up = net_oracle.conv_layer(np.arange(4, dtype=np.float32).reshape(1, 2, 2, 1), np.ones((1, 1, 1, 1), np.float32),
+                               np.zeros(1, np.float32), 1, 1, False, upsample=True)
+    assert up[0, :, :, 0].tolist() == [[0, 0, 1, 1], [0, 0, 1, 1], [2, 2, 3, 3], [2, 2, 3, 3]]

@@ -1,0 +1,209 @@
+"""Drop-in for reference core/parse_model.py: ``ParseModel().build_model(...)`` returns a callable model whose forward
+pass runs the tcgen05 conv kernels of liby3b200.so instead of Keras layers."""
+import ctypes as C
+
+import numpy as np
+import torch
+import yaml
+
+from .. import _lib
+from .. import graph as graph_mod
+from .. import weights as weights_mod
+
+
+class Y3Model:
+    """What ``ParseModel.build_model`` returns: callable like the Keras model (``model(x)`` -> list of 3 grids
+    ``[B, g, g, 3, 5+nclasses]`` float32 in head0/head1/head2 order, reference parse_model.py:310-313) with the weight
+    accessors the reference uses (``load_weights``, ``set_weights``/``get_weights`` in Keras variable order,
+    ``predict``)."""
+
+    def __init__(self, g: graph_mod.Graph, name="yolo"):
+        self.name = name
+        self.graph = g
+        self.nclasses = g.nclasses
+        self.conv_shapes = g.conv_shapes()
+        self._params = None       # list[weights_mod.ConvParams]
+        self._nets = {}           # (H, W) -> dict(handle, max_batch)
+        self._descs = graph_mod.to_descs(g)
+
+    # ---------------- weights ----------------
+    def set_params(self, params):
+        if len(params) != len(self.conv_shapes):
+            raise ValueError(f"expected {len(self.conv_shapes)} conv parameter sets, got {len(params)}")
+        for p, (k, cin, cout, bn) in zip(params, self.conv_shapes):
+            if p.kernel.shape != (k, k, cin, cout) or p.has_bn != bn:
+                raise ValueError(f"conv parameters do not match the model: kernel {p.kernel.shape} vs {(k, k, cin, cout)}")
+        self._params = list(params)
+        for key in list(self._nets):
+            self._upload(self._nets[key]["handle"])
+
+    def set_weights(self, arrays):
+        """Keras order: per conv layer [kernel, (bias)] followed by its BN layer's [gamma, beta, mean, variance]."""
+        self.set_params(weights_mod.params_from_list(arrays, self.conv_shapes))
+
+    def get_weights(self):
+        if self._params is None:
+            raise _lib.Y3Error("model has no weights yet")
+        out = []
+        for p in self._params:
+            out += p.as_list()
+        return out
+
+    def init_weights(self, kind="keras", seed=0):
+        """Random-init weights of the architecture: 'keras' = what a freshly built reference model holds,
+        'variance' = variance-preserving init used by the tolerance tests."""
+        if kind == "keras":
+            self.set_params(weights_mod.init_keras_default(self.conv_shapes, seed))
+        elif kind == "variance":
+            g = self.graph
+            feeds_shortcut = {l.src0 for l in g.layers if l.op == _lib.OP_SHORTCUT}
+            res = [ci for ci, li in enumerate(g.conv_layers) if (li + 1) in feeds_shortcut]
+            self.set_params(weights_mod.init_variance_preserving(self.conv_shapes, seed, nclasses=self.nclasses,
+                                                                 residual_convs=res))
+        else:
+            raise ValueError(kind)
+        return self
+
+    def load_weights(self, path):
+        """Darknet ``.weights`` (reference convert.py) or an ``.npz`` written by ``save_weights``.  TF-checkpoint
+        bundles (``.tf``/``.index``) need TensorFlow's bundle reader and are not supported yet."""
+        path = str(path)
+        if path.endswith(".weights"):
+            self.set_params(weights_mod.read_darknet_weights(path, self.conv_shapes))
+        elif path.endswith(".npz"):
+            z = np.load(path)
+            self.set_weights([z[f"arr_{i}"] for i in range(len(z.files))])
+        else:
+            raise _lib.Y3Unsupported("TF-checkpoint weights need a tensor-bundle reader (SURVEY.md f-1); "
+                                     "convert with the reference's convert.py to Darknet .weights or use .npz")
+        return self
+
+    def expect_partial(self):   # Keras load_weights(...).expect_partial() chaining (inference.py:102)
+        return self
+
+    def save_weights(self, path):
+        np.savez(path, *self.get_weights())
+
+    # ---------------- execution ----------------
+    def _upload(self, handle):
+        lib = _lib.lib()
+        for i, p in enumerate(self._params):
+            keep = [np.ascontiguousarray(a, np.float32) if a is not None else None
+                    for a in (p.kernel, p.bias, p.gamma, p.beta, p.mean, p.var)]
+            args = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in keep]
+            _lib.check(lib.y3_net_load_conv(handle, i, *args, weights_mod.BN_EPS))
+
+    def _net(self, H, W, B, device=None):
+        key = (int(H), int(W))
+        ent = self._nets.get(key)
+        if ent is not None and ent["max_batch"] >= B:
+            return ent
+        lib = _lib.lib()
+        ctx = _lib.context(device)
+        if ent is not None:
+            lib.y3_net_destroy(ent["handle"])
+        h = C.c_void_p()
+        _lib.check(lib.y3_net_create(ctx.handle, self._descs, len(self._descs), int(H), int(W), int(B),
+                                     int(self.nclasses), C.byref(h)))
+        shapes = []
+        for k in range(lib.y3_net_num_outputs(h)):
+            gh, gw, ch = C.c_int(), C.c_int(), C.c_int()
+            _lib.check(lib.y3_net_output_shape(h, k, C.byref(gh), C.byref(gw), C.byref(ch)))
+            shapes.append((gh.value, gw.value, ch.value))
+        ent = {"handle": h, "max_batch": int(B), "ctx": ctx, "out_shapes": shapes}
+        self._nets[key] = ent
+        if self._params is not None:
+            self._upload(h)
+        return ent
+
+    def plan(self, H, W, max_batch=1):
+        """Planner output for (H, W) on a planning-only context -- works without a GPU (host-logic tests)."""
+        lib = _lib.lib()
+        ctx = _lib.Context(-1)
+        h = C.c_void_p()
+        _lib.check(lib.y3_net_create(ctx.handle, self._descs, len(self._descs), int(H), int(W), int(max_batch),
+                                     int(self.nclasses), C.byref(h)))
+        plans = (_lib.LayerPlan * len(self._descs))()
+        _lib.check(lib.y3_net_get_plan(h, plans, len(self._descs)))
+        out = {"arena_bytes": lib.y3_net_arena_bytes(h), "num_convs": lib.y3_net_num_convs(h),
+               "layers": [{f: getattr(p, f) for f, _ in _lib.LayerPlan._fields_} for p in plans]}
+        lib.y3_net_destroy(h)
+        ctx.close()
+        return out
+
+    def __call__(self, x, training=False, outs=None):
+        """x: [B, H, W, 3] float32 NHWC in [0, 1] (torch CUDA tensor; numpy / CPU tensors are copied to the GPU)."""
+        if self._params is None:
+            raise _lib.Y3Error("model has no weights: call load_weights / set_weights / init_weights first")
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        if x.dim() != 4 or x.shape[3] != 3:
+            raise ValueError(f"input shape {tuple(x.shape)} is not [B, H, W, 3]")
+        if not x.is_cuda:
+            x = x.to(torch.device("cuda", _lib.context().device), non_blocking=True)
+        x = x.contiguous().float()
+        B, H, W, _ = x.shape
+        ent = self._net(H, W, B, x.device.index)
+        if outs is None:
+            outs = [torch.empty((B, gh, gw, 3, ch // 3), dtype=torch.float32, device=x.device)
+                    for gh, gw, ch in ent["out_shapes"]]
+        op = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        _lib.check(_lib.lib().y3_net_forward(ent["handle"], _lib.ptr(x), int(B), op, len(outs), _lib.stream_ptr()))
+        return outs
+
+    def predict(self, x, batch_size=32, **kwargs):
+        """Keras ``model.predict``: batches of ``batch_size`` (Keras default 32), numpy arrays out."""
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        chunks = []
+        for i in range(0, x.shape[0], batch_size):
+            chunks.append([o.cpu().numpy() for o in self(x[i:i + batch_size])])
+        return [np.concatenate([c[k] for c in chunks], axis=0) for k in range(len(chunks[0]))]
+
+    def summary(self, print_fn=print):
+        print_fn(f'Model: "{self.name}"  ({len(self.graph.layers)} layers, {len(self.conv_shapes)} convs, '
+                 f'{sum(k * k * ci * co for k, ci, co, _ in self.conv_shapes):,} conv weights)')
+        for i, l in enumerate(self.graph.layers):
+            print_fn(f"{i:4d} {l.sub_model:9s} {graph_mod.OP_NAMES[l.op]:9s} src={l.src0},{l.src1} "
+                     f"k={l.ksize} s={l.stride} filters={l.filters} bn={l.batch_normalize} act={l.activation}")
+
+    def close(self):
+        for ent in self._nets.values():
+            _lib.lib().y3_net_destroy(ent["handle"])
+        self._nets = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ParseModel:
+    """Same entry points as reference core/parse_model.py:10 (``build_model`` :279-314, ``create_model`` :316-322)."""
+
+    def build_model(self, model_inputs, sub_models_configs, output_stage='head', decay_factor=0, nclasses=0,
+                    search_dirs=(), layer_lists=None, **kwargs):
+        """``model_inputs`` (a Keras ``Input`` in the reference) is accepted and ignored: H and W come from the tensor
+        the model is called on.  ``decay_factor`` only matters for training and is ignored."""
+        g = graph_mod.build_graph(sub_models_configs, output_stage, nclasses, search_dirs=search_dirs,
+                                  layer_lists=layer_lists)
+        if not g.outputs:
+            raise ValueError(f"no sub-model name contains output_stage={output_stage!r}")
+        return Y3Model(g)
+
+    def create_model(self, nclasses, model_config_file):
+        with open(model_config_file, 'r') as _stream:
+            model_config = yaml.safe_load(_stream)
+        if "sub_models" in model_config:   # legacy monolithic config/yolov3_model.yaml
+            return Y3Model(graph_mod.build_graph_legacy(model_config, nclasses))
+        return Y3Model(graph_mod.load_model_config(model_config_file, nclasses))
+
+    @staticmethod
+    def builtin_yolov3(nclasses):
+        """Darknet-53 YOLOv3 from the built-in description (identical graph to config/models/yolov3/model.yaml)."""
+        from .. import configs
+        model, files = configs.yolov3_config()
+        return ParseModel().build_model(None, model["sub_models_configs"], model["output_stage"], nclasses=nclasses,
+                                        layer_lists=files)

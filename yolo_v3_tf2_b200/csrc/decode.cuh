@@ -86,8 +86,11 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         const float w = expf(r[2]) * a.anchors[(s * 3 + anc) * 2 + 0];
         const float h = expf(r[3]) * a.anchors[(s * 3 + anc) * 2 + 1];
         const float obj = sigmoidf_acc(r[4]);
-        const float cx = __fdiv_rn(__fadd_rn(sx, (float)gj), (float)a.gw[s]);
-        const float cy = __fdiv_rn(__fadd_rn(sy, (float)gi), (float)a.gh[s]);
+        // The reference divides the (x, y) pair elementwise by tf.shape(xy)[1:3] = (gh, gw)
+        // (yolo_decode_layer.py:5,8): x by the row count, y by the column count.  Identical for square grids; mirrored
+        // literally so non-square inputs give the reference's numbers.
+        const float cx = __fdiv_rn(__fadd_rn(sx, (float)gj), (float)a.gh[s]);
+        const float cy = __fdiv_rn(__fadd_rn(sy, (float)gi), (float)a.gw[s]);
         const float hw = w * 0.5f, hh = h * 0.5f;
         float4 box;
         box.x = __fsub_rn(cx, hw);

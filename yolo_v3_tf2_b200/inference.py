@@ -1,0 +1,100 @@
+"""The assembly of reference inference.py:83-117 (model -> yolo_decode -> YoloNmsLayer) and its
+``gather_valid_detections_results`` (inference.py:21-28), without the file / plotting loop (host I/O, out of scope)."""
+import numpy as np
+import torch
+import yaml
+
+from . import _lib
+from .core.parse_model import ParseModel, Y3Model
+from .core.utils import get_anchors
+from .core.yolo_decode_layer import yolo_decode
+from .core.yolo_nms import nms_padded
+from .core.yolo_nms_layer import YoloNmsLayer
+
+
+class Inference:
+    @staticmethod
+    def gather_valid_detections_results(bboxes_padded, class_indices_padded, scores_padded,
+                                        selected_indices_padded, num_valid_detections):
+        """reference inference.py:21-28, for ONE image: rows ``selected[:num_valid]`` of bboxes [N,4], classes [N],
+        scores [N]."""
+        n = int(num_valid_detections)
+        idx = torch.as_tensor(selected_indices_padded)[:n].long()
+        bboxes = torch.as_tensor(bboxes_padded)[idx.to(torch.as_tensor(bboxes_padded).device)]
+        classes = torch.as_tensor(class_indices_padded)[idx.to(torch.as_tensor(class_indices_padded).device)]
+        scores = torch.as_tensor(scores_padded)[idx.to(torch.as_tensor(scores_padded).device)]
+        return bboxes, classes, scores
+
+
+def gather_detections_batched(bboxes, class_indices, scores, selected, num_valid):
+    """Batched, zero-padded device version of ``gather_valid_detections_results``:
+    -> (boxes [B,max,4] f32, classes [B,max] i64, scores [B,max] f32); rows >= num_valid[b] are zero."""
+    ctx = _lib.context()
+    B, N = scores.shape
+    mx = selected.shape[1]
+    dev = scores.device
+    ob = torch.empty((B, mx, 4), dtype=torch.float32, device=dev)
+    oc = torch.empty((B, mx), dtype=torch.int64, device=dev)
+    os_ = torch.empty((B, mx), dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().y3_gather_detections(ctx.handle, _lib.ptr(bboxes), _lib.ptr(class_indices), _lib.ptr(scores),
+                                               _lib.ptr(selected), _lib.ptr(num_valid), B, N, mx, _lib.ptr(ob),
+                                               _lib.ptr(oc), _lib.ptr(os_), _lib.stream_ptr()))
+    return ob, oc, os_
+
+
+class Detector:
+    """model -> decode -> NMS on one GPU, the composition of reference inference.py:109-117.
+
+    ``detect(x)`` returns the reference's 5-tuple (bboxes [B,N,4], class_indices [B,N] int64, scores [B,N],
+    selected_indices_padded [B,max] int32, num_valid_detections [B] int32).  ``fused=True`` (default) lets the decode
+    kernel emit scores / class ids itself; ``fused=False`` runs the reference's exact op sequence
+    (yolo_decode -> YoloNmsLayer).  Results are identical either way."""
+
+    def __init__(self, model: Y3Model, anchors_table, nclasses, yolo_max_boxes=100, nms_iou_threshold=0.5,
+                 nms_score_threshold=0.1, fused=True):
+        self.model = model
+        self.anchors = np.asarray(anchors_table, dtype=np.float32)
+        self.nclasses = int(nclasses)
+        self.max_boxes = int(yolo_max_boxes)
+        self.iou_thr = float(nms_iou_threshold)
+        self.score_thr = float(nms_score_threshold)
+        self.fused = fused
+        self.nms_layer = YoloNmsLayer(yolo_max_boxes, nms_iou_threshold, nms_score_threshold)
+
+    @classmethod
+    def from_config(cls, detect_config_file, search_dirs=()):
+        """Build from a reference ``detect_config*.yaml`` (keys: model_config_file, classes_name_file, anchors_file,
+        yolo_max_boxes, nms_iou_threshold, nms_score_threshold, input_weights_path; inference.py:52-71)."""
+        with open(detect_config_file, "r") as f:
+            cfg = yaml.safe_load(f)
+        from . import graph as graph_mod
+        anchors = get_anchors(graph_mod._resolve(cfg["anchors_file"], search_dirs)).astype(np.float32)
+        names = [c.strip() for c in open(graph_mod._resolve(cfg["classes_name_file"], search_dirs)).readlines()]
+        nclasses = len(names)   # inference.py:84-85
+        with open(graph_mod._resolve(cfg["model_config_file"], search_dirs), "r") as f:
+            model_config = yaml.safe_load(f)
+        model = ParseModel().build_model(None, model_config["sub_models_configs"], model_config["output_stage"],
+                                         nclasses=nclasses, search_dirs=search_dirs)
+        det = cls(model, anchors, nclasses, cfg["yolo_max_boxes"], cfg["nms_iou_threshold"], cfg["nms_score_threshold"])
+        det.class_names = names
+        det.config = cfg
+        return det
+
+    def detect(self, x):
+        grids = self.model(x)
+        if self.fused:
+            bboxes, conf, probs, scores, cls = yolo_decode(grids, self.anchors, self.nclasses, with_scores=True)
+            sel, nvalid, status = nms_padded(bboxes, scores, self.max_boxes, self.iou_thr, self.score_thr)
+            self.last_status = status
+            return bboxes, cls, scores, sel, nvalid
+        decoded = yolo_decode(grids, self.anchors, self.nclasses)
+        return self.nms_layer(decoded)
+
+    __call__ = detect
+    predict = detect
+
+    def detections(self, x):
+        """detect + batched gather: (boxes [B,max,4], classes [B,max], scores [B,max], num_valid [B])."""
+        bboxes, cls, scores, sel, nvalid = self.detect(x)
+        ob, oc, os_ = gather_detections_batched(bboxes, cls, scores, sel, nvalid)
+        return ob, oc, os_, nvalid
