@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the YOLOv3 hot path (backbone+neck+heads -> decode -> NMS) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (TF is absent: the oracle port)
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic images.
+Workload at N=1: BASELINE.json configs[1] = YOLOv3 Darknet-53, 80 classes, 416x416, batch 64, bf16 activations,
+random-init weights (Keras defaults, the reference's own fresh-model state).  N > 1: weak scaling, 64 images per rank.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NCLASSES = 80
+GFLOP_PER_IMAGE_416 = 65.864          # SURVEY.md section 8d (2*MAC over the 75 convs, C=80)
+
+
+def conv_flops(model, H, W):
+    from yolo_v3_tf2_b200 import _lib
+    p = model.plan(H, W, 1)
+    fl, ci = 0, 0
+    for l, pl in zip(model.graph.layers, p["layers"]):
+        if l.op == _lib.OP_CONV:
+            k, cin, cout, _ = model.conv_shapes[ci]
+            ci += 1
+            fl += 2 * pl["H"] * pl["W"] * cout * k * k * cin
+    launches = sum(1 for pl in p["layers"] if pl["kernel"] != 0)
+    return fl, launches
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_step(model, anchors, x_np, torch_threads):
+    """The reference's CPU path restated (oracle): forward + decode + class reduce + NMS for a small batch."""
+    import torch
+    from oracle import net_oracle, decode_oracle, c_oracle
+    torch.set_num_threads(torch_threads)
+    grids = net_oracle.forward(model.graph.layers, model.graph.outputs, model._params, x_np)
+    b, c, p = decode_oracle.yolo_decode(grids, anchors, NCLASSES)
+    cls, sc = decode_oracle.class_reduce(c, p)
+    sel, nv = c_oracle.nms(b, sc, 100, 0.5, 0.1)
+    return sel, nv
+
+
+def run_reference(args, rank, world):
+    """--impl reference: TensorFlow 2.8.1 is not installable here (no network, Python 3.12), so the arm times the
+    CPU restatement of the reference (oracle) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    cores = os.cpu_count() or 1
+    model = y3.ParseModel.builtin_yolov3(NCLASSES).init_weights("keras", seed=0)
+    anchors = configs.coco_anchors()
+    sample_b = args.ref_batch
+    x = np.random.default_rng(0).random((sample_b, args.size, args.size, 3), dtype=np.float32)
+    for _ in range(args.warmup):
+        cpu_reference_step(model, anchors, x, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(model, anchors, x, cores)
+    dt = time.perf_counter() - t0
+    v = sample_b * args.steps / dt
+    line = {"impl": "reference", "metric": "images/sec (416^2, backbone+decode+NMS)", "value": v, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"YOLOv3 Darknet-53 C=80 {args.size}x{args.size}, random-init, forward+decode+NMS",
+                       "note": "CPU restatement of the reference (TensorFlow absent); bounded sample per step"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample_b} images of {args.size}x{args.size} per step x {args.steps} steps"},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=416)
+    ap.add_argument("--ref-batch", type=int, default=2, help="images per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-images", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs, distributed as y3dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S = args.batch, args.size
+    model = y3.ParseModel.builtin_yolov3(NCLASSES).init_weights("keras", seed=0)
+    anchors = configs.coco_anchors()
+    det = y3.Detector(model, anchors, NCLASSES, yolo_max_boxes=100, nms_iou_threshold=0.5, nms_score_threshold=0.1)
+    flops_img, launches_fwd = conv_flops(model, S, S)
+
+    # synthetic inputs: per-rank seed = global image index block; a few rotating device buffers + pinned host copies
+    nbuf = 3
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host = [torch.rand((B, S, S, 3), generator=gen, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    xs = [h.to(dev) for h in host]
+    mx = det.max_boxes
+
+    from yolo_v3_tf2_b200.core.yolo_nms import nms_padded
+    from yolo_v3_tf2_b200.inference import gather_detections_batched
+
+    def step(x):
+        """public-API step: local detections, then (N > 1) the NCCL gather of the fixed-size records"""
+        local = det.detections(x)
+        if world > 1:
+            y3dist.gather_detections(*local)
+        return local
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value) ----------------
+    for i in range(max(args.warmup, 3)):
+        step(xs[i % nbuf])
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0.record()
+    for i in range(args.steps):
+        x = xs[i % nbuf]
+        fwd_ev[i][0].record()
+        grids = model(x)
+        fwd_ev[i][1].record()
+        bboxes, conf, probs, scores, cls = y3.yolo_decode(grids, anchors, NCLASSES, with_scores=True)
+        sel, nv, status = nms_padded(bboxes, scores, mx, 0.5, 0.1)
+        ob, oc, os_ = gather_detections_batched(bboxes, cls, scores, sel, nv)
+        if world > 1:
+            y3dist.gather_detections(ob, oc, os_, nv)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+    fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / args.steps
+    achieved_tflops = flops_img * B / (fwd_ms / 1e3) / 1e12
+
+    # ---------------- end to end through the public API with host buffers (e2e) ----------------
+    out_host = [torch.empty((B, mx * 6 + 1), dtype=torch.float32).pin_memory() for _ in range(2)]
+    xin = [torch.empty((B, S, S, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+
+    def e2e_loop(nsteps):
+        # double-buffered serving loop: the H2D copy of step i+1 overlaps the compute of step i
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        for b in range(2):
+            free[b].record(main_stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[0])
+            xin[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(nsteps):
+            cur, nxt = i & 1, (i + 1) & 1
+            if i + 1 < nsteps:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[nxt])
+                    xin[nxt].copy_(host[(i + 1) % nbuf], non_blocking=True)
+                    ready[nxt].record(copy_stream)
+            main_stream.wait_event(ready[cur])
+            ob, oc, os_, nv = step(xin[cur])
+            free[cur].record(main_stream)
+            rec = y3dist.pack_detections(ob, oc, os_, nv)
+            out_host[cur].copy_(rec, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_loop(3)
+    sync_all()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    e2e_loop(args.steps)
+    s1.record()
+    sync_all()
+    e2e_ms = s0.elapsed_time(s1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        line = {
+            "metric": "images/sec (416^2, backbone+decode+NMS)", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"YOLOv3 Darknet-53 C=80 {S}x{S} batch {B}/GPU, random-init (Keras defaults), "
+                                   f"forward + decode + NMS(max 100, iou 0.5, score 0.1) + gather",
+                       "images_per_gpu": B, "l2": "inputs rotate over 3 device buffers; each step streams a ~1 GB "
+                                                  "activation arena (>> 126 MB L2) so no step starts with a warm L2"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 3 * 4,
+                    "d2h_bytes_per_step": B * (mx * 6 + 1) * 4,
+                    "note": "Detector.detections() on pinned host batches, double-buffered H2D on a copy stream"},
+            "gpu_launches": args.steps * (launches_fwd + 3),
+            "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "conv_tc_kernel (74 launches/step; forward pass timed with CUDA events, includes the "
+                                   "CUDA-core stem conv = 0.45% of FLOPs)", "forward_ms": fwd_ms,
+                         "flops_per_step": flops_img * B},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            nimg = args.cpu_baseline_images
+            xc = host[0][:nimg].numpy()
+            cpu_reference_step(model, anchors, xc[:1], cores)   # warm-up
+            t0 = time.perf_counter()
+            cpu_reference_step(model, anchors, xc, cores)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nimg / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{nimg} images of {S}x{S}, torch-CPU fp32 oracle forward + numpy decode "
+                                              f"+ C NMS (TensorFlow absent: CPU restatement of the reference)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

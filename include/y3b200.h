@@ -108,6 +108,12 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel_hwio_host, c
 /* x: [B,H,W,3] fp32 NHWC in [0,1].  outs[k]: [B,gh_k,gw_k,3,5+C] fp32 for every output in model order. */
 int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream);
 
+/* Profiling aid: same as y3_net_forward with a CUDA event between kernels; after the call ms_host[i] is the device time
+ * of kernel i and layer_host[i] the layer index it implements (n_steps = y3_net_num_steps). Synchronises the stream. */
+int y3_net_num_steps(y3_net* net);
+int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream,
+                         float* ms_host, int32_t* layer_host, int n_steps);
+
 /* grids[s]: [B,gh[s],gw[s],3,5+C] fp32; anchors_host: 3x3x2 fp32 (scale, anchor, (w,h)) image fractions.
  * bboxes [B,N,4], conf [B,N,1], probs [B,N,C]; scores [B,N] and class_idx [B,N] (int64) optional (both or neither). */
 int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, int n_scales,

@@ -61,7 +61,7 @@ def test_class_reduce_vs_oracle(cuda, C):
     B, N = 3, 1000
     probs = rng.random((B, N, C)).astype(np.float32)
     probs[0, :50, :] = 0.25            # all-equal rows: first index must win
-    probs[1, 5, 7] = probs[1, 5, 3] = 2.0   # duplicated max: lower index wins
+    probs[1, 5, C - 1] = probs[1, 5, 3] = 2.0   # duplicated max: lower index wins
     conf = rng.random((B, N, 1)).astype(np.float32)
     boxes = np.zeros((B, N, 4), np.float32)
     out = y3.yolo_nms((torch.from_numpy(boxes).cuda(), torch.from_numpy(conf).cuda(), torch.from_numpy(probs).cuda()),

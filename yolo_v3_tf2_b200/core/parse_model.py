@@ -151,6 +151,23 @@ class Y3Model:
         _lib.check(_lib.lib().y3_net_forward(ent["handle"], _lib.ptr(x), int(B), op, len(outs), _lib.stream_ptr()))
         return outs
 
+    def profile_layers(self, x):
+        """Per-kernel device times of one forward pass: list of (layer index, ms).  Profiling aid, not part of the
+        reference surface."""
+        B, H, W, _ = x.shape
+        ent = self._net(H, W, B, x.device.index)
+        lib = _lib.lib()
+        n = lib.y3_net_num_steps(ent["handle"])
+        outs = [torch.empty((B, gh, gw, 3, ch // 3), dtype=torch.float32, device=x.device)
+                for gh, gw, ch in ent["out_shapes"]]
+        op = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        ms = np.zeros(n, np.float32)
+        layer = np.zeros(n, np.int32)
+        _lib.check(lib.y3_net_forward_timed(ent["handle"], _lib.ptr(x.contiguous().float()), int(B), op, len(outs),
+                                            _lib.stream_ptr(), ms.ctypes.data_as(C.c_void_p),
+                                            layer.ctypes.data_as(C.c_void_p), n))
+        return list(zip(layer.tolist(), ms.tolist()))
+
     def predict(self, x, batch_size=32, **kwargs):
         """Keras ``model.predict``: batches of ``batch_size`` (Keras default 32), numpy arrays out."""
         if isinstance(x, torch.Tensor):

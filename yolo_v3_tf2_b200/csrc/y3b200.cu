@@ -760,7 +760,38 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
     return Y3_OK;
 }
 
+static int net_forward_impl(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream,
+                            std::vector<cudaEvent_t>* evs);
+
 int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream) {
+    return net_forward_impl(net, x, B, outs, n_outs, stream, nullptr);
+}
+
+int y3_net_num_steps(y3_net* net) { return net ? (int)net->steps.size() : 0; }
+
+int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream,
+                         float* ms_host, int32_t* layer_host, int n_steps) {
+    if (!net || !ms_host || n_steps != (int)net->steps.size()) return fail(Y3_ERR_INVALID, "bad timing buffers");
+    std::vector<cudaEvent_t> evs(net->steps.size() + 1);
+    for (auto& e : evs) Y3_CUDA(cudaEventCreate(&e));
+    int rc = net_forward_impl(net, x, B, outs, n_outs, stream, &evs);
+    if (rc == Y3_OK) {
+        cudaError_t e = cudaEventSynchronize(evs.back());
+        if (e != cudaSuccess) rc = fail(Y3_ERR_CUDA, std::string("cudaEventSynchronize: ") + cudaGetErrorString(e));
+    }
+    if (rc == Y3_OK) {
+        for (size_t i = 0; i < net->steps.size(); ++i) {
+            cudaEventElapsedTime(&ms_host[i], evs[i], evs[i + 1]);
+            if (layer_host) layer_host[i] = net->steps[i].layer;
+        }
+    }
+    for (auto& e : evs) cudaEventDestroy(e);
+    return rc;
+}
+
+static int net_forward_impl(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream,
+                            std::vector<cudaEvent_t>* evs) {
+    (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!net || !x || !outs) return fail(Y3_ERR_INVALID, "null argument");
     if (net->ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (B <= 0 || B > net->max_batch) return fail(Y3_ERR_INVALID, "batch " + std::to_string(B) + " exceeds max_batch");
@@ -769,8 +800,11 @@ int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n
         if (!w.loaded) return fail(Y3_ERR_STATE, "weights not loaded for every conv");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int sms = net->ctx->sms;
+    size_t step_no = 0;
     for (const Step& s : net->steps) {
         const y3_layer_desc& d = net->layers[s.layer];
+        if (evs) Y3_CUDA(cudaEventRecord((*evs)[step_no], st));
+        ++step_no;
         if (s.kind == 1) {
             const TensorInfo& a = net->tensors[s.src];
             const TensorInfo& o = net->tensors[s.dst];
@@ -832,12 +866,14 @@ int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n
             Y3_CUDA(cudaGetLastError());
         }
     }
+    if (evs) Y3_CUDA(cudaEventRecord(evs->back(), st));
     return Y3_OK;
 }
 
 int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, int n_scales,
               const float* anchors_host, int B, int nclasses, float* bboxes, float* conf, float* probs, float* scores,
               int64_t* class_idx, void* stream) {
+    (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!ctx || !grids || !gh || !gw || !anchors_host || !bboxes || !conf || !probs) return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (n_scales < 1 || n_scales > 3) return fail(Y3_ERR_UNSUPPORTED, "1..3 scales supported");
@@ -871,10 +907,10 @@ int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* 
     const int F = 5 + nclasses;
     const size_t smem = (size_t)((y3::kDecodeRecs * F + 3) & ~3) * 4 + y3::kDecodeRecs * 4;
     if (smem > 200 * 1024) return fail(Y3_ERR_UNSUPPORTED, "nclasses too large for the decode tile");
-    static bool configured = false;
-    if (!configured) {
-        Y3_CUDA(cudaFuncSetAttribute(y3::decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        Y3_CUDA(cudaFuncSetAttribute(y3::decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
     y3::decode_kernel<<<chunks, y3::kDecodeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     Y3_CUDA(cudaGetLastError());
@@ -883,6 +919,7 @@ int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* 
 
 int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, int N, int nclasses, float* scores,
                     int64_t* class_idx, void* stream) {
+    (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!ctx || !probs || !conf || !scores || !class_idx) return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (B <= 0 || N <= 0 || nclasses <= 0) return fail(Y3_ERR_INVALID, "bad shape");
@@ -896,6 +933,7 @@ int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, i
 
 int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, int max_boxes, float iou_thr,
            float score_thr, int32_t* selected, int32_t* num_valid, int32_t* status, void* stream) {
+    (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!ctx || !bboxes || !scores || !selected || !num_valid || !status) return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (B <= 0 || N <= 0 || max_boxes <= 0) return fail(Y3_ERR_INVALID, "bad shape");
@@ -911,10 +949,10 @@ int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, 
     a.iou_thr = iou_thr; a.score_thr = score_thr;
     a.selected = selected; a.num_valid = num_valid; a.status = status;
     const size_t smem = (size_t)np * 6 + (size_t)(y3::kNmsKeptCap + y3::kNmsChunk) * 16 + (size_t)y3::kNmsChunk * 8 * 4 + 32;
-    static bool configured = false;
-    if (!configured) {
-        Y3_CUDA(cudaFuncSetAttribute(y3::nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+    static size_t configured = 0;   // static shared memory of the kernel counts against the 227 KB limit too
+    if (smem > configured) {
+        Y3_CUDA(cudaFuncSetAttribute(y3::nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
     y3::nms_kernel<<<B, y3::kNmsThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     Y3_CUDA(cudaGetLastError());
@@ -924,6 +962,7 @@ int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, 
 int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_idx, const float* scores,
                          const int32_t* selected, const int32_t* num_valid, int B, int N, int max_boxes,
                          float* out_boxes, int64_t* out_classes, float* out_scores, void* stream) {
+    (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!ctx || !bboxes || !class_idx || !scores || !selected || !num_valid || !out_boxes || !out_classes || !out_scores)
         return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
@@ -944,6 +983,7 @@ int y3_conv_block_n(int cin, int cout) {
 int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, const void* w_packed,
                    const float* bias, int ksize, int stride, int Cout, int leaky, const void* residual,
                    int64_t res_stride, void* out, int64_t out_stride, int out_fp32, int upsample, void* stream) {
+    (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!ctx || !x || !w_packed || !bias || !out) return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     ConvCfg cfg;
@@ -979,6 +1019,7 @@ int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int
 
 int y3_dbg_tma_tile(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, int ksize, int stride,
                     int swizzle, int tap_r, int tap_s, int c0, int m0, void* out_bytes, void* stream) {
+    (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!ctx || !x || !out_bytes) return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (swizzle != 128 && swizzle != 64) return fail(Y3_ERR_INVALID, "swizzle must be 64 or 128");
