@@ -12,7 +12,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -35,52 +34,58 @@ def conv_flops(model, H, W):
     return fl, launches
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled by an `nvidia-smi -lms` subprocess while the timed regions
+    run (an in-process NVML polling thread was measured to slow kernel launches down 3x, so the sampler lives in its
+    own process)."""
 
-    def __init__(self, index, period=0.1):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._halt = threading.Event()
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index, period_ms=250):
+        import subprocess
+        import tempfile
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", str(period_ms)],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
         except Exception:
-            self.nv = None
+            self.proc = None
 
-    def run(self):
-        if self.nv is None:
-            return
-        nv = self.nv
-        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
-                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
-        while not self._halt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for n, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(n)
-            except Exception:
-                pass
-            time.sleep(self.period)
+    def start(self):
+        return self
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=2)
-        s = sorted(self.samples)
-        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        import statistics
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.out.flush()
+        self.out.seek(0)
+        clocks, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.out.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                clocks.append(int(float(parts[0])))
+                mx = int(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.out.name)
+        except OSError:
+            pass
+        return {"sm_mhz": (int(statistics.median(clocks)) if clocks else None), "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(clocks)}
 
 
 def cpu_reference_step(model, anchors, x_np, torch_threads):
@@ -130,7 +135,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
@@ -191,11 +196,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing (value) ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(max(args.warmup, 3)):
         step(xs[i % nbuf])
     sync_all()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0.record()
@@ -211,7 +216,6 @@ def main():
             y3dist.gather_detections(ob, oc, os_, nv)
     e1.record()
     sync_all()
-    clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -259,6 +263,7 @@ def main():
     s1.record()
     sync_all()
     e2e_ms = s0.elapsed_time(s1)
+    clocks = sampler.stop()
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

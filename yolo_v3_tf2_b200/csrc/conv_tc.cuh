@@ -49,6 +49,111 @@ struct ConvArgs {
 constexpr int kConvThreads = 256;
 constexpr int kBlockM = 128;
 
+// ------------------------------------------------------------------------------------------------------------------
+// Epilogue of one 128 x BLOCK_N accumulator tile, executed by one of the four epilogue warps (TMEM lane quarter q).
+//   TMEM -> registers (thread = one pixel row, 32 fp32 columns per chunk) -> +bias -> LeakyReLU(0.1)
+//   -> per-warp 32x33 fp32 transpose tile in shared memory (conflict free both ways)
+//   -> re-read so that 4 lanes cover 32 consecutive channels of one pixel: residual loads and output stores are
+//      full 32-byte sectors (8 pixels x 64 B per instruction) instead of 32 scattered 16-byte pieces
+//   -> +residual (fp32) -> bf16 -> global   (optionally replicated to the 2x2 nearest-upsample positions)
+// fp32 outputs (the 3*(5+C)-channel heads, pixel stride not a multiple of 4 floats) store 32 consecutive floats of
+// one pixel per instruction.
+// ------------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn, uint32_t t_row, int q, int lane,
+                                              float* xp) {
+    static_assert(BLOCK_N % 32 == 0, "epilogue works on 32-column chunks");
+    const int n_base = tn * BLOCK_N;
+    const int m_w = tm * kBlockM + q * 32;     // first pixel row of this warp's slab
+    const int sub = lane >> 2;                 // 0..7 : pixel row inside an 8-row group
+    const int seg = lane & 3;                  // 0..3 : 8-channel (16 B) segment inside the 32-channel chunk
+    const int hw = p.Ho * p.Wo;
+
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int ncol = n_base + c * 32;   // first output channel of this chunk
+        if (ncol >= p.cout) break;          // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + ncol);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(bp + j);
+                float f0 = __uint_as_float(v[4 * j + 0]) + b4.x;
+                float f1 = __uint_as_float(v[4 * j + 1]) + b4.y;
+                float f2 = __uint_as_float(v[4 * j + 2]) + b4.z;
+                float f3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+                if (p.leaky) {
+                    f0 = f0 > 0.f ? f0 : 0.1f * f0;
+                    f1 = f1 > 0.f ? f1 : 0.1f * f1;
+                    f2 = f2 > 0.f ? f2 : 0.1f * f2;
+                    f3 = f3 > 0.f ? f3 : 0.1f * f3;
+                }
+                xp[lane * 33 + 4 * j + 0] = f0;
+                xp[lane * 33 + 4 * j + 1] = f1;
+                xp[lane * 33 + 4 * j + 2] = f2;
+                xp[lane * 33 + 4 * j + 3] = f3;
+            }
+        }
+        __syncwarp();
+        if (!p.out_fp32) {
+            __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int r = it * 8 + sub;
+                const int m = m_w + r;
+                if (m < p.M) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = xp[r * 33 + seg * 8 + e];
+                    if (p.residual != nullptr) {
+                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + (long long)m * p.res_stride +
+                                                                             ncol + seg * 8));
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 r2 = __bfloat1622float2(h2[e]);
+                            f[2 * e] += r2.x;
+                            f[2 * e + 1] += r2.y;
+                        }
+                    }
+                    __nv_bfloat162 o2[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                    const uint4 o = *reinterpret_cast<uint4*>(o2);
+                    if (!p.upsample) {
+                        *reinterpret_cast<uint4*>(ob + (long long)m * p.out_stride + ncol + seg * 8) = o;
+                    } else {
+                        const int n = m / hw;
+                        const int rem = m - n * hw;
+                        const int po = rem / p.Wo;
+                        const int qo = rem - po * p.Wo;
+                        const long long up_row = 2LL * p.Wo;
+                        const long long pix = ((long long)n * 2 * p.Ho + 2 * po) * up_row + 2 * qo;
+#pragma unroll
+                        for (int rep = 0; rep < 4; ++rep) {
+                            const long long pp = pix + (rep >> 1) * up_row + (rep & 1);
+                            *reinterpret_cast<uint4*>(ob + pp * p.out_stride + ncol + seg * 8) = o;
+                        }
+                    }
+                }
+            }
+        } else {
+            float* of = reinterpret_cast<float*>(p.out);
+            const bool col_ok = (ncol + lane) < p.cout;
+            const int rows = min(32, p.M - m_w);
+            float* dst = of + (long long)m_w * p.out_stride + ncol + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                if (r < rows && col_ok) dst[(long long)r * p.out_stride] = xp[r * 33 + lane];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <int BLOCK_N, int SWZ, int STAGES>
 struct ConvSmem {
     static constexpr int A_BYTES = kBlockM * SWZ;
@@ -180,124 +285,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ===================== epilogue =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;          // row of the 128-row tile owned by this thread
         float* xp = xpose + q * (32 * 33);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-            const int m = tm * kBlockM + row;
-            const bool row_ok = m < p.M;
-            const int n_base = tn * BLOCK_N;
-
-            // output pixel index (dense, or top-left of the 2x2 upsample block)
-            long long opix = m;
-            long long up_row = 0;   // pixels per output row when upsampling
-            if (p.upsample) {
-                const int hw = p.Ho * p.Wo;
-                const int n = m / hw;
-                const int rem = m - n * hw;
-                const int po = rem / p.Wo;
-                const int qo = rem - po * p.Wo;
-                up_row = 2LL * p.Wo;
-                opix = ((long long)n * 2 * p.Ho + 2 * po) * up_row + 2 * qo;
-            }
-
             mbar_wait(tfull_bar(acc), acc_phase, 0x400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32 + (BLOCK_N % 32 ? 1 : 0); ++c) {
-                const int ncol = n_base + c * 32;   // first output channel of this chunk
-                if (ncol >= p.cout) break;          // warp-uniform
-                uint32_t v[32];
-                if (BLOCK_N % 32 == 0 || c * 32 + 32 <= BLOCK_N) {
-                    tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
-                } else {
-                    uint32_t h[16];
-                    tmem_ld_32x16(t_row + (uint32_t)(c * 32), h);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { v[j] = h[j]; v[16 + j] = 0u; }
-                }
-                // residual prefetch overlaps the TMEM load latency
-                uint4 rres[4];
-                const bool has_res = (p.residual != nullptr) && row_ok;
-                if (has_res) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (long long)m * p.res_stride + ncol);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
-                }
-                tmem_ld_wait();
-
-                float f[32];
-                const float4* bp = reinterpret_cast<const float4*>(p.bias + ncol);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b4 = __ldg(bp + j);
-                    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-                    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-                    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-                }
-                if (p.leaky) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
-                }
-                if (has_res) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rres[j]);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 r2 = __bfloat1622float2(h2[e]);
-                            f[8 * j + 2 * e + 0] += r2.x;
-                            f[8 * j + 2 * e + 1] += r2.y;
-                        }
-                    }
-                }
-
-                if (!p.out_fp32) {
-                    // bf16 output: every thread owns 32 consecutive channels (64 B) of its pixel
-                    if (row_ok) {
-                        uint4 o[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 h2[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                h2[e] = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
-                            o[j] = *reinterpret_cast<uint4*>(h2);
-                        }
-                        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
-                        const int reps = p.upsample ? 4 : 1;
-                        for (int rep = 0; rep < reps; ++rep) {
-                            const long long pix = opix + (rep >> 1) * up_row + (rep & 1);
-                            uint4* op = reinterpret_cast<uint4*>(ob + pix * p.out_stride + ncol);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) op[j] = o[j];
-                        }
-                    }
-                } else {
-                    // fp32 output with an arbitrary (e.g. 255-float) pixel stride: transpose through shared memory so
-                    // each store instruction writes 32 consecutive floats of one pixel.
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = f[j];
-                    __syncwarp();
-                    float* of = reinterpret_cast<float*>(p.out);
-                    const int m_w = tm * kBlockM + q * 32;
-                    const bool col_ok = (ncol + lane) < p.cout;
-                    for (int r = 0; r < 32; ++r) {
-                        const int mr = m_w + r;
-                        if (mr < p.M && col_ok) of[(long long)mr * p.out_stride + ncol + lane] = xp[r * 33 + lane];
-                    }
-                    __syncwarp();
-                }
-            }
-            // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
+            epilogue_tile<BLOCK_N>(p, tm, tn, t_row, q, lane, xp);
+            // all TMEM reads of this accumulator are complete (wait::ld) -> hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
