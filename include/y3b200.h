@@ -140,6 +140,12 @@ int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int
                    const float* bias, int ksize, int stride, int Cout, int leaky, const void* residual,
                    int64_t res_stride, void* out, int64_t out_stride, int out_fp32, int upsample, void* stream);
 
+/* The 3-channel stem conv (3x3, 32 filters) on the tensor cores: x fp32 [B,H,W,3]; w_packed bf16 [32][64] with the
+ * 27 BN-folded weights of output o at columns 0..26 AND 32..58 (the kernel multiplies bf16(x) and the bf16 remainder
+ * x - bf16(x) against the same weights, so the fp32 image keeps its precision).  Unit-test entry. */
+int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const void* w_packed, const float* bias,
+                       int stride, int leaky, void* out, int64_t out_stride, void* stream);
+
 /* Debug: fetch one 128-pixel x (swizzle/2)-channel A tile through the conv kernel's TMA path and return the raw
  * (swizzled) shared-memory image, 128*swizzle bytes. */
 int y3_dbg_tma_tile(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, int ksize, int stride,

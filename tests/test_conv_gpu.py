@@ -158,3 +158,37 @@ def test_conv2d_concat_slice_views(cuda):
     assert (got[..., :64] == 0).all() and (got[..., 192:] == 0).all(), "wrote outside the channel slice"
     err = np.abs(got[..., 64:192] - ref)
     assert (err <= 2.0 ** -8 * np.abs(ref) + 5e-3).all(), err.max()
+
+
+@pytest.mark.parametrize("B,H,W,stride", [(2, 32, 32, 1), (1, 416, 416, 1), (3, 35, 29, 1), (2, 64, 64, 2)])
+def test_conv_stem_vs_oracle(cuda, B, H, W, stride):
+    """3-channel stem on the tensor cores: fp32 image split into bf16 hi + lo halves, so only the weights are rounded."""
+    import torch
+    from yolo_v3_tf2_b200 import _lib
+    from oracle import net_oracle
+    if stride == 2 and (H % 2 or W % 2):
+        pytest.skip("even sizes only")
+    ctx = _lib.context()
+    rng = np.random.default_rng(B * 1000 + H)
+    x = rng.random((B, H, W, 3), dtype=np.float32)
+    kern = bf16_round((rng.standard_normal((3, 3, 3, 32)) / np.sqrt(27)).astype(np.float32))
+    bias = (rng.standard_normal(32) * 0.1).astype(np.float32)
+    ref = net_oracle.conv_layer(x, kern, bias, 3, stride, 1)
+    wp = np.zeros((32, 64), np.float32)
+    flat = kern.reshape(27, 32).T          # [o][k], k ordered (r, s, c)
+    wp[:, :27] = flat
+    wp[:, 32:59] = flat
+    wd = torch.from_numpy(wp).cuda().to(torch.bfloat16).contiguous()
+    bd = torch.from_numpy(bias).cuda()
+    xd = torch.from_numpy(x).cuda()
+    Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
+    od = torch.full((B, Ho, Wo, 32), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.lib().y3_conv2d_stem_f32(ctx.handle, _lib.ptr(xd), B, H, W, _lib.ptr(wd), _lib.ptr(bd), stride, 1,
+                                             _lib.ptr(od), 32, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert ctx.watchdog_code() == 0
+    got = od.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - ref)
+    # input precision ~2^-16, output rounded to bf16
+    assert (err <= 2.0 ** -8 * np.abs(ref) + 1e-3).all(), err.max()

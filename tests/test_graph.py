@@ -125,7 +125,8 @@ def test_planner_through_c_abi():
     L = p["layers"]
     assert p["num_convs"] == 75
     kinds = [l["kernel"] for l in L]
-    assert kinds.count(2) == 1 and kinds.count(1) == 74          # stem on CUDA cores, 74 tcgen05 convs
+    assert kinds.count(1) == 75 and kinds.count(2) == 0          # all 75 convs on the tcgen05 path (stem: gather mode)
+    assert (L[0]["block_n"], L[0]["swizzle"]) == (32, 128)
     assert kinds.count(3) == kinds.count(4) == kinds.count(5) == 0   # every add / upsample / concat is fused
     assert sum(1 for l in L if l["fused_add"] >= 0) == 23
     assert sum(1 for l in L if l["fused_upsample"]) == 2

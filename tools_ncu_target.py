@@ -1,0 +1,17 @@
+#!/usr/bin/env python
+"""Tiny target for ncu: two forward passes (+ decode + NMS) of the bench workload; profile the second one.
+usage: python tools_ncu_target.py [batch] [size]"""
+import sys
+import torch
+import yolo_v3_tf2_b200 as y3
+from yolo_v3_tf2_b200 import configs
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 416
+m = y3.ParseModel.builtin_yolov3(80).init_weights("keras", seed=0)
+det = y3.Detector(m, configs.coco_anchors(), 80)
+x = torch.rand((B, S, S, 3), device="cuda")
+for _ in range(2):
+    out = det.detections(x)
+torch.cuda.synchronize()
+print("ok", [tuple(o.shape) for o in out])

@@ -1,0 +1,267 @@
+// Implicit-GEMM conv whose A operand is built by software im2col ("gather") instead of TMA, with the whole weight
+// matrix resident in shared memory.  Used where TMA's per-row issue rate, not bytes, is the limit:
+//   * the 3-channel stem conv (reference backbone.yaml first conv, parse_model.py:13-56): K = 27 is padded to one
+//     64-wide K block holding bf16(x) in columns 0..26 and bf16(x - bf16(x)) in columns 32..58 (hi/lo split, so the
+//     fp32 image loses no precision); the weights are duplicated for both halves.
+//   * 3x3 convs with Cin == 32 (64-byte rows): one K block per filter tap.
+// Same tcgen05/TMEM pipeline and the same epilogue as conv_tc_kernel; only the producer differs:
+//   warps 8-11 (128 threads, one output pixel each) load the tap's channels with 16-byte loads (or 27 scalar loads for
+//   the stem), write them into the swizzled K-major tile the UMMA descriptor expects, fence the async proxy and
+//   arrive on the stage's mbarrier.  Warp 0 loads all K blocks of the weights once with TMA.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace y3 {
+
+// warp layout: 0 weights loader, 1 MMA issuer, 2 TMEM allocator, 3 idle, then 4*NEPI epilogue warps, then 4*NPROD
+// producer warps.  Tiles are dealt round-robin to the epilogue groups (group g owns accumulator stage g) and to the
+// producer groups, so two tiles are gathered / drained concurrently: these layers are latency bound, not byte bound.
+constexpr int kGatherEpiGroups = 2;
+
+template <int NPROD>
+constexpr int gather_threads() { return 32 * (4 + 4 * kGatherEpiGroups + 4 * NPROD); }
+
+template <int BLOCK_N, int SWZ, int STAGES>
+struct GatherSmem {
+    static constexpr int A_BYTES = kBlockM * SWZ;
+    static constexpr int B_BYTES = BLOCK_N * SWZ;
+    static constexpr int XPOSE_BYTES = kGatherEpiGroups * 4 * 32 * 33 * 4;
+    static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
+    static constexpr int total(int num_k_blocks) {
+        return 1024 + STAGES * A_BYTES + num_k_blocks * B_BYTES + XPOSE_BYTES + BAR_BYTES;
+    }
+};
+
+// byte offset of 16-byte chunk j of row r inside a K-major tile written with SWIZZLE_<SWZ>B
+template <int SWZ>
+__device__ __forceinline__ uint32_t swz_off(int r, int j) {
+    if (SWZ == 128) return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+    return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 16-byte asynchronous global->shared copy; src_bytes == 0 zero-fills (padding halo / rows past M)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival once all prior cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BLOCK_N, int SWZ, int STAGES, bool STEM>
+__global__ void __launch_bounds__(gather_threads<STEM ? 2 : 1>(), 1)
+conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+    using S = GatherSmem<BLOCK_N, SWZ, STAGES>;
+    constexpr int NEPI = kGatherEpiGroups;
+    constexpr int NPROD = STEM ? 2 : 1;
+    constexpr int BLOCK_K = SWZ / 2;
+    constexpr int UMMA_K = 16;
+    constexpr int CHUNKS = SWZ / 16;   // 16-byte chunks per row
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(!STEM || SWZ == 128, "stem uses one 64-wide K block");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int nkb = p.num_k_blocks;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_base + STAGES * S::A_BYTES;
+    const uint32_t tiles_bytes = STAGES * S::A_BYTES + nkb * S::B_BYTES;
+    float* xpose = reinterpret_cast<float*>(smem_gen + tiles_bytes);
+    const uint32_t bar_base = smem_base + tiles_bytes + S::XPOSE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 5);
+    volatile uint32_t* tmem_ptr_gen =
+        reinterpret_cast<volatile uint32_t*>(smem_gen + tiles_bytes + S::XPOSE_BYTES + 8 * (2 * STAGES + 5));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m;     // tiles_n == 1 (host-enforced)
+    // number of tiles this CTA processes: tile(j) = blockIdx.x + j * gridDim.x
+    const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmB);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        mbar_init(bfull_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // ===================== weights: all K blocks, once =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bfull_bar, (uint32_t)(nkb * S::B_BYTES));
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem_b + kb * S::B_BYTES, &tmB, bfull_bar, kb * BLOCK_K, 0);
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+        const uint64_t adesc0 = make_smem_desc<SWZ>(smem_a);
+        const uint64_t bdesc0 = make_smem_desc<SWZ>(smem_b);
+        int stage = 0;
+        uint32_t phase = 0;
+        mbar_wait(bfull_bar, 0, 0x700);
+        for (int j = 0; j < my_tiles; ++j) {
+            const int acc = j & 1;
+            mbar_wait(tempty_bar(acc), (uint32_t)(((j >> 1) & 1) ^ 1), 0x200 + acc);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar(stage), phase, 0x300 + stage);
+                fence_proxy_async_smem();   // producer writes came through the generic proxy (st.shared / cp.async)
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(kb * (S::B_BYTES >> 4));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    umma_commit(empty_bar(stage));
+                    if (kb == nkb - 1) umma_commit(tfull_bar(acc));
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4 && warp < 4 + 4 * NEPI) {
+        // ===================== epilogue groups =====================
+        const int eg = (warp - 4) >> 2;
+        const int q = warp & 3;
+        float* xp = xpose + (warp - 4) * (32 * 33);
+        for (int j = eg; j < my_tiles; j += NEPI) {
+            const int acc = j & 1;
+            const int tile = blockIdx.x + j * gridDim.x;
+            mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            epilogue_tile<BLOCK_N>(p, tile, 0, t_row, q, lane, xp);
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    } else if (warp >= 4 + 4 * NEPI) {
+        // ===================== A producers: one output pixel (tile row) per thread =====================
+        const int pg = (warp - 4 - 4 * NEPI) >> 2;
+        const int row = (int)threadIdx.x - 32 * (4 + 4 * NEPI) - 128 * pg;
+        const int hw = p.Ho * p.Wo;
+        if constexpr (STEM) {
+            // 27 fp32 inputs -> hi/lo bf16 halves of one 64-wide K block; the loads of the group's next tile are in
+            // flight while the current one is converted and stored
+            const float* src = reinterpret_cast<const float*>(p.src);
+            auto load27 = [&](int j, float (&v)[27]) {
+                const int m = (blockIdx.x + j * gridDim.x) * kBlockM + row;
+                const bool valid = (j < my_tiles) && (m < p.M);
+                const int n = m / hw;
+                const int rem = m - n * hw;
+                const int po = rem / p.Wo;
+                const int qo = rem - po * p.Wo;
+                const int y0 = po * p.stride + p.lower;
+                const int x0 = qo * p.stride + p.lower;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int y = y0 + r;
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        const int x = x0 + s;
+                        const bool ok = valid && y >= 0 && y < p.H && x >= 0 && x < p.W;
+                        const float* px = src + (((long long)n * p.H + y) * p.W + x) * 3;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(px + c) : 0.0f;
+                    }
+                }
+            };
+            float vn[27];
+            load27(pg, vn);
+            for (int j = pg; j < my_tiles; j += NPROD) {
+                float v[27];
+#pragma unroll
+                for (int i = 0; i < 27; ++i) v[i] = vn[i];
+                load27(j + NPROD, vn);
+                uint32_t w[32];   // 64 bf16: [0,27) hi, [32,59) lo, rest zero
+#pragma unroll
+                for (int i = 0; i < 32; ++i) w[i] = 0u;
+#pragma unroll
+                for (int i = 0; i < 27; ++i) {
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
+                    const uint32_t hb = (uint32_t)__bfloat16_as_ushort(hi), lb = (uint32_t)__bfloat16_as_ushort(lo);
+                    w[i >> 1] |= hb << ((i & 1) * 16);
+                    w[16 + (i >> 1)] |= lb << ((i & 1) * 16);
+                }
+                const int stage = j % STAGES;                      // one K block per tile
+                const uint32_t phase = (uint32_t)((j / STAGES) & 1);
+                mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
+                const uint32_t a_s = smem_a + stage * S::A_BYTES;
+#pragma unroll
+                for (int jc = 0; jc < 8; ++jc)
+                    st_shared_v4(a_s + swz_off<128>(row, jc), make_uint4(w[4 * jc], w[4 * jc + 1], w[4 * jc + 2], w[4 * jc + 3]));
+                fence_proxy_async_smem();
+                mbar_arrive(full_bar(stage));
+            }
+        } else {
+            // bf16 input, Cin == BLOCK_K: one K block per filter tap, copied with cp.async straight into the swizzled
+            // stage (no register staging, up to STAGES taps in flight per thread)
+            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.src);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < my_tiles; ++j) {
+                const int m = (blockIdx.x + j * gridDim.x) * kBlockM + row;
+                const bool valid = m < p.M;
+                const int n = m / hw;
+                const int rem = m - n * hw;
+                const int po = rem / p.Wo;
+                const int qo = rem - po * p.Wo;
+                const int y0 = po * p.stride + p.lower;
+                const int x0 = qo * p.stride + p.lower;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int r = kb / p.ksize, sx = kb - r * p.ksize;
+                    const int y = y0 + r, x = x0 + sx;
+                    const bool ok = valid && y >= 0 && y < p.H && x >= 0 && x < p.W;
+                    const __nv_bfloat16* px = ok ? src + (((long long)n * p.H + y) * p.W + x) * p.src_stride : src;
+                    mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
+                    const uint32_t a_s = smem_a + stage * S::A_BYTES;
+#pragma unroll
+                    for (int jc = 0; jc < CHUNKS; ++jc)
+                        cp_async_16(a_s + swz_off<SWZ>(row, jc), px + jc * 8, ok ? 16u : 0u);
+                    cp_async_arrive_noinc(full_bar(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace y3

@@ -15,10 +15,10 @@
 //   D        :  fp32 accumulator in TMEM, 128 lanes x BLOCK_N columns, double buffered so the epilogue of tile i
 //               overlaps the MMAs of tile i+1.
 //
-// Warp roles (256 threads, one persistent CTA per SM):
+// Warp roles (384 threads, one persistent CTA per SM):
 //   warp 0  TMA producer (one elected lane)         warp 1  MMA issuer (one lane issues tcgen05.mma)
 //   warp 2  TMEM allocator                          warp 3  idle
-//   warps 4-7  epilogue: tcgen05.ld -> +bias -> LeakyReLU(0.1) -> +residual -> bf16 (or fp32 for heads) -> global,
+//   warps 4-7 / 8-11  two epilogue groups, one per accumulator stage: tcgen05.ld -> +bias -> LeakyReLU(0.1) -> +residual -> bf16 (or fp32 for heads) -> global,
 //              optionally replicated 2x2 (nearest upsample) into a channel slice of a wider buffer (concat).
 #pragma once
 #include "ptx.cuh"
@@ -44,9 +44,14 @@ struct ConvArgs {
     long long out_stride;  // elements between consecutive pixels of the output view
     int out_fp32;
     int upsample;          // 1: write every output pixel to the 2x2 block (2p+dy, 2q+dx) of a (2Ho, 2Wo) view
+    // gather kernel only (software im2col): the input view
+    const void* src;       // bf16 NHWC view, or the fp32 [B,H,W,3] image for the stem
+    long long src_stride;  // elements between consecutive input pixels
+    int H, W;              // input spatial size
 };
 
-constexpr int kConvThreads = 256;
+constexpr int kConvEpiGroups = 2;   // epilogue warp groups; group g drains accumulator stage g (tiles j % 2 == g)
+constexpr int kConvThreads = 32 * (4 + 4 * kConvEpiGroups);
 constexpr int kBlockM = 128;
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -68,19 +73,42 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
     const int sub = lane >> 2;                 // 0..7 : pixel row inside an 8-row group
     const int seg = lane & 3;                  // 0..3 : 8-channel (16 B) segment inside the 32-channel chunk
     const int hw = p.Ho * p.Wo;
+    const bool has_res = p.residual != nullptr;
+    const int nchunks = min(BLOCK_N / 32, (p.cout - n_base + 31) / 32);
+
+    // residual tile rows of this lane (4 rows x 16 B per chunk), prefetched one chunk ahead
+    uint4 rcur[4], rnext[4];
+    auto load_res = [&](int c, uint4 (&r4)[4]) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int m = m_w + it * 8 + sub;
+            r4[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (has_res && m < p.M)
+                r4[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + (long long)m * p.res_stride + n_base + c * 32 +
+                                                              seg * 8));
+        }
+    };
+    if (has_res && nchunks > 0) load_res(0, rnext);
 
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = 0; c < nchunks; ++c) {
         const int ncol = n_base + c * 32;   // first output channel of this chunk
-        if (ncol >= p.cout) break;          // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) rcur[it] = rnext[it];
+        if (has_res && c + 1 < nchunks) load_res(c + 1, rnext);
+        float4 bias4[8];   // issued before the TMEM wait so their latency is hidden behind it
         {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + ncol);
 #pragma unroll
+            for (int j = 0; j < 8; ++j) bias4[j] = __ldg(bp + j);
+        }
+        tmem_ld_wait();
+        {
+#pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float4 b4 = __ldg(bp + j);
+                const float4 b4 = bias4[j];
                 float f0 = __uint_as_float(v[4 * j + 0]) + b4.x;
                 float f1 = __uint_as_float(v[4 * j + 1]) + b4.y;
                 float f2 = __uint_as_float(v[4 * j + 2]) + b4.z;
@@ -108,10 +136,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) f[e] = xp[r * 33 + seg * 8 + e];
-                    if (p.residual != nullptr) {
-                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + (long long)m * p.res_stride +
-                                                                             ncol + seg * 8));
-                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+                    if (has_res) {
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rcur[it]);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float2 r2 = __bfloat1622float2(h2[e]);
@@ -160,7 +186,7 @@ struct ConvSmem {
     static constexpr int B_BYTES = BLOCK_N * SWZ;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int XPOSE_BYTES = 4 * 32 * 33 * 4;        // per-epilogue-warp 32x33 fp32 transpose tile
+    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose tile
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16; // full/empty + tmem full/empty + tmem ptr
     static constexpr int TOTAL = 1024 /*align slack*/ + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
 };
@@ -218,37 +244,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
+    // The two single-thread roles run their loops with the WHOLE warp (uniform control flow, so the compiler keeps
+    // addresses / descriptors / barrier phases in uniform registers) and predicate only the issuing instructions on
+    // one elected lane.  An earlier version wrapped the loops in `if (lane == 0)`: ncu showed ~190 SASS instructions
+    // per K block in each role (runtime divisions + ELECT/BRA.U.ANY uniformisation loops), i.e. the kernel was bound by
+    // scalar issue latency, not by the tensor pipe.
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-                const int m0 = tm * kBlockM;
-                int cw = 0, ch = 0, cn = 0;
-                if (p.a_im2col) {
-                    const int hw = p.Ho * p.Wo;
-                    cn = m0 / hw;
-                    const int rem = m0 - cn * hw;
-                    const int po = rem / p.Wo;
-                    const int qo = rem - po * p.Wo;
-                    cw = qo * p.stride + p.lower;
-                    ch = po * p.stride + p.lower;
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        const int hw = p.Ho * p.Wo;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+            const int m0 = tm * kBlockM;
+            const int n0 = tn * BLOCK_N;
+            int kcoord = 0;   // K coordinate of the weight tile
+            if (p.a_im2col) {
+                const int cn = m0 / hw;
+                const int rem = m0 - cn * hw;
+                const int po = rem / p.Wo;
+                const int qo = rem - po * p.Wo;
+                const int cw = qo * p.stride + p.lower;
+                const int ch = po * p.stride + p.lower;
+                for (int r = 0; r < p.ksize; ++r) {
+                    for (int sx = 0; sx < p.ksize; ++sx) {
+                        for (int c0 = 0; c0 < p.kblocks_per_tap * BLOCK_K; c0 += BLOCK_K) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
+                            if (leader) {
+                                mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+                                tma_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), c0, cw, ch, cn,
+                                                   (uint16_t)sx, (uint16_t)r);
+                                tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, full_bar(stage), kcoord, n0);
+                            }
+                            kcoord += BLOCK_K;
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
                 }
+            } else {
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
-                    mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
-                    const int tap = kb / p.kblocks_per_tap;
-                    const int c0 = (kb - tap * p.kblocks_per_tap) * BLOCK_K;
-                    if (p.a_im2col) {
-                        const int r = tap / p.ksize, s = tap - r * p.ksize;
-                        tma_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), c0, cw, ch, cn,
-                                           (uint16_t)s, (uint16_t)r);
-                    } else {
-                        tma_load_2d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), c0, m0);
+                    if (leader) {
+                        mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+                        tma_load_2d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), kcoord, m0);
+                        tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, full_bar(stage), kcoord, n0);
                     }
-                    tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, full_bar(stage), kb * BLOCK_K, tn * BLOCK_N);
+                    kcoord += BLOCK_K;
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -256,21 +298,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x200 + acc);
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+        const uint64_t adesc0 = make_smem_desc<SWZ>(smem_a);
+        const uint64_t bdesc0 = make_smem_desc<SWZ>(smem_b);
+        int stage = 0;
+        uint32_t phase = 0;
+        int j = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+            const int acc = j & 1;
+            mbar_wait(tempty_bar(acc), (uint32_t)(((j >> 1) & 1) ^ 1), 0x200 + acc);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase, 0x300 + stage);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase, 0x300 + stage);
-                    tc_fence_after();
-                    const uint64_t adesc = make_smem_desc<SWZ>(smem_a + stage * S::A_BYTES);
-                    const uint64_t bdesc = make_smem_desc<SWZ>(smem_b + stage * S::B_BYTES);
+                if (leader) {
+                    // stage s sits s*A_BYTES (s*B_BYTES) further: +bytes>>4 in the descriptor's address field
+                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (S::B_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
@@ -279,28 +325,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     umma_commit(empty_bar(stage));   // smem slot reusable once these MMAs have read it
                     if (kb == p.num_k_blocks - 1) umma_commit(tfull_bar(acc));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
         __syncwarp();
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== epilogue =====================
+    } else if (warp >= 4) {
+        // ===================== epilogue groups =====================
+        const int eg = (warp - 4) >> 2;         // group: owns accumulator stage eg
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        float* xp = xpose + q * (32 * 33);
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        float* xp = xpose + (warp - 4) * (32 * 33);
+        int j = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+            if ((j % kConvEpiGroups) != eg) continue;
+            const int acc = j & 1;
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-            mbar_wait(tfull_bar(acc), acc_phase, 0x400 + acc);
+            mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             epilogue_tile<BLOCK_N>(p, tm, tn, t_row, q, lane, xp);
             // all TMEM reads of this accumulator are complete (wait::ld) -> hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
 

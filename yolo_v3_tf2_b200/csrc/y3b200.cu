@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "conv_first.cuh"
+#include "conv_gather.cuh"
 #include "conv_tc.cuh"
 #include "decode.cuh"
 #include "nms.cuh"
@@ -110,6 +111,7 @@ int make_map_im2col(const Driver& d, CUtensorMap* tm, const void* base, int N, i
 // ------------------------------------------------------------------------------------------------
 struct ConvCfg {
     int block_n, swz, stages;
+    int gather;   // 0: TMA-fed A operand, 1: software im2col (Cin == 32, 3x3), 2: fp32 3-channel stem (hi/lo split)
 };
 
 int pick_block_n(int cout) {
@@ -119,7 +121,16 @@ int pick_block_n(int cout) {
     return 256;
 }
 
-bool pick_cfg(int cin, int cout, ConvCfg& c) {
+bool pick_cfg(int cin, int cout, int ksize, ConvCfg& c) {
+    c.gather = 0;
+    if (cin == 3 && ksize == 3 && cout == 32) {   // stem: one 64-wide K block (27 hi + 27 lo), weights resident
+        c.block_n = 32; c.swz = 128; c.stages = 8; c.gather = 2;
+        return true;
+    }
+    if (cin == 32 && ksize == 3 && cout <= 128) {   // 64-byte rows: TMA row rate bound -> software im2col
+        c.block_n = pick_block_n(cout); c.swz = 64; c.stages = 8; c.gather = 1;
+        return true;
+    }
     if (cin % 64 == 0) c.swz = 128;
     else if (cin % 32 == 0) c.swz = 64;
     else return false;
@@ -163,6 +174,34 @@ cudaError_t launch_conv(const ConvCfg& c, const CUtensorMap& ta, const CUtensorM
             case 128: return launch_conv_t<128, 64, 8>(ta, tb, a, sms, st);
             case 256: return launch_conv_t<256, 64, 8>(ta, tb, a, sms, st);
         }
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int BN, int SWZ, int ST, bool STEM>
+cudaError_t launch_gather_t(const CUtensorMap& tb, const y3::ConvArgs& args, int sms, cudaStream_t st) {
+    using S = y3::GatherSmem<BN, SWZ, ST>;
+    auto kern = y3::conv_gather_kernel<BN, SWZ, ST, STEM>;
+    const int smem = S::total(args.num_k_blocks);
+    if (smem > 232448) return cudaErrorInvalidValue;
+    static int configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int grid = std::max(1, std::min(args.tiles_m, sms));
+    kern<<<grid, y3::gather_threads<STEM ? 2 : 1>(), smem, st>>>(tb, args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather(const ConvCfg& c, const CUtensorMap& tb, const y3::ConvArgs& a, int sms, cudaStream_t st) {
+    if (a.tiles_n != 1) return cudaErrorInvalidValue;
+    if (c.gather == 2) return launch_gather_t<32, 128, 8, true>(tb, a, sms, st);
+    switch (c.block_n) {
+        case 32: return launch_gather_t<32, 64, 8, false>(tb, a, sms, st);
+        case 64: return launch_gather_t<64, 64, 8, false>(tb, a, sms, st);
+        case 128: return launch_gather_t<128, 64, 8, false>(tb, a, sms, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -215,6 +254,7 @@ struct BufferInfo {
 struct ConvWeights {
     int cin = 0, cout = 0, k = 0, cout_pad = 0;
     bool direct = false;
+    bool stem_hilo = false;   // tensor-core stem: [cout_pad][64] = 27 weights, 5 zeros, the same 27 weights, 5 zeros
     void* w = nullptr;     // bf16 [cout_pad][k*k*cin]  or fp32 [k*k*cin][cout] for the direct kernel
     float* bias = nullptr; // fp32 [cout_pad]
     bool loaded = false;
@@ -451,12 +491,16 @@ int plan_net(y3_net& n) {
             conv_geometry(a.H, a.W, d.ksize, d.stride, d.pad, s.Ho, s.Wo, s.pad_lo, s.pad_hi);
             ConvWeights& w = n.convs[s.conv_idx];
             w.cin = a.C; w.cout = d.filters; w.k = d.ksize;
-            const bool tc_ok = pick_cfg(a.C, d.filters, s.cfg) && d.src0 != 0;
+            bool tc_ok = pick_cfg(a.C, d.filters, d.ksize, s.cfg);
+            if (tc_ok && s.cfg.gather == 2 && (d.src0 != 0 || residual[i] >= 0 || fused_up[i] || n.tensors[writes[i]].fp32_output))
+                tc_ok = false;
+            if (tc_ok && s.cfg.gather != 2 && d.src0 == 0) tc_ok = false;
             if (tc_ok) {
                 if (!n.tensors[writes[i]].fp32_output && d.filters % 32 != 0)
                     return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": bf16 conv outputs need filters % 32 == 0");
                 s.kind = 1;
                 w.cout_pad = ((d.filters + s.cfg.block_n - 1) / s.cfg.block_n) * s.cfg.block_n;
+                w.stem_hilo = (s.cfg.gather == 2);
                 pl.block_n = s.cfg.block_n; pl.swizzle = s.cfg.swz; pl.stages = s.cfg.stages;
             } else {
                 // direct CUDA-core conv: fp32 NHWC network input with 3 channels, bf16 output, no fusion
@@ -560,17 +604,19 @@ int build_maps(y3_net& n) {
         const y3_layer_desc& d = n.layers[s.layer];
         const TensorInfo& a = n.tensors[s.src];
         const ConvWeights& w = n.convs[s.conv_idx];
-        const __nv_bfloat16* ap = tensor_ptr(n, s.src);
-        int rc;
-        if (d.ksize == 1 && d.stride == 1) {
-            rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * a.H * a.W, a.C, a.pix_stride, y3::kBlockM,
-                             s.cfg.swz, false);
-        } else {
-            rc = make_map_im2col(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, a.C, a.pix_stride, d.ksize, d.stride,
-                                 s.pad_lo, s.pad_hi, s.cfg.swz);
+        int rc = Y3_OK;
+        if (s.cfg.gather == 0) {
+            const __nv_bfloat16* ap = tensor_ptr(n, s.src);
+            if (d.ksize == 1 && d.stride == 1) {
+                rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * a.H * a.W, a.C, a.pix_stride, y3::kBlockM,
+                                 s.cfg.swz, false);
+            } else {
+                rc = make_map_im2col(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, a.C, a.pix_stride, d.ksize, d.stride,
+                                     s.pad_lo, s.pad_hi, s.cfg.swz);
+            }
         }
         if (rc) return rc;
-        const uint64_t K = (uint64_t)d.ksize * d.ksize * a.C;
+        const uint64_t K = (s.cfg.gather == 2) ? 64 : (uint64_t)d.ksize * d.ksize * a.C;
         rc = make_map_2d(n.ctx->drv, &s.tmB, w.w, w.cout_pad, K, K, s.cfg.block_n, s.cfg.swz, true);
         if (rc) return rc;
     }
@@ -586,8 +632,13 @@ y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
     a.lower = -s.pad_lo;
     a.a_im2col = !(d.ksize == 1 && d.stride == 1);
     a.ksize = d.ksize;
-    a.kblocks_per_tap = cin / (s.cfg.swz / 2);
-    a.num_k_blocks = d.ksize * d.ksize * a.kblocks_per_tap;
+    if (s.cfg.gather == 2) {
+        a.kblocks_per_tap = 1;
+        a.num_k_blocks = 1;
+    } else {
+        a.kblocks_per_tap = cin / (s.cfg.swz / 2);
+        a.num_k_blocks = d.ksize * d.ksize * a.kblocks_per_tap;
+    }
     a.tiles_m = (a.M + y3::kBlockM - 1) / y3::kBlockM;
     a.tiles_n = (d.filters + s.cfg.block_n - 1) / s.cfg.block_n;
     a.cout = d.filters;
@@ -676,7 +727,7 @@ int y3_net_create(y3_ctx* ctx, const y3_layer_desc* layers, int n_layers, int H,
         cudaMemset(n->arena, 0, (size_t)n->arena_bytes);
         for (ConvWeights& w : n->convs) {
             const size_t K = (size_t)w.k * w.k * w.cin;
-            const size_t wbytes = w.direct ? K * w.cout * 4 : (size_t)w.cout_pad * K * 2;
+            const size_t wbytes = w.direct ? K * w.cout * 4 : (size_t)w.cout_pad * (w.stem_hilo ? 64 : K) * 2;
             if (cudaMalloc(&w.w, wbytes) != cudaSuccess || cudaMalloc(&w.bias, (size_t)w.cout_pad * 4) != cudaSuccess) {
                 y3_net_destroy(n);
                 return fail(Y3_ERR_CUDA, "cudaMalloc(weights) failed");
@@ -749,6 +800,16 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
         for (size_t kk = 0; kk < K; ++kk)
             for (int o = 0; o < cout; ++o) packed[kk * cout + o] = kernel[kk * cout + o] * scale[o];   // HWIO is already [K][Cout]
         Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    } else if (w.stem_hilo) {
+        // columns [0,27) multiply bf16(x), columns [32,59) multiply the bf16 remainder x - bf16(x): same weights twice
+        std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * 64, __float2bfloat16(0.0f));
+        for (size_t kk = 0; kk < K; ++kk)
+            for (int o = 0; o < cout; ++o) {
+                const __nv_bfloat16 v = __float2bfloat16(kernel[kk * cout + o] * scale[o]);
+                packed[(size_t)o * 64 + kk] = v;
+                packed[(size_t)o * 64 + 32 + kk] = v;
+            }
+        Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     } else {
         std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * K, __float2bfloat16(0.0f));
         for (size_t kk = 0; kk < K; ++kk)
@@ -823,7 +884,19 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
                 ca.out = tensor_ptr(*net, s.dst);
                 ca.out_stride = o.pix_stride;
             }
-            Y3_CUDA(launch_conv(s.cfg, s.tmA, s.tmB, ca, sms, st));
+            if (s.cfg.gather) {
+                ca.H = a.H; ca.W = a.W;
+                if (s.cfg.gather == 2) {
+                    ca.src = x;
+                    ca.src_stride = 3;
+                } else {
+                    ca.src = tensor_ptr(*net, s.src);
+                    ca.src_stride = a.pix_stride;
+                }
+                Y3_CUDA(launch_gather(s.cfg, s.tmB, ca, sms, st));
+            } else {
+                Y3_CUDA(launch_conv(s.cfg, s.tmA, s.tmB, ca, sms, st));
+            }
         } else if (s.kind == 2) {
             const TensorInfo& a = net->tensors[s.src];
             const TensorInfo& o = net->tensors[s.dst];
@@ -976,7 +1049,7 @@ int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_
 
 int y3_conv_block_n(int cin, int cout) {
     ConvCfg c;
-    if (!pick_cfg(cin, cout, c)) return 0;
+    if (!pick_cfg(cin, cout, 1, c)) return 0;   // the tile width does not depend on the filter size
     return c.block_n;
 }
 
@@ -987,7 +1060,7 @@ int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int
     if (!ctx || !x || !w_packed || !bias || !out) return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     ConvCfg cfg;
-    if (!pick_cfg(Cin, Cout, cfg)) return fail(Y3_ERR_UNSUPPORTED, "Cin must be a multiple of 32");
+    if (!pick_cfg(Cin, Cout, ksize, cfg) || cfg.gather == 2) return fail(Y3_ERR_UNSUPPORTED, "Cin must be a multiple of 32");
     if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return fail(Y3_ERR_UNSUPPORTED, "k in {1,3}, stride in {1,2}");
     if (!out_fp32 && Cout % 32 != 0) return fail(Y3_ERR_UNSUPPORTED, "bf16 conv outputs need Cout % 32 == 0");
     Step s;
@@ -996,11 +1069,13 @@ int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int
     conv_geometry(H, W, ksize, stride, stride == 1 ? 1 : 0, s.Ho, s.Wo, s.pad_lo, s.pad_hi);
     y3_layer_desc d{};
     d.ksize = ksize; d.stride = stride; d.filters = Cout; d.activation = leaky;
-    int rc;
-    if (ksize == 1 && stride == 1)
-        rc = make_map_2d(ctx->drv, &s.tmA, x, (uint64_t)B * H * W, Cin, x_stride, y3::kBlockM, cfg.swz, false);
-    else
-        rc = make_map_im2col(ctx->drv, &s.tmA, x, B, H, W, Cin, x_stride, ksize, stride, s.pad_lo, s.pad_hi, cfg.swz);
+    int rc = Y3_OK;
+    if (cfg.gather == 0) {
+        if (ksize == 1 && stride == 1)
+            rc = make_map_2d(ctx->drv, &s.tmA, x, (uint64_t)B * H * W, Cin, x_stride, y3::kBlockM, cfg.swz, false);
+        else
+            rc = make_map_im2col(ctx->drv, &s.tmA, x, B, H, W, Cin, x_stride, ksize, stride, s.pad_lo, s.pad_hi, cfg.swz);
+    }
     if (rc) return rc;
     const int cout_pad = ((Cout + cfg.block_n - 1) / cfg.block_n) * cfg.block_n;
     const uint64_t K = (uint64_t)ksize * ksize * Cin;
@@ -1013,7 +1088,35 @@ int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int
     ca.out = out;
     ca.out_stride = out_stride;
     ca.out_fp32 = out_fp32;
-    Y3_CUDA(launch_conv(cfg, s.tmA, s.tmB, ca, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
+    if (cfg.gather) {
+        ca.src = x; ca.src_stride = x_stride; ca.H = H; ca.W = W;
+        Y3_CUDA(launch_gather(cfg, s.tmB, ca, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
+    } else {
+        Y3_CUDA(launch_conv(cfg, s.tmA, s.tmB, ca, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
+    }
+    return Y3_OK;
+}
+
+int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const void* w_packed, const float* bias,
+                       int stride, int leaky, void* out, int64_t out_stride, void* stream) {
+    (void)cudaGetLastError();
+    if (!ctx || !x || !w_packed || !bias || !out) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    ConvCfg cfg;
+    pick_cfg(3, 32, 3, cfg);
+    Step s;
+    s.cfg = cfg;
+    conv_geometry(H, W, 3, stride, 1, s.Ho, s.Wo, s.pad_lo, s.pad_hi);
+    y3_layer_desc d{};
+    d.ksize = 3; d.stride = stride; d.filters = 32; d.activation = leaky;
+    int rc = make_map_2d(ctx->drv, &s.tmB, w_packed, 32, 64, 64, 32, 128, true);
+    if (rc) return rc;
+    y3::ConvArgs ca = conv_args(s, d, 3, B);
+    ca.bias = bias;
+    ca.out = out;
+    ca.out_stride = out_stride;
+    ca.src = x; ca.src_stride = 3; ca.H = H; ca.W = W;
+    Y3_CUDA(launch_gather(cfg, s.tmB, ca, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
     return Y3_OK;
 }
 
