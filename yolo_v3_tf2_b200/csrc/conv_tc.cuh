@@ -191,7 +191,11 @@ struct ConvSmem {
     static constexpr int TOTAL = 1024 /*align slack*/ + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
 };
 
-template <int BLOCK_N, int SWZ, int STAGES>
+// CLUSTER == 2: two CTAs of a cluster work on two adjacent M tiles of the same N tile.  Each loads its own A tile and
+// HALF of the weight tile, multicast into both CTAs' shared memory, so every SM issues 128 + BLOCK_N/2 TMA rows per
+// K block instead of 128 + BLOCK_N (the per-SM TMA issue rate is what bounds the 3x3 layers).  A stage may be refilled
+// only after BOTH CTAs' MMAs have read it, so tcgen05.commit arrives on the empty barrier of both CTAs (count 2).
+template <int BLOCK_N, int SWZ, int STAGES, int CLUSTER>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
     using S = ConvSmem<BLOCK_N, SWZ, STAGES>;
@@ -218,7 +222,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    // work items: (group of CLUSTER adjacent M tiles) x (N tile); every CTA of a cluster walks the same sequence
+    const int cta_rank = (CLUSTER > 1) ? (int)cluster_ctarank() : 0;
+    const int num_tiles = ((p.tiles_m + CLUSTER - 1) / CLUSTER) * p.tiles_n;
+    const int first_tile = (int)blockIdx.x / CLUSTER;
+    const int tile_step = (int)gridDim.x / CLUSTER;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -227,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CLUSTER);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -241,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -255,8 +264,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         const int hw = p.Ho * p.Wo;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        auto load_b = [&](int st, int kcoord, int n0) {
+            if (CLUSTER == 1) {
+                tma_load_2d(smem_b + st * S::B_BYTES, &tmB, full_bar(st), kcoord, n0);
+            } else {
+                constexpr int HALF = BLOCK_N / CLUSTER;
+                tma_load_2d_mc(smem_b + st * S::B_BYTES + cta_rank * (HALF * SWZ), &tmB, full_bar(st), kcoord,
+                               n0 + cta_rank * HALF, (uint16_t)((1u << CLUSTER) - 1u));
+            }
+        };
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
+            const int tm = tmg * CLUSTER + cta_rank;
             const int m0 = tm * kBlockM;
             const int n0 = tn * BLOCK_N;
             int kcoord = 0;   // K coordinate of the weight tile
@@ -275,7 +294,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
                                 tma_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), c0, cw, ch, cn,
                                                    (uint16_t)sx, (uint16_t)r);
-                                tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, full_bar(stage), kcoord, n0);
+                                load_b(stage, kcoord, n0);
                             }
                             kcoord += BLOCK_K;
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -288,7 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (leader) {
                         mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
                         tma_load_2d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), kcoord, m0);
-                        tma_load_2d(smem_b + stage * S::B_BYTES, &tmB, full_bar(stage), kcoord, n0);
+                        load_b(stage, kcoord, n0);
                     }
                     kcoord += BLOCK_K;
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -305,7 +324,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         int j = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
             const int acc = j & 1;
             mbar_wait(tempty_bar(acc), (uint32_t)(((j >> 1) & 1) ^ 1), 0x200 + acc);
             tc_fence_after();
@@ -323,7 +342,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                   (uint32_t)((kb | k) != 0));
                     }
-                    umma_commit(empty_bar(stage));   // smem slot reusable once these MMAs have read it
+                    // smem slot reusable once these MMAs have read it (in a cluster: tell both producers)
+                    if (CLUSTER == 1) umma_commit(empty_bar(stage));
+                    else umma_commit_mc(empty_bar(stage), (uint16_t)((1u << CLUSTER) - 1u));
                     if (kb == p.num_k_blocks - 1) umma_commit(tfull_bar(acc));
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -336,10 +357,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         float* xp = xpose + (warp - 4) * (32 * 33);
         int j = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
             if ((j % kConvEpiGroups) != eg) continue;
             const int acc = j & 1;
-            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
+            const int tm = tmg * CLUSTER + cta_rank;
             mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -352,6 +374,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it / arrive on it
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "conv_first.cuh"
 #include "conv_gather.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 #include "decode.cuh"
 #include "nms.cuh"
 #include "ptx.cuh"
@@ -112,6 +114,8 @@ int make_map_im2col(const Driver& d, CUtensorMap* tm, const void* base, int N, i
 struct ConvCfg {
     int block_n, swz, stages;
     int gather;   // 0: TMA-fed A operand, 1: software im2col (Cin == 32, 3x3), 2: fp32 3-channel stem (hi/lo split)
+    int cluster;  // 1: single CTA; 2: CTA pairs share the weight tile through TMA multicast (cta_group::1 MMAs);
+                  // 3: CTA pairs issue cta_group::2 MMAs on 256 x BLOCK_N tiles (each CTA stages half of the weights)
 };
 
 int pick_block_n(int cout) {
@@ -123,11 +127,14 @@ int pick_block_n(int cout) {
 
 bool pick_cfg(int cin, int cout, int ksize, ConvCfg& c) {
     c.gather = 0;
+    static const int cluster_env = []() { const char* e = getenv("Y3_CLUSTER"); return e ? atoi(e) : 3; }();
+    c.cluster = (cluster_env == 2) ? 2 : 1;
     if (cin == 3 && ksize == 3 && cout == 32) {   // stem: one 64-wide K block (27 hi + 27 lo), weights resident
         c.block_n = 32; c.swz = 128; c.stages = 8; c.gather = 2;
         return true;
     }
-    if (cin == 32 && ksize == 3 && cout <= 128) {   // 64-byte rows: TMA row rate bound -> software im2col
+    static const bool gather32 = []() { const char* e = getenv("Y3_GATHER_CIN32"); return e && e[0] == '1'; }();
+    if (gather32 && cin == 32 && ksize == 3 && cout <= 128) {   // optional software-im2col path for 64-byte rows
         c.block_n = pick_block_n(cout); c.swz = 64; c.stages = 8; c.gather = 1;
         return true;
     }
@@ -137,45 +144,100 @@ bool pick_cfg(int cin, int cout, int ksize, ConvCfg& c) {
     c.block_n = pick_block_n(cout);
     if (c.swz == 128) c.stages = (c.block_n == 256) ? 4 : (c.block_n == 128 ? 6 : 8);
     else c.stages = 8;
+    if (cluster_env == 3 && c.swz == 128 && c.block_n >= 128) {
+        c.cluster = 3;
+        c.stages = (c.block_n == 256) ? 6 : 8;
+    }
     return true;
 }
 
-template <int BN, int SWZ, int ST>
+template <int BN, int SWZ, int ST, int CL>
 cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& args, int sms,
                           cudaStream_t st) {
     using S = y3::ConvSmem<BN, SWZ, ST>;
     static_assert(S::TOTAL <= 232448, "shared memory budget");
-    auto kern = y3::conv_tc_kernel<BN, SWZ, ST>;
+    auto kern = y3::conv_tc_kernel<BN, SWZ, ST, CL>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int tiles = args.tiles_m * args.tiles_n;
-    const int grid = std::max(1, std::min(tiles, sms));
-    kern<<<grid, y3::kConvThreads, S::TOTAL, st>>>(ta, tb, args);
-    return cudaGetLastError();
+    const int work = ((args.tiles_m + CL - 1) / CL) * args.tiles_n;   // (groups of CL M tiles) x N tiles
+    int grid = std::max(1, std::min(work, sms / CL)) * CL;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(y3::kConvThreads);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, args);
+}
+
+template <int CL>
+cudaError_t launch_conv_cl(const ConvCfg& c, const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& a,
+                           int sms, cudaStream_t st) {
+    if (c.swz == 128) {
+        switch (c.block_n) {
+            case 32: return launch_conv_t<32, 128, 8, CL>(ta, tb, a, sms, st);
+            case 64: return launch_conv_t<64, 128, 8, CL>(ta, tb, a, sms, st);
+            case 128: return launch_conv_t<128, 128, 6, CL>(ta, tb, a, sms, st);
+            case 256: return launch_conv_t<256, 128, 4, CL>(ta, tb, a, sms, st);
+        }
+    } else {
+        switch (c.block_n) {
+            case 32: return launch_conv_t<32, 64, 8, CL>(ta, tb, a, sms, st);
+            case 64: return launch_conv_t<64, 64, 8, CL>(ta, tb, a, sms, st);
+            case 128: return launch_conv_t<128, 64, 8, CL>(ta, tb, a, sms, st);
+            case 256: return launch_conv_t<256, 64, 8, CL>(ta, tb, a, sms, st);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int BN, int ST>
+cudaError_t launch_conv2_t(const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& args, int sms,
+                           cudaStream_t st) {
+    using S = y3::Conv2Smem<BN, 128, ST>;
+    static_assert(S::TOTAL <= 232448, "shared memory budget");
+    auto kern = y3::conv_tc2_kernel<BN, 128, ST>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int work = ((args.tiles_m + 1) / 2) * args.tiles_n;
+    int grid = std::max(1, std::min(work, sms / 2)) * 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(y3::kConvThreads);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, args);
 }
 
 cudaError_t launch_conv(const ConvCfg& c, const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& a, int sms,
                         cudaStream_t st) {
-    if (c.swz == 128) {
-        switch (c.block_n) {
-            case 32: return launch_conv_t<32, 128, 8>(ta, tb, a, sms, st);
-            case 64: return launch_conv_t<64, 128, 8>(ta, tb, a, sms, st);
-            case 128: return launch_conv_t<128, 128, 6>(ta, tb, a, sms, st);
-            case 256: return launch_conv_t<256, 128, 4>(ta, tb, a, sms, st);
-        }
-    } else {
-        switch (c.block_n) {
-            case 32: return launch_conv_t<32, 64, 8>(ta, tb, a, sms, st);
-            case 64: return launch_conv_t<64, 64, 8>(ta, tb, a, sms, st);
-            case 128: return launch_conv_t<128, 64, 8>(ta, tb, a, sms, st);
-            case 256: return launch_conv_t<256, 64, 8>(ta, tb, a, sms, st);
-        }
+    if (c.cluster == 3) {   // CTA pair, cta_group::2 MMA
+        if (c.block_n == 256) return launch_conv2_t<256, 6>(ta, tb, a, sms, st);
+        if (c.block_n == 128) return launch_conv2_t<128, 8>(ta, tb, a, sms, st);
+        return cudaErrorInvalidValue;
     }
-    return cudaErrorInvalidValue;
+    return c.cluster == 2 ? launch_conv_cl<2>(c, ta, tb, a, sms, st) : launch_conv_cl<1>(c, ta, tb, a, sms, st);
 }
 
 template <int BN, int SWZ, int ST, bool STEM>
@@ -617,7 +679,7 @@ int build_maps(y3_net& n) {
         }
         if (rc) return rc;
         const uint64_t K = (s.cfg.gather == 2) ? 64 : (uint64_t)d.ksize * d.ksize * a.C;
-        rc = make_map_2d(n.ctx->drv, &s.tmB, w.w, w.cout_pad, K, K, s.cfg.block_n, s.cfg.swz, true);
+        rc = make_map_2d(n.ctx->drv, &s.tmB, w.w, w.cout_pad, K, K, s.cfg.block_n / (s.cfg.gather ? 1 : (s.cfg.cluster >= 2 ? 2 : 1)), s.cfg.swz, true);
         if (rc) return rc;
     }
     n.maps_built = true;
@@ -1079,7 +1141,7 @@ int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int
     if (rc) return rc;
     const int cout_pad = ((Cout + cfg.block_n - 1) / cfg.block_n) * cfg.block_n;
     const uint64_t K = (uint64_t)ksize * ksize * Cin;
-    rc = make_map_2d(ctx->drv, &s.tmB, w_packed, cout_pad, K, K, cfg.block_n, cfg.swz, true);
+    rc = make_map_2d(ctx->drv, &s.tmB, w_packed, cout_pad, K, K, cfg.block_n / (cfg.gather ? 1 : (cfg.cluster >= 2 ? 2 : 1)), cfg.swz, true);
     if (rc) return rc;
     y3::ConvArgs ca = conv_args(s, d, Cin, B);
     ca.bias = bias;
