@@ -21,6 +21,11 @@ NCLASSES = 80
 GFLOP_PER_IMAGE_416 = 65.864          # SURVEY.md section 8d (2*MAC over the 75 convs, C=80)
 
 
+def workload_name(size, batch):
+    return (f"YOLOv3 Darknet-53 C=80 {size}x{size} batch {batch}/GPU, random-init (Keras defaults), "
+            f"forward + decode + NMS(max 100, iou 0.5, score 0.1) + gather")
+
+
 def conv_flops(model, H, W):
     from yolo_v3_tf2_b200 import _lib
     p = model.plan(H, W, 1)
@@ -123,8 +128,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "images/sec (416^2, backbone+decode+NMS)", "value": v, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"YOLOv3 Darknet-53 C=80 {args.size}x{args.size}, random-init, forward+decode+NMS",
-                       "note": "CPU restatement of the reference (TensorFlow absent); bounded sample per step"},
+            "config": {"workload": workload_name(args.size, args.batch), "images_per_gpu": args.batch,
+                       "note": f"reference arm: CPU restatement of the reference (TensorFlow 2.8.1 is not installable here), "
+                               f"each step is a bounded sample of {sample_b} images of that workload"},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"{sample_b} images of {args.size}x{args.size} per step x {args.steps} steps"},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -281,9 +287,7 @@ def main():
             "metric": "images/sec (416^2, backbone+decode+NMS)", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"YOLOv3 Darknet-53 C=80 {S}x{S} batch {B}/GPU, random-init (Keras defaults), "
-                                   f"forward + decode + NMS(max 100, iou 0.5, score 0.1) + gather",
-                       "images_per_gpu": B, "l2": "inputs rotate over 3 device buffers; each step streams a ~1 GB "
+            "config": {"workload": workload_name(S, B), "images_per_gpu": B, "l2": "inputs rotate over 3 device buffers; each step streams a ~1 GB "
                                                   "activation arena (>> 126 MB L2) so no step starts with a warm L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 3 * 4,

@@ -11,7 +11,7 @@ $SMALL > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 260 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "ncu launches exit $?"
 $SMALL > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'conv_tc_kernelILi256ELi128' -s 40 -c 2 -o gpurun_out/${TAG}_prof_conv $SMALL > gpurun_out/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'conv_tc2_kernel' -s 108 -c 2 -o gpurun_out/${TAG}_prof_conv $SMALL > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "ncu conv exit $?"
 $SMALL > gpurun_out/${TAG}_plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'decode_kernel|nms_kernel' -s 6 -c 2 -o gpurun_out/${TAG}_prof_post $SMALL > gpurun_out/${TAG}_ncu3.log 2>&1

@@ -34,3 +34,15 @@ for i, (layer, _) in enumerate(runs[0]):
         tot_fl += fl
     tot_ms += ms
 print(f"total {tot_ms:.3f} ms  {tot_fl / tot_ms / 1e9:.1f} TFLOP/s  {B / tot_ms * 1e3:.0f} img/s (forward only)")
+
+# whole forward without per-layer events (what PDL / launch overlap actually buys)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+outs = m(x)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(20):
+    m(x, outs=outs)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 20
+print(f"whole forward, back-to-back launches: {ms:.3f} ms  {tot_fl / ms / 1e9:.1f} TFLOP/s  {B / ms * 1e3:.0f} img/s")

@@ -252,6 +252,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CLUSTER > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
+    // from here on we touch activations it wrote (and buffers it may still be reading), so wait for it to finish.
+    pdl_launch_dependents();
+    pdl_wait();
 
     // The two single-thread roles run their loops with the WHOLE warp (uniform control flow, so the compiler keeps
     // addresses / descriptors / barrier phases in uniform registers) and predicate only the issuing instructions on

@@ -86,6 +86,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
+    // from here on we touch activations it wrote (and buffers it may still be reading), so wait for it to finish.
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================

@@ -151,6 +151,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor is still running; pdl_wait() blocks until the predecessor grid has completed and its memory is
+// visible, pdl_launch_dependents() lets the successor start its own prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

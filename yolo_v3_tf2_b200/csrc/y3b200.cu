@@ -111,6 +111,9 @@ int make_map_im2col(const Driver& d, CUtensorMap* tm, const void* base, int N, i
 // ------------------------------------------------------------------------------------------------
 // conv tile configuration + launch
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch between consecutive conv layers (Y3_PDL=0 disables)
+const bool g_use_pdl = []() { const char* e = getenv("Y3_PDL"); return !(e && e[0] == '0'); }();
+
 struct ConvCfg {
     int block_n, swz, stages;
     int gather;   // 0: TMA-fed A operand, 1: software im2col (Cin == 32, 3x3), 2: fp32 3-channel stem (hi/lo split)
@@ -170,13 +173,15 @@ cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const y3
     cfg.blockDim = dim3(y3::kConvThreads);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kern, ta, tb, args);
 }
 
@@ -220,13 +225,15 @@ cudaError_t launch_conv2_t(const CUtensorMap& ta, const CUtensorMap& tb, const y
     cfg.blockDim = dim3(y3::kConvThreads);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kern, ta, tb, args);
 }
 
@@ -253,8 +260,17 @@ cudaError_t launch_gather_t(const CUtensorMap& tb, const y3::ConvArgs& args, int
         configured = smem;
     }
     const int grid = std::max(1, std::min(args.tiles_m, sms));
-    kern<<<grid, y3::gather_threads<STEM ? 2 : 1>(), smem, st>>>(tb, args);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(y3::gather_threads<STEM ? 2 : 1>());
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, tb, args);
 }
 
 cudaError_t launch_gather(const ConvCfg& c, const CUtensorMap& tb, const y3::ConvArgs& a, int sms, cudaStream_t st) {
