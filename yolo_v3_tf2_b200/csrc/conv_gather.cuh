@@ -25,7 +25,7 @@ template <int BLOCK_N, int SWZ, int STAGES>
 struct GatherSmem {
     static constexpr int A_BYTES = kBlockM * SWZ;
     static constexpr int B_BYTES = BLOCK_N * SWZ;
-    static constexpr int XPOSE_BYTES = kGatherEpiGroups * 4 * 32 * 33 * 4;
+    static constexpr int XPOSE_BYTES = kGatherEpiGroups * 4 * kXposeWarpFloats * 4;
     static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
     static constexpr int total(int num_k_blocks) {
         return 1024 + STAGES * A_BYTES + num_k_blocks * B_BYTES + XPOSE_BYTES + BAR_BYTES;
@@ -158,7 +158,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
         // ===================== epilogue groups =====================
         const int eg = (warp - 4) >> 2;
         const int q = warp & 3;
-        float* xp = xpose + (warp - 4) * (32 * 33);
+        float* xp = xpose + (warp - 4) * kXposeWarpFloats;
         for (int j = eg; j < my_tiles; j += NEPI) {
             const int acc = j & 1;
             const int tile = blockIdx.x + j * gridDim.x;

@@ -64,6 +64,9 @@ constexpr int kBlockM = 128;
 // fp32 outputs (the 3*(5+C)-channel heads, pixel stride not a multiple of 4 floats) store 32 consecutive floats of
 // one pixel per instruction.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kXposePitch = 36;                       // floats per transpose-tile row: 144 B keeps 16-byte alignment
+constexpr int kXposeWarpFloats = 32 * kXposePitch;    // and makes both the 128-bit writes and reads conflict free
+
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn, uint32_t t_row, int q, int lane,
                                               float* xp) {
@@ -75,6 +78,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
     const int hw = p.Ho * p.Wo;
     const bool has_res = p.residual != nullptr;
     const int nchunks = min(BLOCK_N / 32, (p.cout - n_base + 31) / 32);
+    const float slope = p.leaky ? 0.1f : 1.0f;   // LeakyReLU(0.1)(x) = max(x, 0.1x); slope 1 makes it the identity
+    float4* xrow = reinterpret_cast<float4*>(xp + lane * kXposePitch);
 
     // residual tile rows of this lane (4 rows x 16 B per chunk), prefetched one chunk ahead
     uint4 rcur[4], rnext[4];
@@ -105,25 +110,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
             for (int j = 0; j < 8; ++j) bias4[j] = __ldg(bp + j);
         }
         tmem_ld_wait();
-        {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 b4 = bias4[j];
-                float f0 = __uint_as_float(v[4 * j + 0]) + b4.x;
-                float f1 = __uint_as_float(v[4 * j + 1]) + b4.y;
-                float f2 = __uint_as_float(v[4 * j + 2]) + b4.z;
-                float f3 = __uint_as_float(v[4 * j + 3]) + b4.w;
-                if (p.leaky) {
-                    f0 = f0 > 0.f ? f0 : 0.1f * f0;
-                    f1 = f1 > 0.f ? f1 : 0.1f * f1;
-                    f2 = f2 > 0.f ? f2 : 0.1f * f2;
-                    f3 = f3 > 0.f ? f3 : 0.1f * f3;
-                }
-                xp[lane * 33 + 4 * j + 0] = f0;
-                xp[lane * 33 + 4 * j + 1] = f1;
-                xp[lane * 33 + 4 * j + 2] = f2;
-                xp[lane * 33 + 4 * j + 3] = f3;
-            }
+        for (int j = 0; j < 8; ++j) {
+            float4 f;
+            f.x = __uint_as_float(v[4 * j + 0]) + bias4[j].x;
+            f.y = __uint_as_float(v[4 * j + 1]) + bias4[j].y;
+            f.z = __uint_as_float(v[4 * j + 2]) + bias4[j].z;
+            f.w = __uint_as_float(v[4 * j + 3]) + bias4[j].w;
+            f.x = fmaxf(f.x, slope * f.x);
+            f.y = fmaxf(f.y, slope * f.y);
+            f.z = fmaxf(f.z, slope * f.z);
+            f.w = fmaxf(f.w, slope * f.w);
+            xrow[j] = f;
         }
         __syncwarp();
         if (!p.out_fp32) {
@@ -133,9 +131,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
                 const int r = it * 8 + sub;
                 const int m = m_w + r;
                 if (m < p.M) {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = xp[r * 33 + seg * 8 + e];
+                    const float4* src = reinterpret_cast<const float4*>(xp + r * kXposePitch + seg * 8);
+                    const float4 lo = src[0], hi = src[1];
+                    float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
                     if (has_res) {
                         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rcur[it]);
 #pragma unroll
@@ -173,7 +171,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
             float* dst = of + (long long)m_w * p.out_stride + ncol + lane;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-                if (r < rows && col_ok) dst[(long long)r * p.out_stride] = xp[r * 33 + lane];
+                if (r < rows && col_ok) dst[(long long)r * p.out_stride] = xp[r * kXposePitch + lane];
             }
         }
         __syncwarp();
@@ -186,7 +184,7 @@ struct ConvSmem {
     static constexpr int B_BYTES = BLOCK_N * SWZ;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose tile
+    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * kXposeWarpFloats * 4;   // per-epilogue-warp 32 x 36 fp32 transpose tile
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16; // full/empty + tmem full/empty + tmem ptr
     static constexpr int TOTAL = 1024 /*align slack*/ + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
 };
@@ -359,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue groups =====================
         const int eg = (warp - 4) >> 2;         // group: owns accumulator stage eg
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        float* xp = xpose + (warp - 4) * (32 * 33);
+        float* xp = xpose + (warp - 4) * kXposeWarpFloats;
         int j = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
             if ((j % kConvEpiGroups) != eg) continue;

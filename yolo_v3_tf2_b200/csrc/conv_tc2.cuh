@@ -24,7 +24,7 @@ struct Conv2Smem {
     static constexpr int B_BYTES = (BLOCK_N / 2) * SWZ;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * 32 * 33 * 4;
+    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * kXposeWarpFloats * 4;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int TOTAL = 1024 + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
 };
@@ -178,7 +178,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ===================== epilogue groups (both CTAs, each drains its own 128 TMEM lanes) =====================
         const int eg = (warp - 4) >> 2;
         const int q = warp & 3;
-        float* xp = xpose + (warp - 4) * (32 * 33);
+        float* xp = xpose + (warp - 4) * kXposeWarpFloats;
         int j = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
             if ((j % kConvEpiGroups) != eg) continue;

@@ -114,6 +114,10 @@ int make_map_im2col(const Driver& d, CUtensorMap* tm, const void* base, int N, i
 // programmatic dependent launch between consecutive conv layers (Y3_PDL=0 disables)
 const bool g_use_pdl = []() { const char* e = getenv("Y3_PDL"); return !(e && e[0] == '0'); }();
 
+constexpr int fit_stages(int stage_bytes);
+constexpr int st1(int bn, int swz);
+constexpr int st2(int bn);
+
 struct ConvCfg {
     int block_n, swz, stages;
     int gather;   // 0: TMA-fed A operand, 1: software im2col (Cin == 32, 3x3), 2: fp32 3-channel stem (hi/lo split)
@@ -145,11 +149,10 @@ bool pick_cfg(int cin, int cout, int ksize, ConvCfg& c) {
     else if (cin % 32 == 0) c.swz = 64;
     else return false;
     c.block_n = pick_block_n(cout);
-    if (c.swz == 128) c.stages = (c.block_n == 256) ? 4 : (c.block_n == 128 ? 6 : 8);
-    else c.stages = 8;
+    c.stages = st1(c.block_n, c.swz);
     if (cluster_env == 3 && c.swz == 128 && c.block_n >= 128) {
         c.cluster = 3;
-        c.stages = (c.block_n == 256) ? 6 : 8;
+        c.stages = st2(c.block_n);
     }
     return true;
 }
@@ -185,22 +188,30 @@ cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const y3
     return cudaLaunchKernelEx(&cfg, kern, ta, tb, args);
 }
 
+// deepest pipeline (at most 8 stages) that fits next to the transpose tiles, barriers and alignment slack
+constexpr int fit_stages(int stage_bytes) {
+    int st = (232448 - 1024 - y3::kConvEpiGroups * 4 * y3::kXposeWarpFloats * 4 - 256) / stage_bytes;
+    return st > 8 ? 8 : st;
+}
+constexpr int st1(int bn, int swz) { return fit_stages((y3::kBlockM + bn) * swz); }        // single-CTA tile
+constexpr int st2(int bn) { return fit_stages((y3::kBlockM + bn / 2) * 128); }             // CTA-pair tile
+
 template <int CL>
 cudaError_t launch_conv_cl(const ConvCfg& c, const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& a,
                            int sms, cudaStream_t st) {
     if (c.swz == 128) {
         switch (c.block_n) {
-            case 32: return launch_conv_t<32, 128, 8, CL>(ta, tb, a, sms, st);
-            case 64: return launch_conv_t<64, 128, 8, CL>(ta, tb, a, sms, st);
-            case 128: return launch_conv_t<128, 128, 6, CL>(ta, tb, a, sms, st);
-            case 256: return launch_conv_t<256, 128, 4, CL>(ta, tb, a, sms, st);
+            case 32: return launch_conv_t<32, 128, st1(32, 128), CL>(ta, tb, a, sms, st);
+            case 64: return launch_conv_t<64, 128, st1(64, 128), CL>(ta, tb, a, sms, st);
+            case 128: return launch_conv_t<128, 128, st1(128, 128), CL>(ta, tb, a, sms, st);
+            case 256: return launch_conv_t<256, 128, st1(256, 128), CL>(ta, tb, a, sms, st);
         }
     } else {
         switch (c.block_n) {
-            case 32: return launch_conv_t<32, 64, 8, CL>(ta, tb, a, sms, st);
-            case 64: return launch_conv_t<64, 64, 8, CL>(ta, tb, a, sms, st);
-            case 128: return launch_conv_t<128, 64, 8, CL>(ta, tb, a, sms, st);
-            case 256: return launch_conv_t<256, 64, 8, CL>(ta, tb, a, sms, st);
+            case 32: return launch_conv_t<32, 64, st1(32, 64), CL>(ta, tb, a, sms, st);
+            case 64: return launch_conv_t<64, 64, st1(64, 64), CL>(ta, tb, a, sms, st);
+            case 128: return launch_conv_t<128, 64, st1(128, 64), CL>(ta, tb, a, sms, st);
+            case 256: return launch_conv_t<256, 64, st1(256, 64), CL>(ta, tb, a, sms, st);
         }
     }
     return cudaErrorInvalidValue;
@@ -240,8 +251,8 @@ cudaError_t launch_conv2_t(const CUtensorMap& ta, const CUtensorMap& tb, const y
 cudaError_t launch_conv(const ConvCfg& c, const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& a, int sms,
                         cudaStream_t st) {
     if (c.cluster == 3) {   // CTA pair, cta_group::2 MMA
-        if (c.block_n == 256) return launch_conv2_t<256, 6>(ta, tb, a, sms, st);
-        if (c.block_n == 128) return launch_conv2_t<128, 8>(ta, tb, a, sms, st);
+        if (c.block_n == 256) return launch_conv2_t<256, st2(256)>(ta, tb, a, sms, st);
+        if (c.block_n == 128) return launch_conv2_t<128, st2(128)>(ta, tb, a, sms, st);
         return cudaErrorInvalidValue;
     }
     return c.cluster == 2 ? launch_conv_cl<2>(c, ta, tb, a, sms, st) : launch_conv_cl<1>(c, ta, tb, a, sms, st);
@@ -573,6 +584,20 @@ int plan_net(y3_net& n) {
             if (tc_ok && s.cfg.gather == 2 && (d.src0 != 0 || residual[i] >= 0 || fused_up[i] || n.tensors[writes[i]].fp32_output))
                 tc_ok = false;
             if (tc_ok && s.cfg.gather != 2 && d.src0 == 0) tc_ok = false;
+            if (tc_ok && s.cfg.cluster == 3 && s.cfg.block_n == 256) {
+                // tile-count quantisation: a layer runs ceil(work / clusters) rounds of tiles; when 256-wide tiles
+                // leave most clusters idle in the last round (13x13 layers: 172 tiles on 74 clusters = 3 rounds,
+                // 23 % idle) 128-wide tiles are cheaper even though every A tile is then fetched twice.
+                const long long M = (long long)n.max_batch * s.Ho * s.Wo;
+                const long long pairs = ((M + y3::kBlockM - 1) / y3::kBlockM + 1) / 2;
+                const long long clusters = std::max(1, n.ctx->sms / 2);
+                const long long r256 = (pairs * ((d.filters + 255) / 256) + clusters - 1) / clusters;
+                const long long r128 = (pairs * ((d.filters + 127) / 128) + clusters - 1) / clusters;
+                if ((double)r128 * 0.5 * 1.10 < (double)r256 * 0.97) {
+                    s.cfg.block_n = 128;
+                    s.cfg.stages = st2(128);
+                }
+            }
             if (tc_ok) {
                 if (!n.tensors[writes[i]].fp32_output && d.filters % 32 != 0)
                     return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": bf16 conv outputs need filters % 32 == 0");
