@@ -151,6 +151,11 @@ int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const v
 int y3_dbg_tma_tile(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, int ksize, int stride,
                     int swizzle, int tap_r, int tap_s, int c0, int m0, void* out_bytes, void* stream);
 
+/* Debug: D[128,64] = X[shift .. shift+128, :] * W^T with X (rows x swizzle/2, bf16) staged once by TMA and the UMMA
+ * A descriptor advanced by `shift` swizzle rows (base_off_mode 1 also sets the descriptor's base-offset field). */
+int y3_dbg_umma_shift(y3_ctx* ctx, const void* x, int rows, const void* w, int swizzle, int shift, int base_off_mode,
+                      float* out, void* stream);
+
 /* last device-side watchdog code (0 = none) */
 int y3_watchdog_code(y3_ctx* ctx);
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "y3_conv_block_n": (_i, [_i, _i]),
     "y3_conv2d_bf16": (_i, [_p, _p, _i, _i, _i, _i, _i64, _p, _p, _i, _i, _i, _i, _p, _i64, _p, _i64, _i, _i, _p]),
     "y3_conv2d_stem_f32": (_i, [_p, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i64, _p]),
+    "y3_dbg_umma_shift": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p]),
     "y3_dbg_tma_tile": (_i, [_p, _p, _i, _i, _i, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "y3_watchdog_code": (_i, [_p]),
 }

@@ -48,6 +48,8 @@ struct ConvArgs {
     const void* src;       // bf16 NHWC view, or the fp32 [B,H,W,3] image for the stem
     long long src_stride;  // elements between consecutive input pixels
     int H, W;              // input spatial size
+    int dbg;               // profiling knobs (env Y3_DBG): 1 epilogue drains TMEM only, 2 no global stores,
+                           // 4 producer skips the A loads, 8 no MMAs are issued (results are garbage)
 };
 
 constexpr int kConvEpiGroups = 2;   // epilogue warp groups; group g drains accumulator stage g (tiles j % 2 == g)
@@ -110,6 +112,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
             for (int j = 0; j < 8; ++j) bias4[j] = __ldg(bp + j);
         }
         tmem_ld_wait();
+        if (p.dbg & 1) continue;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 f;
@@ -147,7 +150,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
                     const uint4 o = *reinterpret_cast<uint4*>(o2);
-                    if (!p.upsample) {
+                    if (p.dbg & 2) {
+                        if (o.x == 0x12345678u && o.y == 0x9abcdef0u) ob[0] = __float2bfloat16(0.f);   // keep the math alive
+                    } else if (!p.upsample) {
                         *reinterpret_cast<uint4*>(ob + (long long)m * p.out_stride + ncol + seg * 8) = o;
                     } else {
                         const int n = m / hw;
@@ -380,6 +385,76 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// Debug helper: does a UMMA smem descriptor accept a start address that is a whole number of swizzle rows (but not a
+// multiple of the 8-row swizzle period) into a TMA-written SWIZZLE_<SWZ>B tile?  Loads X[rows][SWZ/2] and W[64][SWZ/2],
+// issues D[128,64] = X[shift .. shift+128) * W^T with the A descriptor advanced by `shift` rows, optionally with the
+// descriptor's base-offset field set to the row phase, and writes D (fp32) out.
+template <int SWZ>
+__global__ void umma_shift_test_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                       int rows, int shift, int base_off_mode, float* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int BLOCK_K = SWZ / 2;
+    const uint32_t x_bytes = (uint32_t)rows * SWZ;
+    const uint32_t smem_x = smem_base;
+    const uint32_t smem_w = smem_base + (uint32_t)((rows + 127) / 128) * 128u * SWZ;
+    const uint32_t bar = smem_w + 64 * SWZ;
+    const uint32_t bar2 = bar + 8;
+    const uint32_t tptr = bar + 16;
+    uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tptr_gen = reinterpret_cast<volatile uint32_t*>(gen + (tptr - smem_base));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar2, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tptr, 64);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tptr_gen;
+    if (threadIdx.x == 0) {
+        // X arrives as whole 128-row boxes (rows past the tensor are zero filled but still counted), then W
+        const int nbox = (rows + 127) / 128;
+        mbar_arrive_expect_tx(bar, (uint32_t)nbox * 128u * SWZ + 64u * SWZ);
+        for (int b = 0; b < nbox; ++b) tma_load_2d(smem_x + b * 128 * SWZ, &tmX, bar, 0, b * 128);
+        tma_load_2d(smem_w, &tmW, bar, 0, 0);
+    }
+    mbar_wait(bar, 0, 0x800);
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+        const uint32_t a_addr = smem_x + (uint32_t)shift * SWZ;
+        uint64_t adesc = make_smem_desc<SWZ>(a_addr);
+        if (base_off_mode == 1) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+        const uint64_t bdesc = make_smem_desc<SWZ>(smem_w);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
+        umma_commit(bar2);
+    }
+    mbar_wait(bar2, 0, 0x801);
+    tc_fence_after();
+    if (warp < 4) {
+        uint32_t v[32];
+        for (int c = 0; c < 2; ++c) {
+            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+            for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c * 32 + j] = __uint_as_float(v[j]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 64);
     }
 }
 

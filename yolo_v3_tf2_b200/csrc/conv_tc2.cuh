@@ -116,9 +116,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                             if (leader_lane) {
                                 const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-                                if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);
-                                tma2_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, lead_full, c0, cw, ch, cn,
-                                                    (uint16_t)sx, (uint16_t)r);
+                                if (is_leader)
+                                    mbar_arrive_expect_tx(full_bar(stage), (p.dbg & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
+                                if (!(p.dbg & 4))
+                                    tma2_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, lead_full, c0, cw, ch, cn,
+                                                        (uint16_t)sx, (uint16_t)r);
                                 tma2_load_2d(smem_b + stage * S::B_BYTES, &tmB, lead_full, kcoord, nb);
                             }
                             kcoord += BLOCK_K;
@@ -131,8 +133,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                     if (leader_lane) {
                         const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-                        if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);
-                        tma2_load_2d(smem_a + stage * S::A_BYTES, &tmA, lead_full, kcoord, m0);
+                        if (is_leader)
+                            mbar_arrive_expect_tx(full_bar(stage), (p.dbg & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
+                        if (!(p.dbg & 4)) tma2_load_2d(smem_a + stage * S::A_BYTES, &tmA, lead_full, kcoord, m0);
                         tma2_load_2d(smem_b + stage * S::B_BYTES, &tmB, lead_full, kcoord, nb);
                     }
                     kcoord += BLOCK_K;
@@ -162,10 +165,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (leader_lane) {
                         const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
                         const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (S::B_BYTES >> 4));
+                        if (!(p.dbg & 8)) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma2_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                       (uint32_t)((kb | k) != 0));
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma2_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                           (uint32_t)((kb | k) != 0));
+                        }
                         umma2_commit_mc(empty_bar(stage), 3);               // both producers may refill the stage
                         if (kb == p.num_k_blocks - 1) umma2_commit_mc(tfull_bar(acc), 3);   // both epilogues may drain
                     }

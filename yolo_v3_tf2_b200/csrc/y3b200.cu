@@ -747,6 +747,8 @@ y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
     a.cout = d.filters;
     a.leaky = d.activation;
     a.upsample = s.fused_up;
+    static const int dbg = []() { const char* e = getenv("Y3_DBG"); return e ? atoi(e) : 0; }();
+    a.dbg = dbg;
     return a;
 }
 
@@ -1220,6 +1222,33 @@ int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const v
     ca.out_stride = out_stride;
     ca.src = x; ca.src_stride = 3; ca.H = H; ca.W = W;
     Y3_CUDA(launch_gather(cfg, s.tmB, ca, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
+    return Y3_OK;
+}
+
+int y3_dbg_umma_shift(y3_ctx* ctx, const void* x, int rows, const void* w, int swizzle, int shift, int base_off_mode,
+                      float* out, void* stream) {
+    (void)cudaGetLastError();
+    if (!ctx || !x || !w || !out) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (swizzle != 128 && swizzle != 64) return fail(Y3_ERR_INVALID, "swizzle must be 64 or 128");
+    if (rows < shift + 128 || rows > 512) return fail(Y3_ERR_INVALID, "need shift + 128 <= rows <= 512");
+    const int bk = swizzle / 2;
+    CUtensorMap tx, tw;
+    int rc = make_map_2d(ctx->drv, &tx, x, rows, bk, bk, 128, swizzle, false);
+    if (rc) return rc;
+    rc = make_map_2d(ctx->drv, &tw, w, 64, bk, bk, 64, swizzle, true);
+    if (rc) return rc;
+    const int nbox = (rows + 127) / 128;
+    const size_t smem = 1024 + (size_t)nbox * 128 * swizzle + 64 * swizzle + 64;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (swizzle == 128) {
+        Y3_CUDA(cudaFuncSetAttribute(y3::umma_shift_test_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        y3::umma_shift_test_kernel<128><<<1, 128, smem, st>>>(tx, tw, rows, shift, base_off_mode, out);
+    } else {
+        Y3_CUDA(cudaFuncSetAttribute(y3::umma_shift_test_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        y3::umma_shift_test_kernel<64><<<1, 128, smem, st>>>(tx, tw, rows, shift, base_off_mode, out);
+    }
+    Y3_CUDA(cudaGetLastError());
     return Y3_OK;
 }
 
