@@ -73,6 +73,8 @@ typedef struct {
     int32_t chan_offset;      /* channel offset inside the buffer (concat slices) */
     int32_t pix_stride;       /* channels between consecutive pixels of the buffer */
     int32_t block_n, swizzle, stages;   /* tcgen05 tile configuration */
+    int32_t flat;             /* conv: 1 = flat-patch 3x3 kernel (input staged once per channel block, taps = row shifts) */
+    int32_t padded;           /* tensor stored as [B, H+1, W+1, C] with a zero last row / column */
     int64_t arena_offset;     /* byte offset of the buffer inside the activation arena */
 } y3_layer_plan;
 
@@ -139,6 +141,12 @@ int y3_conv_block_n(int cin, int cout);
 int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int64_t x_stride, const void* w_packed,
                    const float* bias, int ksize, int stride, int Cout, int leaky, const void* residual,
                    int64_t res_stride, void* out, int64_t out_stride, int out_fp32, int upsample, void* stream);
+
+/* 3x3 stride-1 'same' conv on a haloed-flat input x_padded [B, H+1, W+1, Cin] (zero last row / column), weights packed
+ * [Cout_pad][Cin/BK][3][3][BK] (BK = 64 if Cin % 64 == 0 else 32); output / residual dense.  Unit-test entry. */
+int y3_conv2d_flat_bf16(y3_ctx* ctx, const void* x_padded, int B, int H, int W, int Cin, const void* w_packed,
+                        const float* bias, int Cout, int leaky, const void* residual, int64_t res_stride, void* out,
+                        int64_t out_stride, void* stream);
 
 /* The 3-channel stem conv (3x3, 32 filters) on the tensor cores: x fp32 [B,H,W,3]; w_packed bf16 [32][64] with the
  * 27 BN-folded weights of output o at columns 0..26 AND 32..58 (the kernel multiplies bf16(x) and the bf16 remainder

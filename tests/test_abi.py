@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_struct_layouts_match_header(built):
     from yolo_v3_tf2_b200 import _lib
     assert C.sizeof(_lib.LayerDesc) == 9 * 4
-    assert C.sizeof(_lib.LayerPlan) == 12 * 4 + 8
+    assert C.sizeof(_lib.LayerPlan) == 14 * 4 + 8
 
 
 def test_no_cpu_fallback(built):

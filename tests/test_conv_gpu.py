@@ -192,3 +192,51 @@ def test_conv_stem_vs_oracle(cuda, B, H, W, stride):
     err = np.abs(got - ref)
     # input precision ~2^-16, output rounded to bf16
     assert (err <= 2.0 ** -8 * np.abs(ref) + 1e-3).all(), err.max()
+
+
+FLAT_CASES = [
+    # (B, H, W, Cin, Cout, leaky, residual)
+    (2, 13, 13, 64, 128, 1, False), (3, 13, 13, 128, 256, 1, True), (2, 26, 26, 256, 512, 1, True),
+    (1, 52, 52, 128, 256, 1, True), (2, 104, 104, 64, 128, 1, True), (1, 208, 208, 32, 64, 1, True),
+    (5, 19, 19, 128, 256, 0, False), (2, 13, 13, 512, 1024, 1, True), (1, 9, 17, 64, 64, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", FLAT_CASES, ids=[str(c) for c in FLAT_CASES])
+def test_conv_flat_vs_oracle(cuda, case):
+    """3x3 stride-1 conv on the zero-haloed flat layout [B, H+1, W+1, C]: one staged patch per 64-channel block, the
+    nine taps are row-shifted UMMA descriptors.  Same tolerance as the im2col-fed kernel."""
+    import torch
+    from yolo_v3_tf2_b200 import _lib
+    from oracle import net_oracle
+    B, H, W, Cin, Cout, leaky, use_res = case
+    ctx = _lib.context()
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    x = bf16_round(rng.standard_normal((B, H, W, Cin)).astype(np.float32))
+    kern = bf16_round((rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32))
+    bias = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    res = bf16_round(rng.standard_normal((B, H, W, Cout)).astype(np.float32)) if use_res else None
+    ref = net_oracle.conv_layer(x, kern, bias, 3, 1, leaky, res)
+    bk = 64 if Cin % 64 == 0 else 32
+    bn = 64 if Cout <= 64 else (128 if Cout <= 128 else 256)
+    cout_pad = ((Cout + bn - 1) // bn) * bn
+    wp = np.zeros((cout_pad, Cin // bk, 3, 3, bk), np.float32)
+    wp[:Cout] = kern.reshape(3, 3, Cin // bk, bk, Cout).transpose(4, 2, 0, 1, 3)
+    wd = torch.from_numpy(wp).cuda().to(torch.bfloat16).contiguous()
+    bd = torch.zeros(cout_pad, dtype=torch.float32, device="cuda")
+    bd[:Cout] = torch.from_numpy(bias).cuda()
+    xpad = np.zeros((B, H + 1, W + 1, Cin), np.float32)
+    xpad[:, :H, :W] = x
+    xd = torch.from_numpy(xpad).cuda().to(torch.bfloat16).contiguous()
+    rd = torch.from_numpy(res).cuda().to(torch.bfloat16).contiguous() if use_res else None
+    od = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.lib().y3_conv2d_flat_bf16(ctx.handle, _lib.ptr(xd), B, H, W, Cin, _lib.ptr(wd), _lib.ptr(bd), Cout, leaky,
+                                              _lib.ptr(rd), Cout, _lib.ptr(od), Cout, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert ctx.watchdog_code() == 0
+    got = od.float().cpu().numpy()
+    assert np.isfinite(got).all(), "unwritten / non-finite outputs"
+    K = 9 * Cin
+    tol = 2.0 ** -8 * np.abs(ref) + 2e-3 * np.sqrt(K) / 32 + 1e-3
+    err = np.abs(got - ref)
+    assert (err <= tol).all(), f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"

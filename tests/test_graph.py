@@ -130,6 +130,11 @@ def test_planner_through_c_abi():
     assert kinds.count(3) == kinds.count(4) == kinds.count(5) == 0   # every add / upsample / concat is fused
     assert sum(1 for l in L if l["fused_add"] >= 0) == 23
     assert sum(1 for l in L if l["fused_upsample"]) == 2
+    # all 32 3x3 stride-1 convs behind a 1x1 conv run the flat-patch kernel on a zero-haloed input
+    assert sum(1 for l in L if l["flat"]) == 32 and sum(1 for l in L if l["padded"]) == 32
+    for i, l in enumerate(g.layers):
+        if L[i]["flat"]:
+            assert l.ksize == 3 and l.stride == 1 and L[l.src0 - 1]["padded"] == 1
     # concat operands live inside the concat buffer: same buffer id, channel offsets 0 and Ca, pixel stride Ca+Cb
     for i, l in enumerate(g.layers):
         if l.op == _lib.OP_CONCAT:

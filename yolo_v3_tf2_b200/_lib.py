@@ -21,7 +21,7 @@ class LayerDesc(C.Structure):
 class LayerPlan(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("H", "W", "C", "kernel", "fused_add", "fused_upsample", "buffer", "chan_offset", "pix_stride",
-                 "block_n", "swizzle", "stages")] + [("arena_offset", C.c_int64)]
+                 "block_n", "swizzle", "stages", "flat", "padded")] + [("arena_offset", C.c_int64)]
 
 
 class Y3Error(RuntimeError):
@@ -61,6 +61,7 @@ SIGNATURES = {
     "y3_gather_detections": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "y3_conv_block_n": (_i, [_i, _i]),
     "y3_conv2d_bf16": (_i, [_p, _p, _i, _i, _i, _i, _i64, _p, _p, _i, _i, _i, _i, _p, _i64, _p, _i64, _i, _i, _p]),
+    "y3_conv2d_flat_bf16": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _i64, _p, _i64, _p]),
     "y3_conv2d_stem_f32": (_i, [_p, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i64, _p]),
     "y3_dbg_umma_shift": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p]),
     "y3_dbg_tma_tile": (_i, [_p, _p, _i, _i, _i, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -165,7 +165,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
             mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile<BLOCK_N>(p, tile, 0, t_row, q, lane, xp);
+            epilogue_tile(p, BLOCK_N, tile * kBlockM, 0, t_row, q, lane, xp);
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }

@@ -44,6 +44,17 @@ struct ConvArgs {
     long long out_stride;  // elements between consecutive pixels of the output view
     int out_fp32;
     int upsample;          // 1: write every output pixel to the 2x2 block (2p+dy, 2q+dx) of a (2Ho, 2Wo) view
+    // Iteration space of the GEMM M index: per image an it_h x it_w grid.  Normally (Ho, Wo); (Ho+1, Wo+1) when the
+    // conv walks the zero-haloed flat layout [B, Ho+1, Wo+1, C] of its input (rows with y == Ho or x == Wo are halo
+    // positions and produce no output).  out_padded: the output itself is stored in that haloed layout (and the
+    // epilogue writes the zero halo next to the last column / row).
+    int it_h, it_w;
+    int out_padded;
+    // flat-patch 3x3 kernel only (conv_flat.cuh)
+    int block_n;           // N tile (64 / 128 / 256), runtime there
+    int cblocks;           // Cin / BLOCK_K
+    int patch_boxes, box_rows;   // one patch = patch_boxes TMA boxes of box_rows haloed-flat pixels
+    int pst, bst;          // pipeline depth: patches / weight blocks
     // gather kernel only (software im2col): the input view
     const void* src;       // bf16 NHWC view, or the fp32 [B,H,W,3] image for the stem
     long long src_stride;  // elements between consecutive input pixels
@@ -69,29 +80,64 @@ constexpr int kBlockM = 128;
 constexpr int kXposePitch = 36;                       // floats per transpose-tile row: 144 B keeps 16-byte alignment
 constexpr int kXposeWarpFloats = 32 * kXposePitch;    // and makes both the 128-bit writes and reads conflict free
 
-template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn, uint32_t t_row, int q, int lane,
-                                              float* xp) {
-    static_assert(BLOCK_N % 32 == 0, "epilogue works on 32-column chunks");
-    const int n_base = tn * BLOCK_N;
-    const int m_w = tm * kBlockM + q * 32;     // first pixel row of this warp's slab
+// Where does GEMM row m (iteration index) go?  Identity for dense->dense layers; otherwise decode (n, y, x) on the
+// iteration grid, drop halo rows, and re-encode for the output / residual layouts.
+struct RowMap {
+    bool valid;
+    bool last_x, last_y;    // pixel sits in the last column / row of its image (needed to zero the halo it borders)
+    long long out;          // output pixel index (top-left pixel of the 2x2 block when upsampling)
+    long long res;          // residual pixel index (dense layout)
+};
+
+__device__ __forceinline__ RowMap map_row(const ConvArgs& p, int m) {
+    RowMap r;
+    if (p.it_h == p.Ho && p.it_w == p.Wo && !p.out_padded && !p.upsample) {
+        r.valid = m < p.M;
+        r.last_x = r.last_y = false;
+        r.out = r.res = m;
+        return r;
+    }
+    const int per = p.it_h * p.it_w;
+    const int n = m / per;
+    const int rem = m - n * per;
+    const int y = rem / p.it_w;
+    const int x = rem - y * p.it_w;
+    r.valid = (m < p.M) && (y < p.Ho) && (x < p.Wo);
+    r.last_x = (x == p.Wo - 1);
+    r.last_y = (y == p.Ho - 1);
+    const long long dense = ((long long)n * p.Ho + y) * p.Wo + x;
+    r.res = dense;
+    if (p.upsample) r.out = ((long long)n * 2 * p.Ho + 2 * y) * (2LL * p.Wo) + 2 * x;
+    else if (p.out_padded) r.out = ((long long)n * (p.Ho + 1) + y) * (p.Wo + 1) + x;
+    else r.out = dense;
+    return r;
+}
+
+// Epilogue of one 128 x block_n accumulator tile whose first GEMM row is m_base, for TMEM lane quarter q.
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int block_n, int m_base, int tn, uint32_t t_row, int q,
+                                              int lane, float* xp) {
+    const int n_base = tn * block_n;
+    const int m_w = m_base + q * 32;           // first GEMM row of this warp's slab
     const int sub = lane >> 2;                 // 0..7 : pixel row inside an 8-row group
     const int seg = lane & 3;                  // 0..3 : 8-channel (16 B) segment inside the 32-channel chunk
-    const int hw = p.Ho * p.Wo;
     const bool has_res = p.residual != nullptr;
-    const int nchunks = min(BLOCK_N / 32, (p.cout - n_base + 31) / 32);
+    const int nchunks = min(block_n / 32, (p.cout - n_base + 31) / 32);
     const float slope = p.leaky ? 0.1f : 1.0f;   // LeakyReLU(0.1)(x) = max(x, 0.1x); slope 1 makes it the identity
     float4* xrow = reinterpret_cast<float4*>(xp + lane * kXposePitch);
+
+    // the four rows this lane stores (transposed mapping): where they go, where their residual comes from
+    RowMap rm[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) rm[it] = map_row(p, m_w + it * 8 + sub);
 
     // residual tile rows of this lane (4 rows x 16 B per chunk), prefetched one chunk ahead
     uint4 rcur[4], rnext[4];
     auto load_res = [&](int c, uint4 (&r4)[4]) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-            const int m = m_w + it * 8 + sub;
             r4[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (has_res && m < p.M)
-                r4[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + (long long)m * p.res_stride + n_base + c * 32 +
+            if (has_res && rm[it].valid)
+                r4[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + rm[it].res * p.res_stride + n_base + c * 32 +
                                                               seg * 8));
         }
     };
@@ -132,8 +178,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int r = it * 8 + sub;
-                const int m = m_w + r;
-                if (m < p.M) {
+                if (rm[it].valid) {
                     const float4* src = reinterpret_cast<const float4*>(xp + r * kXposePitch + seg * 8);
                     const float4 lo = src[0], hi = src[1];
                     float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -150,26 +195,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int tm, int tn,
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
                     const uint4 o = *reinterpret_cast<uint4*>(o2);
+                    __nv_bfloat16* dst = ob + rm[it].out * p.out_stride + ncol + seg * 8;
                     if (p.dbg & 2) {
                         if (o.x == 0x12345678u && o.y == 0x9abcdef0u) ob[0] = __float2bfloat16(0.f);   // keep the math alive
-                    } else if (!p.upsample) {
-                        *reinterpret_cast<uint4*>(ob + (long long)m * p.out_stride + ncol + seg * 8) = o;
+                    } else if (p.upsample) {
+                        const long long up_row = 2LL * p.Wo * p.out_stride;
+                        *reinterpret_cast<uint4*>(dst) = o;
+                        *reinterpret_cast<uint4*>(dst + p.out_stride) = o;
+                        *reinterpret_cast<uint4*>(dst + up_row) = o;
+                        *reinterpret_cast<uint4*>(dst + up_row + p.out_stride) = o;
                     } else {
-                        const int n = m / hw;
-                        const int rem = m - n * hw;
-                        const int po = rem / p.Wo;
-                        const int qo = rem - po * p.Wo;
-                        const long long up_row = 2LL * p.Wo;
-                        const long long pix = ((long long)n * 2 * p.Ho + 2 * po) * up_row + 2 * qo;
-#pragma unroll
-                        for (int rep = 0; rep < 4; ++rep) {
-                            const long long pp = pix + (rep >> 1) * up_row + (rep & 1);
-                            *reinterpret_cast<uint4*>(ob + pp * p.out_stride + ncol + seg * 8) = o;
+                        *reinterpret_cast<uint4*>(dst) = o;
+                        if (p.out_padded && (rm[it].last_x || rm[it].last_y)) {
+                            // keep the zero halo of the [B, Ho+1, Wo+1, C] layout intact (arena buffers are recycled)
+                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                            const long long row = (long long)(p.Wo + 1) * p.out_stride;
+                            if (rm[it].last_x) *reinterpret_cast<uint4*>(dst + p.out_stride) = z;
+                            if (rm[it].last_y) *reinterpret_cast<uint4*>(dst + row) = z;
+                            if (rm[it].last_x && rm[it].last_y) *reinterpret_cast<uint4*>(dst + row + p.out_stride) = z;
                         }
                     }
                 }
             }
         } else {
+            // fp32 heads: dense -> dense only (host-enforced), 32 consecutive floats of one pixel per instruction
             float* of = reinterpret_cast<float*>(p.out);
             const bool col_ok = (ncol + lane) < p.cout;
             const int rows = min(32, p.M - m_w);
@@ -372,7 +421,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile<BLOCK_N>(p, tm, tn, t_row, q, lane, xp);
+            epilogue_tile(p, BLOCK_N, tm * kBlockM, tn, t_row, q, lane, xp);
             // all TMEM reads of this accumulator are complete (wait::ld) -> hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));

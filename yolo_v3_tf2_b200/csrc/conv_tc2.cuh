@@ -193,7 +193,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile<BLOCK_N>(p, tm, tn, t_row, q, lane, xp);
+            epilogue_tile(p, BLOCK_N, tm * kBlockM, tn, t_row, q, lane, xp);
             tc_fence_before();
             if (is_leader) mbar_arrive(tempty_bar(acc));
             else mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));

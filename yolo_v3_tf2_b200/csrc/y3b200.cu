@@ -16,6 +16,7 @@
 #include "conv_gather.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
+#include "conv_flat.cuh"
 #include "decode.cuh"
 #include "nms.cuh"
 #include "ptx.cuh"
@@ -295,6 +296,59 @@ cudaError_t launch_gather(const ConvCfg& c, const CUtensorMap& tb, const y3::Con
     return cudaErrorInvalidValue;
 }
 
+const bool g_use_flat = []() { const char* e = getenv("Y3_FLAT"); return !(e && e[0] == '0'); }();
+
+// patch / pipeline geometry of the flat-patch kernel for a haloed row pitch of wp pixels
+struct FlatGeom {
+    int patch_boxes, box_rows, pst, bst;
+    size_t smem;
+};
+bool flat_geometry(int wp, int swz, int block_n, FlatGeom& g) {
+    const int need = 130 + 2 * wp;                       // 128 pixels + one haloed row and one pixel on each side
+    g.patch_boxes = (need + 255) / 256;
+    g.box_rows = (((need + g.patch_boxes - 1) / g.patch_boxes) + 7) & ~7;
+    if (g.box_rows > 256) return false;
+    const size_t patch = (((size_t)g.patch_boxes * g.box_rows * swz) + 1023) & ~(size_t)1023;
+    const size_t bb = (size_t)(block_n / 2) * swz;
+    const size_t fixed = 1024 + (size_t)y3::kConvEpiGroups * 4 * y3::kXposeWarpFloats * 4 + 512;
+    const size_t avail = 232448 - fixed;
+    g.pst = 3;
+    if (3 * patch + 4 * bb > avail) g.pst = 2;
+    if ((size_t)g.pst * patch + 2 * bb > avail) return false;
+    g.bst = (int)std::min<size_t>(8, (avail - (size_t)g.pst * patch) / bb);
+    g.smem = fixed + (size_t)g.pst * patch + (size_t)g.bst * bb;
+    return true;
+}
+
+cudaError_t launch_flat(int swz, const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& args, size_t smem,
+                        int sms, cudaStream_t st) {
+    auto kern = (swz == 128) ? y3::conv_flat_kernel<128> : y3::conv_flat_kernel<64>;
+    static size_t configured[2] = {0, 0};
+    size_t& conf = configured[swz == 128 ? 0 : 1];
+    if (smem > conf) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        conf = smem;
+    }
+    const int work = ((args.tiles_m + 1) / 2) * args.tiles_n;
+    const int grid = std::max(1, std::min(work, sms / 2)) * 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(y3::kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, args);
+}
+
 // reference padding rule (core/parse_model.py:29-43)
 void conv_geometry(int H, int W, int k, int stride, int pad, int& Ho, int& Wo, int& pad_lo, int& pad_hi) {
     if (stride > 1) {
@@ -331,6 +385,7 @@ struct TensorInfo {
     bool fp32_output = false;     // network output written by a head conv
     int out_index = -1;
     int buffer = -1, chan_off = 0, pix_stride = 0;
+    bool padded = false;          // stored as [B, H+1, W+1, C] with a zero last row / column (feeds a flat 3x3 conv)
 };
 
 struct BufferInfo {
@@ -343,6 +398,8 @@ struct BufferInfo {
 struct ConvWeights {
     int cin = 0, cout = 0, k = 0, cout_pad = 0;
     bool direct = false;
+    bool flat_order = false;  // K ordered (channel block, r, s, c) for the flat-patch kernel
+    int flat_bk = 0;
     bool stem_hilo = false;   // tensor-core stem: [cout_pad][64] = 27 weights, 5 zeros, the same 27 weights, 5 zeros
     void* w = nullptr;     // bf16 [cout_pad][k*k*cin]  or fp32 [k*k*cin][cout] for the direct kernel
     float* bias = nullptr; // fp32 [cout_pad]
@@ -358,6 +415,10 @@ struct Step {
     ConvCfg cfg{};
     int Ho = 0, Wo = 0, pad_lo = 0, pad_hi = 0;
     int fused_up = 0;
+    int flat = 0;          // 1: 3x3 stride-1 conv on a haloed-flat input (conv_flat_kernel)
+    int in_padded = 0;     // 1x1 conv walking a haloed-flat input
+    int out_padded = 0;    // output stored haloed-flat
+    int patch_boxes = 0, box_rows = 0, pst = 0, bst = 0;
     CUtensorMap tmA, tmB;
 };
 
@@ -545,10 +606,44 @@ int plan_net(y3_net& n) {
             off += o.C;
         }
     }
+    // ---- haloed-flat tensors: outputs of plain 1x1 convs whose consumers are 3x3 stride-1 'same' convs (and
+    // possibly other 1x1 convs).  Such a 3x3 conv then stages one patch per 64-channel block instead of nine im2col
+    // tiles (conv_flat.cuh). ----
+    std::vector<char> flat_conv(L, 0);
+    if (g_use_flat) {
+        for (int i = 0; i < L; ++i) {
+            const y3_layer_desc& d = n.layers[i];
+            TensorInfo& t = n.tensors[i + 1];
+            if (d.op != Y3_OP_CONV || d.ksize != 1 || d.stride != 1 || writes[i] != i + 1) continue;
+            if (!t.materialized || t.fp32_output || t.buffer >= 0 || t.C % 32 != 0 || d.src0 == 0) continue;
+            bool ok = !t.consumers.empty(), any3 = false;
+            for (int c : t.consumers) {
+                const y3_layer_desc& cd = n.layers[c];
+                if (cd.op != Y3_OP_CONV || cd.src0 != i + 1 || cd.stride != 1) { ok = false; break; }
+                if (cd.ksize == 3) {
+                    // the flat kernel: pad 1, bf16 output, no fused upsample, tile widths 64/128/256
+                    FlatGeom g;
+                    const int bn = pick_block_n(cd.filters);
+                    const int swz = (t.C % 64 == 0) ? 128 : 64;
+                    if (cd.pad != 1 || fused_up[c] || n.tensors[writes[c]].fp32_output || bn < 64 || cd.filters % 32 != 0 ||
+                        !flat_geometry(t.W + 1, swz, bn, g)) { ok = false; break; }
+                    any3 = true;
+                } else if (cd.ksize != 1 || t.C % 64 != 0) { ok = false; break; }
+            }
+            if (!ok || !any3) continue;
+            t.padded = true;
+            for (int c : t.consumers)
+                if (n.layers[c].ksize == 3) flat_conv[c] = 1;
+        }
+    }
     for (int t = 1; t <= L; ++t) {
         TensorInfo& ti = n.tensors[t];
         if (ti.materialized && !ti.fp32_output && ti.buffer < 0) {
-            ti.buffer = new_buffer(ti.H, ti.W, ti.C);
+            if (ti.padded) {
+                ti.buffer = new_buffer(ti.H + 1, ti.W + 1, ti.C);
+            } else {
+                ti.buffer = new_buffer(ti.H, ti.W, ti.C);
+            }
             ti.chan_off = 0;
             ti.pix_stride = ti.C;
         }
@@ -598,13 +693,33 @@ int plan_net(y3_net& n) {
                     s.cfg.stages = st2(128);
                 }
             }
+            if (tc_ok && flat_conv[i]) {
+                s.flat = 1;
+                s.cfg.gather = 0;
+                s.cfg.cluster = 3;
+                s.cfg.swz = (a.C % 64 == 0) ? 128 : 64;
+                s.cfg.block_n = pick_block_n(d.filters);
+                FlatGeom g;
+                flat_geometry(a.W + 1, s.cfg.swz, s.cfg.block_n, g);
+                s.patch_boxes = g.patch_boxes; s.box_rows = g.box_rows; s.pst = g.pst; s.bst = g.bst;
+                s.cfg.stages = g.bst;
+            }
+            if (tc_ok && !s.flat) {
+                s.in_padded = a.padded ? 1 : 0;
+                if (s.in_padded && (s.cfg.gather || d.ksize != 1))
+                    return fail(Y3_ERR_STATE, "internal: haloed-flat input reached a kernel that cannot read it");
+            }
+            if (tc_ok) s.out_padded = n.tensors[writes[i]].padded ? 1 : 0;
             if (tc_ok) {
                 if (!n.tensors[writes[i]].fp32_output && d.filters % 32 != 0)
                     return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": bf16 conv outputs need filters % 32 == 0");
                 s.kind = 1;
                 w.cout_pad = ((d.filters + s.cfg.block_n - 1) / s.cfg.block_n) * s.cfg.block_n;
                 w.stem_hilo = (s.cfg.gather == 2);
+                w.flat_order = s.flat != 0;
+                w.flat_bk = s.cfg.swz / 2;
                 pl.block_n = s.cfg.block_n; pl.swizzle = s.cfg.swz; pl.stages = s.cfg.stages;
+                pl.flat = s.flat;
             } else {
                 // direct CUDA-core conv: fp32 NHWC network input with 3 channels, bf16 output, no fusion
                 if (d.src0 != 0 || a.C != 3 || (d.filters != 32 && d.filters != 16) || residual[i] >= 0 || fused_up[i] ||
@@ -692,6 +807,7 @@ int plan_net(y3_net& n) {
         pl.chan_offset = t.chan_off;
         pl.pix_stride = t.pix_stride;
         pl.arena_offset = (t.materialized && t.buffer >= 0) ? n.buffers[t.buffer].offset : -1;
+        pl.padded = t.padded ? 1 : 0;
     }
     return Y3_OK;
 }
@@ -708,9 +824,17 @@ int build_maps(y3_net& n) {
         const TensorInfo& a = n.tensors[s.src];
         const ConvWeights& w = n.convs[s.conv_idx];
         int rc = Y3_OK;
-        if (s.cfg.gather == 0) {
+        if (s.flat) {
+            // haloed-flat input as a [pixels, channels] matrix; negative / past-the-end rows are zero filled by TMA
             const __nv_bfloat16* ap = tensor_ptr(n, s.src);
-            if (d.ksize == 1 && d.stride == 1) {
+            rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * (a.H + 1) * (a.W + 1), a.C, a.pix_stride,
+                             s.box_rows, s.cfg.swz, false);
+        } else if (s.cfg.gather == 0) {
+            const __nv_bfloat16* ap = tensor_ptr(n, s.src);
+            if (s.in_padded) {
+                rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * (a.H + 1) * (a.W + 1), a.C, a.pix_stride,
+                                 y3::kBlockM, s.cfg.swz, false);
+            } else if (d.ksize == 1 && d.stride == 1) {
                 rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * a.H * a.W, a.C, a.pix_stride, y3::kBlockM,
                                  s.cfg.swz, false);
             } else {
@@ -747,6 +871,22 @@ y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
     a.cout = d.filters;
     a.leaky = d.activation;
     a.upsample = s.fused_up;
+    a.it_h = s.Ho; a.it_w = s.Wo;
+    a.out_padded = s.out_padded;
+    if (s.flat || s.in_padded) {
+        // the GEMM M index walks the haloed grid of the input
+        a.it_h = s.Ho + 1; a.it_w = s.Wo + 1;
+        a.M = B * a.it_h * a.it_w;
+        a.tiles_m = (a.M + y3::kBlockM - 1) / y3::kBlockM;
+        a.a_im2col = 0;
+    }
+    if (s.flat) {
+        a.block_n = s.cfg.block_n;
+        a.cblocks = cin / (s.cfg.swz / 2);
+        a.patch_boxes = s.patch_boxes; a.box_rows = s.box_rows;
+        a.pst = s.pst; a.bst = s.bst;
+        a.num_k_blocks = 9 * a.cblocks;
+    }
     static const int dbg = []() { const char* e = getenv("Y3_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = dbg;
     return a;
@@ -917,8 +1057,15 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
         Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     } else {
         std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * K, __float2bfloat16(0.0f));
-        for (size_t kk = 0; kk < K; ++kk)
-            for (int o = 0; o < cout; ++o) packed[(size_t)o * K + kk] = __float2bfloat16(kernel[kk * cout + o] * scale[o]);
+        for (size_t kk = 0; kk < K; ++kk) {
+            size_t dst = kk;   // HWIO row kk = (tap, channel)
+            if (w.flat_order) {
+                // flat-patch kernel: K ordered (channel block, tap, channel in block) so one patch serves 9 K blocks
+                const size_t tap = kk / cin, ch = kk % cin;
+                dst = ((ch / w.flat_bk) * (size_t)(k * k) + tap) * w.flat_bk + ch % w.flat_bk;
+            }
+            for (int o = 0; o < cout; ++o) packed[(size_t)o * K + dst] = __float2bfloat16(kernel[kk * cout + o] * scale[o]);
+        }
         Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     }
     Y3_CUDA(cudaMemcpy(w.bias, shift.data(), shift.size() * 4, cudaMemcpyHostToDevice));
@@ -989,7 +1136,11 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
                 ca.out = tensor_ptr(*net, s.dst);
                 ca.out_stride = o.pix_stride;
             }
-            if (s.cfg.gather) {
+            if (s.flat) {
+                FlatGeom g;
+                flat_geometry(a.W + 1, s.cfg.swz, s.cfg.block_n, g);
+                Y3_CUDA(launch_flat(s.cfg.swz, s.tmA, s.tmB, ca, g.smem, sms, st));
+            } else if (s.cfg.gather) {
                 ca.H = a.H; ca.W = a.W;
                 if (s.cfg.gather == 2) {
                     ca.src = x;
@@ -1199,6 +1350,41 @@ int y3_conv2d_bf16(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, int
     } else {
         Y3_CUDA(launch_conv(cfg, s.tmA, s.tmB, ca, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
     }
+    return Y3_OK;
+}
+
+int y3_conv2d_flat_bf16(y3_ctx* ctx, const void* x_padded, int B, int H, int W, int Cin, const void* w_packed,
+                        const float* bias, int Cout, int leaky, const void* residual, int64_t res_stride, void* out,
+                        int64_t out_stride, void* stream) {
+    (void)cudaGetLastError();
+    if (!ctx || !x_padded || !w_packed || !bias || !out) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (Cin % 32 != 0 || Cout % 32 != 0) return fail(Y3_ERR_UNSUPPORTED, "Cin and Cout must be multiples of 32");
+    Step s;
+    s.flat = 1;
+    s.cfg.gather = 0; s.cfg.cluster = 3;
+    s.cfg.swz = (Cin % 64 == 0) ? 128 : 64;
+    s.cfg.block_n = pick_block_n(Cout);
+    if (s.cfg.block_n < 64) return fail(Y3_ERR_UNSUPPORTED, "Cout >= 64 required");
+    FlatGeom g;
+    if (!flat_geometry(W + 1, s.cfg.swz, s.cfg.block_n, g)) return fail(Y3_ERR_UNSUPPORTED, "patch does not fit in shared memory");
+    s.patch_boxes = g.patch_boxes; s.box_rows = g.box_rows; s.pst = g.pst; s.bst = g.bst;
+    s.Ho = H; s.Wo = W; s.pad_lo = 1; s.pad_hi = 1;
+    y3_layer_desc d{};
+    d.ksize = 3; d.stride = 1; d.filters = Cout; d.activation = leaky;
+    int rc = make_map_2d(ctx->drv, &s.tmA, x_padded, (uint64_t)B * (H + 1) * (W + 1), Cin, Cin, s.box_rows, s.cfg.swz, false);
+    if (rc) return rc;
+    const int cout_pad = ((Cout + s.cfg.block_n - 1) / s.cfg.block_n) * s.cfg.block_n;
+    const uint64_t K = 9ull * Cin;
+    rc = make_map_2d(ctx->drv, &s.tmB, w_packed, cout_pad, K, K, s.cfg.block_n / 2, s.cfg.swz, true);
+    if (rc) return rc;
+    y3::ConvArgs ca = conv_args(s, d, Cin, B);
+    ca.bias = bias;
+    ca.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    ca.res_stride = res_stride;
+    ca.out = out;
+    ca.out_stride = out_stride;
+    Y3_CUDA(launch_flat(s.cfg.swz, s.tmA, s.tmB, ca, g.smem, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
     return Y3_OK;
 }
 
