@@ -130,11 +130,8 @@ def test_planner_through_c_abi():
     assert kinds.count(3) == kinds.count(4) == kinds.count(5) == 0   # every add / upsample / concat is fused
     assert sum(1 for l in L if l["fused_add"] >= 0) == 23
     assert sum(1 for l in L if l["fused_upsample"]) == 2
-    # all 32 3x3 stride-1 convs behind a 1x1 conv run the flat-patch kernel on a zero-haloed input
-    assert sum(1 for l in L if l["flat"]) == 32 and sum(1 for l in L if l["padded"]) == 32
-    for i, l in enumerate(g.layers):
-        if L[i]["flat"]:
-            assert l.ksize == 3 and l.stride == 1 and L[l.src0 - 1]["padded"] == 1
+    # the flat-patch 3x3 kernel is opt-in (Y3_FLAT=1, see test_planner_flat_opt_in): by default nothing is haloed
+    assert sum(1 for l in L if l["flat"]) == 0 and sum(1 for l in L if l["padded"]) == 0
     # concat operands live inside the concat buffer: same buffer id, channel offsets 0 and Ca, pixel stride Ca+Cb
     for i, l in enumerate(g.layers):
         if l.op == _lib.OP_CONCAT:
@@ -150,6 +147,26 @@ def test_planner_through_c_abi():
     assert [(o["H"], o["W"], o["C"]) for o in outs] == [(19, 19, 255), (38, 38, 255), (76, 76, 255)]
     with pytest.raises(ValueError):
         m.plan(400, 416, 1)
+
+
+def test_planner_flat_opt_in():
+    """Y3_FLAT=1 (read when the library loads, hence the subprocess): all 32 3x3 stride-1 convs behind a 1x1 conv run the
+    flat-patch kernel on a zero-haloed input."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import yolo_v3_tf2_b200 as y3\n"
+        "m = y3.ParseModel.builtin_yolov3(80)\n"
+        "L = m.plan(416, 416, 8)['layers']\n"
+        "assert sum(1 for l in L if l['flat']) == 32 and sum(1 for l in L if l['padded']) == 32\n"
+        "for i, l in enumerate(m.graph.layers):\n"
+        "    if L[i]['flat']:\n"
+        "        assert l.ksize == 3 and l.stride == 1 and L[l.src0 - 1]['padded'] == 1\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, Y3_FLAT="1", PYTHONPATH=root)
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=root)
 
 
 def test_planner_arena_no_live_overlap():

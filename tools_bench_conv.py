@@ -33,3 +33,25 @@ for name, g, cin, cout, k, stride, res in cases:
     ms = float(np.median(ts))
     fl = 2.0 * B * g * g * cout * k * k * cin
     print(f"{name:24s} {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s")
+    if k == 3 and stride == 1:
+        # the same layer through the flat-patch kernel (haloed input)
+        bk = 64 if cin % 64 == 0 else 32
+        bnf = 64 if cout <= 64 else (128 if cout <= 128 else 256)
+        cpf = ((cout + bnf - 1) // bnf) * bnf
+        wf = (torch.randn((cpf, cin // bk, 3, 3, bk), device="cuda") / (9 * cin) ** 0.5).to(torch.bfloat16)
+        bf = torch.zeros(cpf, device="cuda")
+        xp = torch.zeros((B, g + 1, g + 1, cin), device="cuda", dtype=torch.bfloat16)
+        xp[:, :g, :g] = x
+        def runf():
+            _lib.check(lib.y3_conv2d_flat_bf16(ctx.handle, _lib.ptr(xp), B, g, g, cin, _lib.ptr(wf), _lib.ptr(bf), cout, 1,
+                                               _lib.ptr(r), cout, _lib.ptr(o), cout, _lib.stream_ptr()))
+        for _ in range(3):
+            runf()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0.record(); runf(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts))
+        print(f"{'   flat-patch kernel':24s} {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s")
