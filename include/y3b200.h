@@ -164,6 +164,12 @@ int y3_dbg_tma_tile(y3_ctx* ctx, const void* x, int B, int H, int W, int Cin, in
 int y3_dbg_umma_shift(y3_ctx* ctx, const void* x, int rows, const void* w, int swizzle, int shift, int base_off_mode,
                       float* out, void* stream);
 
+/* Profiling: while dev_u64_buffer (device memory, 32 x grid-size uint64) is non-null, every CTA of the CTA-pair conv
+ * kernel records %globaltimer at 12 points of its life (entry, prologue done, predecessor complete, last load issued,
+ * first operands landed, last MMA issued, first accumulator complete, epilogue hand-off / stores complete per group,
+ * exit).  Pass NULL to switch it off. */
+int y3_dbg_timestamps(void* dev_u64_buffer);
+
 /* last device-side watchdog code (0 = none) */
 int y3_watchdog_code(y3_ctx* ctx);
 

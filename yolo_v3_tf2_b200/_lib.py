@@ -65,6 +65,7 @@ SIGNATURES = {
     "y3_conv2d_stem_f32": (_i, [_p, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i64, _p]),
     "y3_dbg_umma_shift": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p]),
     "y3_dbg_tma_tile": (_i, [_p, _p, _i, _i, _i, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "y3_dbg_timestamps": (_i, [_p]),
     "y3_watchdog_code": (_i, [_p]),
 }
 

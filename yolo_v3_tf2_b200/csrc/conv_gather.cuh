@@ -25,8 +25,8 @@ template <int BLOCK_N, int SWZ, int STAGES>
 struct GatherSmem {
     static constexpr int A_BYTES = kBlockM * SWZ;
     static constexpr int B_BYTES = BLOCK_N * SWZ;
-    static constexpr int XPOSE_BYTES = kGatherEpiGroups * 4 * kXposeWarpFloats * 4;
-    static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
+    static constexpr int XPOSE_BYTES = kGatherEpiGroups * 4 * kEpiWarpBytes;
+    static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kGatherEpiGroups;
     static constexpr int total(int num_k_blocks) {
         return 1024 + STAGES * A_BYTES + num_k_blocks * B_BYTES + XPOSE_BYTES + BAR_BYTES;
     }
@@ -37,10 +37,6 @@ template <int SWZ>
 __device__ __forceinline__ uint32_t swz_off(int r, int j) {
     if (SWZ == 128) return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
     return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
-}
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // 16-byte asynchronous global->shared copy; src_bytes == 0 zero-fills (padding halo / rows past M)
@@ -54,7 +50,8 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 
 template <int BLOCK_N, int SWZ, int STAGES, bool STEM>
 __global__ void __launch_bounds__(gather_threads<STEM ? 2 : 1>(), 1)
-conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                   const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
     using S = GatherSmem<BLOCK_N, SWZ, STAGES>;
     constexpr int NEPI = kGatherEpiGroups;
     constexpr int NPROD = STEM ? 2 : 1;
@@ -72,7 +69,6 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_base + STAGES * S::A_BYTES;
     const uint32_t tiles_bytes = STAGES * S::A_BYTES + nkb * S::B_BYTES;
-    float* xpose = reinterpret_cast<float*>(smem_gen + tiles_bytes);
     const uint32_t bar_base = smem_base + tiles_bytes + S::XPOSE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -80,6 +76,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 4);
     const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 5);
+    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 5) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
     volatile uint32_t* tmem_ptr_gen =
         reinterpret_cast<volatile uint32_t*>(smem_gen + tiles_bytes + S::XPOSE_BYTES + 8 * (2 * STAGES + 5));
 
@@ -100,7 +97,12 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
             mbar_init(tempty_bar(a), 128);
         }
         mbar_init(bfull_bar, 1);
+        for (int w = 0; w < kEpiMaxBufs * 4 * NEPI; ++w) mbar_init(res_bar(0) + 8u * w, 1);
         fence_mbar_init();
+    }
+    if (warp == 3 && lane == 0 && p.tma_out) {
+        tma_prefetch_desc(&tmO);
+        if (p.residual) tma_prefetch_desc(&tmR);
     }
     if (warp == 2) {
         tmem_alloc(tmem_ptr_smem, TMEM_COLS);
@@ -158,16 +160,28 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
         // ===================== epilogue groups =====================
         const int eg = (warp - 4) >> 2;
         const int q = warp & 3;
-        float* xp = xpose + (warp - 4) * kXposeWarpFloats;
-        for (int j = eg; j < my_tiles; j += NEPI) {
-            const int acc = j & 1;
-            const int tile = blockIdx.x + j * gridDim.x;
-            mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile(p, BLOCK_N, tile * kBlockM, 0, t_row, q, lane, xp);
-            tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+        float* xp = reinterpret_cast<float*>(smem_gen + tiles_bytes + (warp - 4) * kEpiWarpBytes);
+        if (p.tma_out) {
+            const uint32_t stg = smem_base + tiles_bytes + (uint32_t)((warp - 4) * kEpiWarpBytes);
+            const EpiTiles et{(int)blockIdx.x + eg * (int)gridDim.x, NEPI * (int)gridDim.x, num_tiles, 1, 1, 0};
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * BLOCK_N);
+            if (BLOCK_N >= 64 && p.tma_out == 64)
+                epilogue_role_tma<64, 2>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
+                                         tempty_bar(eg), false, nullptr, 7 + eg);
+            else
+                epilogue_role_tma<32, 4>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
+                                         tempty_bar(eg), false, nullptr, 7 + eg);
+        } else {
+            for (int j = eg; j < my_tiles; j += NEPI) {
+                const int acc = j & 1;
+                const int tile = blockIdx.x + j * gridDim.x;
+                mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+                epilogue_tile(p, BLOCK_N, tile * kBlockM, 0, t_row, q, lane, xp);
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
+            }
         }
     } else if (warp >= 4 + 4 * NEPI) {
         // ===================== A producers: one output pixel (tile row) per thread =====================

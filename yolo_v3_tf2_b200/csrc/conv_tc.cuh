@@ -59,6 +59,10 @@ struct ConvArgs {
     const void* src;       // bf16 NHWC view, or the fp32 [B,H,W,3] image for the stem
     long long src_stride;  // elements between consecutive input pixels
     int H, W;              // input spatial size
+    int tma_out;           // 0: register-transpose epilogue; 32 / 64: bf16 dense output written with TMA stores in chunks
+                           //    of that many columns (epilogue_role_tma); tmO (and tmR when a residual is fused) are
+                           //    tensor maps with a 32-row x tma_out-column box
+    unsigned long long* ts;   // profiling: when non-null every CTA records %globaltimer at 12 points into ts[32*blockIdx.x + k]
     int dbg;               // profiling knobs (env Y3_DBG): 1 epilogue drains TMEM only, 2 no global stores,
                            // 4 producer skips the A loads, 8 no MMAs are issued (results are garbage)
 };
@@ -232,15 +236,205 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int block_n, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-store epilogue for the common case (bf16 output, dense pixel indexing, no upsample).  One epilogue warp owns the
+// 32 TMEM lanes (= 32 output pixels) q*32.. of every tile of its group and walks them in chunks of CW columns through a
+// ring of NBUF staging buffers (32 rows x CW bf16, written with the tensor map's swizzle):
+//   [residual]  one lane TMA-loads the 32 x CW residual block of a chunk NBUF-1 chunks ahead of the one being
+//               processed (also across tile boundaries, and before the accumulator is even complete)
+//   TMEM -> registers (thread = pixel row) -> accumulator handed back to the MMA warp right after the tile's last load
+//   -> +bias -> LeakyReLU(0.1) [-> + residual read back from the staging buffer] -> bf16
+//   -> 16-byte st.shared into the staging buffer (bank-conflict free) -> fence.proxy.async
+//   -> one lane issues a 2-D TMA store of the 32 x CW block; the buffer is reused NBUF chunks later, so the store's
+//      read of shared memory is never waited for on the spot.
+// No per-row address arithmetic, no transposing re-read, no scattered global stores: ~1/3 of the instructions of
+// epilogue_tile.  Rows past M and columns past Cout are clipped by the tensor map.  What motivated it: with loads and
+// MMAs disabled the 3x3 128->256 @52 layer still spent 70 of its 96 us in the old epilogue; the first (single-buffer)
+// version of this one took 1.3 us per chunk because every chunk waited for the previous store to drain its buffer.
+//   CW = 64 -> SWIZZLE_128B rows of 128 B, NBUF = 2;   CW = 32 -> SWIZZLE_64B rows of 64 B, NBUF = 4
+//   (residual layers use CW = 32 so the residual prefetch runs 3 chunks ahead).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kEpiWarpBytes = 8192;    // staging ring per epilogue warp; a multiple of the 1024 B swizzle period
+constexpr int kEpiMaxBufs = 4;         // residual mbarriers per epilogue warp
+
+// the tile sequence of one epilogue group of one CTA: tile ids first, first + step, ... < end;
+// tile -> (tmg = tile / tiles_n, tn = tile % tiles_n), M tile = tmg * cl + cta_rank
+struct EpiTiles {
+    int first, step, end;
+    int tiles_n, cl, cta_rank;
+};
+
+template <int CW>
+struct EpiCursor {     // walks (tile, chunk) in processing order
+    int tile, c, nch, ncol, row;
+    bool valid;
+    __device__ __forceinline__ void load(const ConvArgs& p, const EpiTiles& et, int block_n, int q) {
+        valid = tile < et.end;
+        if (!valid) return;
+        const int tmg = tile / et.tiles_n, tn = tile - tmg * et.tiles_n;
+        const int tm = tmg * et.cl + et.cta_rank;
+        const int n_base = tn * block_n;
+        nch = min(block_n / CW, (p.cout - n_base + CW - 1) / CW);
+        ncol = n_base;
+        row = tm * kBlockM + q * 32;
+        c = 0;
+    }
+    __device__ __forceinline__ void next(const ConvArgs& p, const EpiTiles& et, int block_n, int q) {
+        if (++c < nch) {
+            ncol += CW;
+        } else {
+            tile += et.step;
+            load(p, et, block_n, q);
+        }
+    }
+};
+
+template <int CW, int NBUF>
+__device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUtensorMap* tmO, const CUtensorMap* tmR,
+                                                  int block_n, const EpiTiles et, uint32_t t_acc, int q, int lane,
+                                                  uint32_t stg, uint32_t res_bar0, uint32_t tfull_bar,
+                                                  uint32_t tempty_addr, bool tempty_remote, unsigned long long* ts,
+                                                  int ts_slot) {
+    static_assert((CW == 64 || CW == 32) && NBUF >= 2 && NBUF <= kEpiMaxBufs && NBUF * 32 * CW * 2 <= kEpiWarpBytes, "ring");
+    constexpr uint32_t ROW_BYTES = CW * 2;
+    constexpr uint32_t BUF_BYTES = 32 * ROW_BYTES;
+    const bool drain_only = (p.dbg & 1) != 0;
+    const bool has_res = (p.residual != nullptr) && !drain_only;
+    const float slope = p.leaky ? 0.1f : 1.0f;   // LeakyReLU(0.1)(x) = max(x, 0.1x); slope 1 makes it the identity
+    const uint32_t sw = (CW == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+    const uint32_t row_off = (uint32_t)lane * ROW_BYTES;
+
+    EpiCursor<CW> pr, pf;    // chunk being processed / chunk whose residual is fetched next
+    pr.tile = et.first;
+    pr.load(p, et, block_n, q);
+    pf = pr;
+    uint32_t g = 0, gp = 0;  // their running chunk numbers; chunk n lives in ring slot n % NBUF
+    auto issue_res = [&]() {   // lane 0 only
+        const uint32_t b = gp % NBUF;
+        mbar_arrive_expect_tx(res_bar0 + 8u * b, BUF_BYTES);
+        tma_load_2d(stg + b * BUF_BYTES, tmR, res_bar0 + 8u * b, pf.ncol, pf.row);
+    };
+    if (has_res) {
+        // all ring slots are free: fetch the residual of the first NBUF-1 chunks before the first accumulator is ready
+#pragma unroll 1
+        for (int i = 0; i < NBUF - 1 && pf.valid; ++i) {
+            if (lane == 0) issue_res();
+            pf.next(p, et, block_n, q);
+            ++gp;
+        }
+    }
+
+    uint32_t jj = 0;         // tiles of this group seen so far (accumulator phase)
+#pragma unroll 1
+    while (pr.valid) {
+        if (pr.c == 0) {
+            mbar_wait(tfull_bar, jj & 1u, 0x400);
+            tc_fence_after();
+            if (jj == 0 && lane == 0 && q == 0 && ts_slot == 7) ts_mark(ts, 6);   // first accumulator complete
+        }
+        const uint32_t b = g % NBUF;
+        const uint32_t buf = stg + b * BUF_BYTES;
+        if (ts != nullptr && ts_slot == 7 && q == 0 && lane == 0 && g == 1) ts_clock(ts, 16);   // chunk 1 starts
+        if (!has_res) {
+            // slot b was last used by chunk g - NBUF: its store must have finished reading shared memory
+            if (lane == 0) tma_store_wait_read<NBUF - 1>();
+            __syncwarp();
+        }
+        uint32_t v[CW];
+        tmem_ld_32x32(t_acc + (uint32_t)(pr.c * CW), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        if constexpr (CW == 64) tmem_ld_32x32(t_acc + (uint32_t)(pr.c * CW + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[CW - 32]));
+        // bias of the first 32 columns: issued before the TMEM wait so the (L1-resident after the first tile) loads
+        // overlap it; the shared-memory accesses below carry no memory clobber, so the second half's loads hoist too
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + pr.ncol);
+        float4 bz[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bz[j] = __ldg(bp + j);
+        tmem_ld_wait();
+        const bool stamp = ts != nullptr && ts_slot == 7 && q == 0 && lane == 0 && g >= 1 && g <= 2;   // chunks 1, 2 of warp 4
+        if (stamp) ts_clock(ts, g == 1 ? 17 : 23);   // out of TMEM
+        if (pr.c == pr.nch - 1) {
+            // every TMEM read of this accumulator has completed -> hand it back to the MMA warp now
+            tc_fence_before();
+            if (tempty_remote) mbar_arrive_cluster(tempty_addr);
+            else mbar_arrive(tempty_addr);
+            ++jj;
+        }
+        if (!drain_only) {
+            if (has_res) mbar_wait(res_bar0 + 8u * b, (g / NBUF) & 1u, 0x600 + b);
+            if (stamp && g == 1) ts_clock(ts, 18);   // residual landed
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j) {      // one 16-byte (8-channel) piece of this thread's row at a time
+                const float4 b0 = (j < 4) ? bz[2 * j] : __ldg(bp + 2 * j), b1 = (j < 4) ? bz[2 * j + 1] : __ldg(bp + 2 * j + 1);
+                float f[8];
+                f[0] = __uint_as_float(v[8 * j + 0]) + b0.x;
+                f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
+                f[2] = __uint_as_float(v[8 * j + 2]) + b0.z;
+                f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
+                f[4] = __uint_as_float(v[8 * j + 4]) + b1.x;
+                f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
+                f[6] = __uint_as_float(v[8 * j + 6]) + b1.z;
+                f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], slope * f[e]);
+                const uint32_t addr = buf + row_off + ((((uint32_t)j) ^ sw) << 4);
+                if (has_res) {
+                    const uint4 r = ld_shared_v4_relaxed(addr);   // ordered after the residual barrier wait (both volatile)
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 r2 = __bfloat1622float2(h2[e]);
+                        f[2 * e] += r2.x;
+                        f[2 * e + 1] += r2.y;
+                    }
+                }
+                __nv_bfloat162 o2[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                st_shared_v4_relaxed(addr, *reinterpret_cast<uint4*>(o2));   // same address as the load it depends on
+            }
+            if (stamp && g == 1) ts_clock(ts, 19);   // math + st.shared issued
+            fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy); also a compiler barrier
+            if (stamp && g == 1) ts_clock(ts, 20);   // fenced
+            __syncwarp();
+            if (lane == 0) {
+                if (!(p.dbg & 2)) tma_store_2d(tmO, buf, pr.ncol, pr.row);
+                tma_store_commit();
+                if (stamp && g == 1) ts_clock(ts, 21);   // store issued
+                if (has_res && pf.valid) {
+                    // all stores but the one just issued have read their buffers: the slot of chunk g - 1 is free,
+                    // and it is the slot of chunk gp = g + NBUF - 1
+                    tma_store_wait_read<1>();
+                    issue_res();
+                }
+                if (stamp && g == 1) ts_clock(ts, 22);   // residual prefetch issued
+            }
+            if (has_res && pf.valid) {
+                pf.next(p, et, block_n, q);
+                ++gp;
+            }
+        }
+        pr.next(p, et, block_n, q);
+        ++g;
+    }
+    if (lane == 0) {
+        if (q == 0) ts_mark(ts, ts_slot);         // last chunk handed to the TMA
+        tma_store_wait<0>();                      // every bulk store has completed (not just been read) before exit
+        if (q == 0) ts_mark(ts, ts_slot + 2);
+    }
+}
+
 template <int BLOCK_N, int SWZ, int STAGES>
 struct ConvSmem {
     static constexpr int A_BYTES = kBlockM * SWZ;
     static constexpr int B_BYTES = BLOCK_N * SWZ;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * kXposeWarpFloats * 4;   // per-epilogue-warp 32 x 36 fp32 transpose tile
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16; // full/empty + tmem full/empty + tmem ptr
+    // epilogue region: per-warp staging ring of the TMA-store epilogue; the register-transpose epilogue (fp32 heads,
+    // fused upsample) uses the first 32 x 36 fp32 of each warp's share instead
+    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * kEpiWarpBytes;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kConvEpiGroups; // full/empty + tmem full/empty + tmem ptr + residual ring
     static constexpr int TOTAL = 1024 /*align slack*/ + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
+    static_assert(kEpiWarpBytes >= kXposeWarpFloats * 4 && TILE_BYTES % 1024 == 0, "staging rings share the transpose region");
 };
 
 // CLUSTER == 2: two CTAs of a cluster work on two adjacent M tiles of the same N tile.  Each loads its own A tile and
@@ -249,7 +443,8 @@ struct ConvSmem {
 // only after BOTH CTAs' MMAs have read it, so tcgen05.commit arrives on the empty barrier of both CTAs (count 2).
 template <int BLOCK_N, int SWZ, int STAGES, int CLUSTER>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
     using S = ConvSmem<BLOCK_N, SWZ, STAGES>;
     constexpr int BLOCK_K = SWZ / 2;   // bf16 elements per swizzle row
     constexpr int UMMA_K = 16;
@@ -262,13 +457,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_base + STAGES * S::A_BYTES;
-    float* xpose = reinterpret_cast<float*>(smem_gen + S::TILE_BYTES);
     const uint32_t bar_base = smem_base + S::TILE_BYTES + S::XPOSE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
     volatile uint32_t* tmem_ptr_gen =
         reinterpret_cast<volatile uint32_t*>(smem_gen + S::TILE_BYTES + S::XPOSE_BYTES + 8 * (2 * STAGES + 4));
 
@@ -293,11 +488,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 128);
         }
+        for (int w = 0; w < kEpiMaxBufs * 4 * kConvEpiGroups; ++w) mbar_init(res_bar(0) + 8u * w, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
         tmem_alloc(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish();
+    }
+    if (warp == 3 && lane == 0 && p.tma_out) {
+        tma_prefetch_desc(&tmO);
+        if (p.residual) tma_prefetch_desc(&tmR);
     }
     tc_fence_before();
     __syncthreads();
@@ -411,20 +611,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue groups =====================
         const int eg = (warp - 4) >> 2;         // group: owns accumulator stage eg
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        float* xp = xpose + (warp - 4) * kXposeWarpFloats;
-        int j = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
-            if ((j % kConvEpiGroups) != eg) continue;
-            const int acc = j & 1;
-            const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
-            const int tm = tmg * CLUSTER + cta_rank;
-            mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile(p, BLOCK_N, tm * kBlockM, tn, t_row, q, lane, xp);
-            // all TMEM reads of this accumulator are complete (wait::ld) -> hand it back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+        float* xp = reinterpret_cast<float*>(smem_gen + S::TILE_BYTES + (warp - 4) * kEpiWarpBytes);
+        if (p.tma_out) {
+            const uint32_t stg = smem_base + S::TILE_BYTES + (uint32_t)((warp - 4) * kEpiWarpBytes);
+            const EpiTiles et{first_tile + eg * tile_step, kConvEpiGroups * tile_step, num_tiles, p.tiles_n, CLUSTER, cta_rank};
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * BLOCK_N);
+            if (BLOCK_N >= 64 && p.tma_out == 64)
+                epilogue_role_tma<64, 2>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
+                                         tempty_bar(eg), false, nullptr, 7 + eg);
+            else
+                epilogue_role_tma<32, 4>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
+                                         tempty_bar(eg), false, nullptr, 7 + eg);
+        } else {
+            int j = 0;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
+                if ((j % kConvEpiGroups) != eg) continue;
+                const int acc = j & 1;
+                const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
+                const int tm = tmg * CLUSTER + cta_rank;
+                mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+                epilogue_tile(p, BLOCK_N, tm * kBlockM, tn, t_row, q, lane, xp);
+                // all TMEM reads of this accumulator are complete (wait::ld) -> hand it back to the MMA warp
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
+            }
         }
     }
 

@@ -24,14 +24,15 @@ struct Conv2Smem {
     static constexpr int B_BYTES = (BLOCK_N / 2) * SWZ;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * kXposeWarpFloats * 4;
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * kEpiWarpBytes;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kConvEpiGroups;
     static constexpr int TOTAL = 1024 + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
 };
 
 template <int BLOCK_N, int SWZ, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
     using S = Conv2Smem<BLOCK_N, SWZ, STAGES>;
     constexpr int BLOCK_K = SWZ / 2;
     constexpr int UMMA_K = 16;
@@ -44,13 +45,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_base + STAGES * S::A_BYTES;
-    float* xpose = reinterpret_cast<float*>(smem_gen + S::TILE_BYTES);
     const uint32_t bar_base = smem_base + S::TILE_BYTES + S::XPOSE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
     volatile uint32_t* tmem_ptr_gen =
         reinterpret_cast<volatile uint32_t*>(smem_gen + S::TILE_BYTES + S::XPOSE_BYTES + 8 * (2 * STAGES + 4));
 
@@ -62,6 +63,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int first_tile = (int)blockIdx.x / 2;
     const int tile_step = (int)gridDim.x / 2;
 
+    if (threadIdx.x == 0) ts_mark(p.ts, 0);   // kernel entry
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -75,21 +77,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 256);
         }
+        for (int w = 0; w < kEpiMaxBufs * 4 * kConvEpiGroups; ++w) mbar_init(res_bar(0) + 8u * w, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
         tmem_alloc2(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish2();
     }
+    if (warp == 3 && lane == 0 && p.tma_out) {
+        tma_prefetch_desc(&tmO);
+        if (p.residual) tma_prefetch_desc(&tmR);
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    if (threadIdx.x == 0) ts_mark(p.ts, 1);   // prologue done
     // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
     // from here on we touch activations it wrote (and buffers it may still be reading), so wait for it to finish.
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) ts_mark(p.ts, 2);   // predecessor grid complete
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -143,6 +152,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
         }
+        if (lane == 0) ts_mark(p.ts, 3);   // producer issued its last load
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
@@ -162,6 +172,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase, 0x300 + stage);
                     tc_fence_after();
+                    if (j == 0 && kb == 0 && lane == 0) ts_mark(p.ts, 4);   // first operands landed
                     if (leader_lane) {
                         const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
                         const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (S::B_BYTES >> 4));
@@ -177,26 +188,40 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (lane == 0) ts_mark(p.ts, 5);   // last MMA issued
         }
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue groups (both CTAs, each drains its own 128 TMEM lanes) =====================
         const int eg = (warp - 4) >> 2;
         const int q = warp & 3;
-        float* xp = xpose + (warp - 4) * kXposeWarpFloats;
-        int j = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
-            if ((j % kConvEpiGroups) != eg) continue;
-            const int acc = j & 1;
-            const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
-            const int tm = tmg * 2 + cta_rank;
-            mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile(p, BLOCK_N, tm * kBlockM, tn, t_row, q, lane, xp);
-            tc_fence_before();
-            if (is_leader) mbar_arrive(tempty_bar(acc));
-            else mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        float* xp = reinterpret_cast<float*>(smem_gen + S::TILE_BYTES + (warp - 4) * kEpiWarpBytes);
+        if (p.tma_out) {
+            const uint32_t stg = smem_base + S::TILE_BYTES + (uint32_t)((warp - 4) * kEpiWarpBytes);
+            const EpiTiles et{first_tile + eg * tile_step, kConvEpiGroups * tile_step, num_tiles, p.tiles_n, 2, cta_rank};
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * BLOCK_N);
+            const uint32_t tempty = is_leader ? tempty_bar(eg) : mapa_shared(tempty_bar(eg), 0);
+            if (p.tma_out == 64)
+                epilogue_role_tma<64, 2>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
+                                         tempty, !is_leader, p.ts, 7 + eg);
+            else
+                epilogue_role_tma<32, 4>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
+                                         tempty, !is_leader, p.ts, 7 + eg);
+        } else {
+            int j = 0;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
+                if ((j % kConvEpiGroups) != eg) continue;
+                const int acc = j & 1;
+                const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
+                const int tm = tmg * 2 + cta_rank;
+                mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+                epilogue_tile(p, BLOCK_N, tm * kBlockM, tn, t_row, q, lane, xp);
+                tc_fence_before();
+                if (is_leader) mbar_arrive(tempty_bar(acc));
+                else mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+            }
         }
     }
 
@@ -207,6 +232,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         tmem_dealloc2(tmem_base, TMEM_COLS);
     }
+    if (threadIdx.x == 0) ts_mark(p.ts, 11);   // exit
 }
 
 }  // namespace y3

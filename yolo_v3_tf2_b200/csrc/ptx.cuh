@@ -24,6 +24,21 @@ __device__ __forceinline__ uint32_t lane_id() {
     return l;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// profiling stamp k of this CTA (see ConvArgs::ts); one thread calls it
+constexpr int kTsSlots = 32;
+__device__ __forceinline__ void ts_mark(unsigned long long* ts, int k) {
+    if (ts) ts[kTsSlots * blockIdx.x + k] = global_timer_ns();
+}
+// slots 16.. hold SM cycle counts (clock64) for intervals inside one warp
+__device__ __forceinline__ void ts_clock(unsigned long long* ts, int k) {
+    if (ts) ts[kTsSlots * blockIdx.x + k] = (unsigned long long)clock64();
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
@@ -181,6 +196,26 @@ __device__ __forceinline__ void tma_store_wait_read() {
 template <int N>
 __device__ __forceinline__ void tma_store_wait() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// Same without the "memory" clobber: the compiler may move ordinary loads (bias __ldg) across them.  Only for code whose
+// ordering against other shared-memory traffic is established elsewhere (data dependence, a following fence + sync).
+__device__ __forceinline__ void st_shared_v4_relaxed(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ uint4 ld_shared_v4_relaxed(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 
 // 1-D bulk copy global -> shared (bytes multiple of 16, both addresses 16-byte aligned)
