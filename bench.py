@@ -39,6 +39,19 @@ def conv_flops(model, H, W):
     return fl, launches
 
 
+def conv_traffic_bytes(size, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one forward pass, from the newest committed
+    ncu capture (profiles/*_traffic.json, taken at 416^2 batch 64); None for any other workload."""
+    if size != 416 or batch != 64:
+        return None
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), key=os.path.getmtime)
+    if not files:
+        return None
+    d = json.load(open(files[-1]))
+    return d["dram_bytes_read"] + d["dram_bytes_write"]
+
+
 class ClockSampler:
     """SM clock and throttle reasons of one GPU, sampled by an `nvidia-smi -lms` subprocess while the timed regions
     run (an in-process NVML polling thread was measured to slow kernel launches down 3x, so the sampler lives in its
@@ -295,10 +308,12 @@ def main():
                     "note": "Detector.detections() on pinned host batches, double-buffered H2D on a copy stream"},
             "gpu_launches": args.steps * (launches_fwd + 3),
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "conv_tc_kernel (74 launches/step; forward pass timed with CUDA events, includes the "
-                                   "CUDA-core stem conv = 0.45% of FLOPs)", "forward_ms": fwd_ms,
-                         "flops_per_step": flops_img * B},
+                         "frac": achieved_tflops / peak, "traffic": conv_traffic_bytes(S, B), "peak_source": peak_src,
+                         "kernel": f"tcgen05 implicit-GEMM conv kernels ({launches_fwd} launches/step = the whole forward "
+                                   "pass, timed with CUDA events inside the timed loop; achieved = algorithmic conv FLOPs of "
+                                   "one batch / that time); traffic = DRAM bytes of those launches from the committed ncu "
+                                   "capture (profiles/), algorithmic bytes = 190 MB/img",
+                         "forward_ms": fwd_ms, "flops_per_step": flops_img * B},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

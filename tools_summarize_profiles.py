@@ -33,6 +33,37 @@ if os.path.exists(lp):
         for r in rows:
             f.write(f"\"{r['Kernel Name'].split('(')[0]}\",\"{r['Grid Size']}\",\"{r['Block Size']}\",{r['Metric Value']}\n")
 
+tp = f"gpurun_out/{tag}_traffic.csv"
+if os.path.exists(tp):
+    txt = open(tp).read()
+    rows = list(csv.DictReader(io.StringIO(txt[txt.index('"ID","Process ID"'):])))
+    per = collections.OrderedDict()
+    for r in rows:
+        d = per.setdefault(r["ID"], {"name": r["Kernel Name"].split("(")[0].replace("void ", "")})
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        if "byte" in u:
+            v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        elif u in ("us", "usecond"):
+            v *= 1e3
+        elif u in ("ms", "msecond"):
+            v *= 1e6
+        d[r["Metric Name"]] = v
+    rd = sum(d.get("dram__bytes_read.sum", 0) for d in per.values())
+    wr = sum(d.get("dram__bytes_write.sum", 0) for d in per.values())
+    tt = sum(d.get("gpu__time_duration.sum", 0) for d in per.values())
+    out.append(f"## DRAM traffic of one forward pass ({len(per)} conv launches, batch 64, 416x416)\n")
+    out.append(f"read {rd / 1e9:.3f} GB + write {wr / 1e9:.3f} GB = **{(rd + wr) / 1e9:.3f} GB** per forward pass "
+               f"(algorithmic bytes, SURVEY 8d: 190 MB/img x 64 = 12.16 GB); serialised kernel time {tt / 1e6:.3f} ms\n")
+    out.append("| # | kernel | us | DRAM read MB | DRAM write MB | tensor pipe % of elapsed |\n|---|---|---|---|---|---|")
+    for i, d in enumerate(per.values()):
+        out.append(f"| {i} | `{d['name']}` | {d.get('gpu__time_duration.sum', 0) / 1e3:.1f} | {d.get('dram__bytes_read.sum', 0) / 1e6:.1f} | "
+                   f"{d.get('dram__bytes_write.sum', 0) / 1e6:.1f} | {d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 0):.1f} |")
+    out.append("")
+    import json
+    json.dump({"dram_bytes_read": rd, "dram_bytes_write": wr, "launches": len(per), "kernel_time_ms": tt / 1e6},
+              open(f"profiles/{name}_traffic.json", "w"))
+
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
