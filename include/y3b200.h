@@ -46,7 +46,7 @@ typedef struct y3_net y3_net;
  * Y3_OP_UPSAMPLE src0            nearest x2                                parse_model.py:59-75
  * Y3_OP_CONCAT   src0,src1       channel concat [src0, src1]               parse_model.py:102-140
  * Y3_OP_YOLO     src0            [B,g,g,3*(5+C)] -> [B,g,g,3,5+C] view; marks a network output   parse_model.py:163-213
- * Y3_OP_MAXPOOL  (yolov3-tiny)   rejected with Y3_ERR_UNSUPPORTED for now  parse_model.py:78-99
+ * Y3_OP_MAXPOOL  src0            max pool ksize x ksize, stride, pad: 1 'same' / 0 'valid' (yolov3-tiny)   parse_model.py:78-99
  */
 enum { Y3_OP_CONV = 0, Y3_OP_SHORTCUT = 1, Y3_OP_UPSAMPLE = 2, Y3_OP_CONCAT = 3, Y3_OP_YOLO = 4, Y3_OP_MAXPOOL = 5 };
 
@@ -66,7 +66,7 @@ typedef struct {
 /* what the planner decided for one layer; lets CPU-only tests check the host logic without a GPU */
 typedef struct {
     int32_t H, W, C;          /* output shape of the layer's tensor */
-    int32_t kernel;           /* 0 none (fused/view), 1 tcgen05 conv, 2 direct conv, 3 add, 4 upsample, 5 copy */
+    int32_t kernel;           /* 0 none (fused/view), 1 tcgen05 conv, 2 direct conv, 3 add, 4 upsample, 5 copy, 6 maxpool */
     int32_t fused_add;        /* conv: residual tensor id added in the epilogue, else -1 */
     int32_t fused_upsample;   /* conv: 1 if the epilogue writes the 2x upsampled tensor */
     int32_t buffer;           /* arena buffer id holding this tensor, -1 for views of fused ops / outputs */

@@ -12,6 +12,8 @@ Semantics restated, with the reference line each follows:
   * UpSampling2D(size=2) nearest                                        parse_model.py:71-72
   * Concatenate(axis=3)([layers..., inputs...])                         parse_model.py:116-134
   * Reshape((g, g, 3, 5+C)) -- pure view, grid taken from the tensor    parse_model.py:209-210
+  * MaxPooling2D(size, strides, padding): 'same' = ceil(H/stride) outputs, total padding
+    max((Ho-1)*stride + size - H, 0) with the smaller half first, padding never wins the max (-inf)  parse_model.py:78-99
 """
 import numpy as np
 import torch
@@ -56,6 +58,8 @@ def forward(layers, outputs, params, x_nhwc, dtype=torch.float32, keep=None):
                 y = torch.cat([a, t[l.src1]], dim=1)
             elif l.op == OP_YOLO:
                 y = a
+            elif l.op == OP_MAXPOOL:
+                y = maxpool_tf(a, l.ksize, l.stride, l.pad == 1)
             else:
                 raise ValueError(f"oracle: unsupported op {l.op}")
             t[i + 1] = y
@@ -67,6 +71,17 @@ def forward(layers, outputs, params, x_nhwc, dtype=torch.float32, keep=None):
     if keep is not None:
         return outs, {k: t[k].permute(0, 2, 3, 1).contiguous().numpy() for k in keep}
     return outs
+
+
+def maxpool_tf(a_nchw, size, stride, same):
+    """Keras/TF MaxPooling2D on an NCHW torch tensor with TF's 'same' padding rule (asymmetric, -inf padding)."""
+    if same:
+        H, W = a_nchw.shape[2], a_nchw.shape[3]
+        Ho, Wo = -(-H // stride), -(-W // stride)
+        ph = max((Ho - 1) * stride + size - H, 0)
+        pw = max((Wo - 1) * stride + size - W, 0)
+        a_nchw = F.pad(a_nchw, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2), value=float("-inf"))
+    return F.max_pool2d(a_nchw, size, stride)
 
 
 def conv_layer(x_nhwc, kernel_hwio, bias, ksize, stride, leaky, residual=None, upsample=False, dtype=torch.float32):

@@ -42,6 +42,46 @@ def test_builtin_yolov3_structure():
     assert abs(flops / 1e9 - 65.864) < 0.01
 
 
+def test_builtin_yolov3_tiny_structure():
+    """YOLOv3-tiny (reference config/models/yolov3_tiny/*.yaml; parse_model.py:78-99 maxpool): 13 convs, 6 pools,
+    heads at H/32 and H/16; the planner pads the 16-filter stem to 32 stored channels and runs every conv on the
+    tensor cores."""
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import _lib
+    m = y3.ParseModel.builtin_yolov3_tiny(80)
+    g = m.graph
+    assert [co for _, _, co, _ in m.conv_shapes] == [16, 32, 64, 128, 256, 512, 1024, 256, 512, 255, 128, 256, 255]
+    pools = [l for l in g.layers if l.op == _lib.OP_MAXPOOL]
+    assert [(l.ksize, l.stride, l.pad) for l in pools] == [(2, 2, 1)] * 5 + [(2, 1, 1)]
+    cats = [l for l in g.layers if l.op == _lib.OP_CONCAT]
+    assert [(g.channels(c.src0), g.channels(c.src1)) for c in cats] == [(128, 256)]
+    assert len(g.outputs) == 2
+    p = m.plan(416, 416, 4)
+    L = p["layers"]
+    outs = [L[t - 1] for t in g.outputs]
+    assert [(o["H"], o["W"], o["C"]) for o in outs] == [(13, 13, 255), (26, 26, 255)]
+    kinds = [l["kernel"] for l in L]
+    assert kinds.count(1) == 13 and kinds.count(6) == 6 and kinds.count(2) == 0
+    # the stride-1 'same' pool keeps 13x13; the logical channel count of the stem stays 16 (32 are stored)
+    pool_layers = [i for i, l in enumerate(g.layers) if l.op == _lib.OP_MAXPOOL]
+    assert (L[pool_layers[-1]]["H"], L[pool_layers[-1]]["W"]) == (13, 13)
+    assert L[0]["C"] == 16 and L[0]["pix_stride"] == 32 and L[1]["pix_stride"] == 32
+    assert sum(1 for l in L if l["fused_upsample"]) == 1
+    with pytest.raises(_lib.Y3Unsupported):
+        _mini({"a": [_conv(32), {"type": "maxpool", "size_xy": [2, 3], "stride_xy": [2, 2], "padding": "same"}]},
+              [{"name": "head", "layers_config_file": "a", "outputs_layers": [-1]}])
+
+
+@pytest.mark.skipif(not has_ref, reason="reference checkout not present")
+def test_reference_tiny_yamls_match_builtin():
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import graph
+    builtin = y3.ParseModel.builtin_yolov3_tiny(80).graph
+    g_ref = graph.load_model_config(os.path.join(REF, "config/models/yolov3_tiny/model.yaml"), 80)
+    assert _strip(g_ref) == _strip(builtin)
+    assert g_ref.outputs == builtin.outputs
+
+
 @pytest.mark.parametrize("nclasses,filters", [(80, 255), (38, 129), (37, 126), (3, 24)])
 def test_head_filters_expression(nclasses, filters):
     import yolo_v3_tf2_b200 as y3
@@ -200,7 +240,8 @@ def test_planner_arena_no_live_overlap():
 
 def test_unfusable_graphs_fall_back_to_standalone_kernels_or_reject():
     """A shortcut whose conv output is also used elsewhere cannot be fused -> planner schedules an add kernel;
-    maxpool (yolov3-tiny) is rejected loudly -- there is no CPU fallback."""
+    a maxpool gets its own kernel; pool sizes the kernel does not implement are rejected loudly -- there is no CPU
+    fallback."""
     import yolo_v3_tf2_b200 as y3
     from yolo_v3_tf2_b200 import _lib
     layers = [_conv(32, 3), _conv(64, 3, 2), _conv(32, 1), _conv(64, 3),
@@ -214,5 +255,9 @@ def test_unfusable_graphs_fall_back_to_standalone_kernels_or_reject():
     tiny = [_conv(32, 3), {"type": "maxpool", "size_xy": [2, 2], "stride_xy": [2, 2], "padding": "same"},
             _conv("3*(2+2+1+nclasses)", 1, bn=False, act="linear"), {"type": "yolo", "grid_size": 13}]
     m2 = _mini({"a": tiny}, [{"name": "head", "layers_config_file": "a", "outputs_layers": [-1]}])
+    assert [l["kernel"] for l in m2.plan(64, 64, 1)["layers"]][:2] == [1, 6]
+    big = [_conv(32, 3), {"type": "maxpool", "size_xy": [5, 5], "stride_xy": [1, 1], "padding": "same"},
+           _conv("3*(2+2+1+nclasses)", 1, bn=False, act="linear"), {"type": "yolo", "grid_size": 13}]
+    m3 = _mini({"a": big}, [{"name": "head", "layers_config_file": "a", "outputs_layers": [-1]}])
     with pytest.raises(_lib.Y3Unsupported, match="maxpool"):
-        m2.plan(64, 64, 1)
+        m3.plan(64, 64, 1)

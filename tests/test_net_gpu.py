@@ -38,6 +38,52 @@ def test_forward_vs_oracle(cuda, init, size, B, C):
     _compare(grids, ref)
 
 
+@pytest.mark.parametrize("init,size,B,C", [("variance", 64, 2, 80), ("keras", 96, 3, 80), ("variance", 416, 2, 80),
+                                           ("variance", 160, 1, 37)])
+def test_tiny_forward_vs_oracle(cuda, init, size, B, C):
+    """YOLOv3-tiny (config/models/yolov3_tiny): maxpool kernel incl. the stride-1 'same' pool, the 16-filter stem stored
+    as 32 channels, 2 heads."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from oracle import net_oracle
+    model = y3.ParseModel.builtin_yolov3_tiny(C).init_weights(init, seed=11)
+    x = np.random.default_rng(1).random((B, size, size, 3), dtype=np.float32)
+    grids = model(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    ref = net_oracle.forward(model.graph.layers, model.graph.outputs, model._params, x)
+    assert [tuple(g.shape) for g in grids] == [(B, size // s, size // s, 3, 5 + C) for s in (32, 16)]
+    _compare(grids, ref)
+
+
+def test_maxpool_variants_vs_oracle(cuda):
+    """'valid' pooling, 3x3 stride-2 'same' pooling and odd spatial sizes through a small graph."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from oracle import net_oracle
+
+    def conv(f, size=3, bn=True, act="leaky"):
+        d = {"type": "convolutional", "filters": f, "size": size, "stride": 1, "pad": 1, "activation": act}
+        if bn:
+            d["batch_normalize"] = 1
+        return d
+
+    def pool(size, stride, padding):
+        return {"type": "maxpool", "size_xy": [size, size], "stride_xy": [stride, stride], "padding": padding}
+
+    layers = [{"type": "route", "source": {"inputs": [0]}}, conv(32), pool(3, 2, "same"), conv(64), pool(2, 2, "valid"),
+              conv(64), pool(2, 1, "same"), pool(3, 1, "valid"), conv(64), conv("3*(2+2+1+nclasses)", 1, bn=False, act="linear"),
+              {"type": "yolo", "grid_size": 0}]
+    subs = [{"name": "head", "layers_config_file": "a", "outputs_layers": [-1]}]
+    model = y3.ParseModel().build_model(None, subs, "head", nclasses=3, layer_lists={"a": layers})
+    model.init_weights("variance", seed=2)
+    x = np.random.default_rng(4).random((2, 96, 96, 3), dtype=np.float32)   # 96 -> 48 -> 24 -> 24 -> 22
+    grids = model(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    ref = net_oracle.forward(model.graph.layers, model.graph.outputs, model._params, x)
+    assert tuple(grids[0].shape) == (2, 22, 22, 3, 8)
+    _compare(grids, ref)
+
+
 def test_forward_batch_invariance_and_rebatch(cuda):
     """Images are independent: a batch of 5 gives the same rows as 5 single-image calls (bit-exact), and growing the
     batch re-plans the arena."""

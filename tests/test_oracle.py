@@ -135,3 +135,24 @@ def test_net_oracle_conv_semantics():
     up = net_oracle.conv_layer(np.arange(4, dtype=np.float32).reshape(1, 2, 2, 1), np.ones((1, 1, 1, 1), np.float32),
                                np.zeros(1, np.float32), 1, 1, False, upsample=True)
     assert up[0, :, :, 0].tolist() == [[0, 0, 1, 1], [0, 0, 1, 1], [2, 2, 3, 3], [2, 2, 3, 3]]
+
+
+def test_maxpool_oracle_tf_same_rule():
+    """Keras MaxPooling2D 'same' (parse_model.py:78-99): ceil(H/stride) outputs, padding after the data when the total is
+    odd, and the padding never wins; 'valid' drops the ragged edge."""
+    import torch
+    from oracle import net_oracle
+    a = torch.arange(25, dtype=torch.float32).reshape(1, 1, 5, 5) - 30.0      # all negative: zero padding would win
+    s1 = net_oracle.maxpool_tf(a, 2, 1, True)                                   # yolov3-tiny's last pool
+    assert s1.shape == (1, 1, 5, 5)
+    exp = a.clone()
+    exp[..., :4, :4] = a[..., 1:, 1:]
+    exp[..., :4, 4] = a[..., 1:, 4]
+    exp[..., 4, :4] = a[..., 4, 1:]
+    assert torch.equal(s1, exp)
+    s2 = net_oracle.maxpool_tf(a, 2, 2, True)
+    assert s2.shape == (1, 1, 3, 3) and s2[0, 0, 2, 2] == a[0, 0, 4, 4] and s2[0, 0, 0, 0] == a[0, 0, 1, 1]
+    v = net_oracle.maxpool_tf(a, 2, 2, False)
+    assert v.shape == (1, 1, 2, 2) and v[0, 0, 1, 1] == a[0, 0, 3, 3]
+    s3 = net_oracle.maxpool_tf(a, 3, 2, True)      # total padding 2 -> one before, one after
+    assert s3.shape == (1, 1, 3, 3) and s3[0, 0, 0, 0] == a[0, 0, 1, 1] and s3[0, 0, 2, 2] == a[0, 0, 4, 4]

@@ -91,6 +91,51 @@ def yolov3_config():
     return model, files
 
 
+def _maxpool(size, stride):
+    return {"type": "maxpool", "size_xy": [size, size], "stride_xy": [stride, stride], "padding": "same"}
+
+
+def yolov3_tiny_config():
+    """YOLOv3-tiny in the reference's schema (config/models/yolov3_tiny/{model,backbone,neck0-1,head0-1}.yaml):
+    7 conv + 6 maxpool backbone (the last pool is 2x2 stride 1 'same'), two heads at H/32 and H/16."""
+    backbone = [_route(inputs=[0])]
+    for f in (16, 32, 64, 128, 256):
+        backbone += [_conv(f, 3), _maxpool(2, 2)]
+    backbone += [_conv(512, 3), _maxpool(2, 1), _conv(1024, 3)]
+    files = {
+        "builtin/yolov3_tiny/backbone.yaml": backbone,
+        "builtin/yolov3_tiny/neck0.yaml": [_route(inputs=[0]), _conv(256, 1)],
+        "builtin/yolov3_tiny/head0.yaml": [_route(inputs=[0]), _conv(512, 3), _conv(FILTER_EXPR, 1, bn=False, act="linear"),
+                                           {"type": "yolo", "grid_size": 13, "jitter": 0.3}],
+        "builtin/yolov3_tiny/neck1.yaml": [_route(inputs=[-2]), _conv(128, 1), {"type": "upsample", "stride": 2},
+                                           _route(layers=[-1], inputs=[-1])],
+        "builtin/yolov3_tiny/head1.yaml": [_route(inputs=[0]), _conv(256, 3), _conv(FILTER_EXPR, 1, bn=False, act="linear"),
+                                           {"type": "yolo", "grid_size": 26, "jitter": 0.3}],
+    }
+
+    def src(*pairs):
+        return {"source": [{"name": n, "entry_index": i} for n, i in pairs]}
+
+    subs = [
+        {"name": "backbone", "layers_config_file": "builtin/yolov3_tiny/backbone.yaml", "outputs_layers": [-5, -1]},
+        {"name": "neck0", "inputs": src(("backbone", -1)), "layers_config_file": "builtin/yolov3_tiny/neck0.yaml", "outputs_layers": [-1]},
+        {"name": "head0", "inputs": src(("neck0", 0)), "layers_config_file": "builtin/yolov3_tiny/head0.yaml", "outputs_layers": [-1]},
+        {"name": "neck1", "inputs": src(("neck0", -1), ("backbone", -2)), "layers_config_file": "builtin/yolov3_tiny/neck1.yaml", "outputs_layers": [-1]},
+        {"name": "head1", "inputs": src(("neck1", 0)), "layers_config_file": "builtin/yolov3_tiny/head1.yaml", "outputs_layers": [-1]},
+    ]
+    model = {"decay_factor": 0.0005, "output_stage": "head", "grid_sizes": [13, 26], "sub_models_configs": subs}
+    return model, files
+
+
+# the reference's tiny anchors are not shipped; the Darknet yolov3-tiny anchors / 416, largest first, as a [2,3,2] table
+TINY_ANCHORS_PX = [(81, 82), (135, 169), (344, 319), (10, 14), (23, 27), (37, 58)]
+
+
+def tiny_anchors():
+    import numpy as np
+    return (np.array(TINY_ANCHORS_PX, dtype=np.float64) / 416.0).astype(np.float32).reshape(2, 3, 2)
+
+
 # COCO anchors of the reference (datasets/coco2012/anchors.txt:1-9 = the Darknet yolov3 anchors / 416), largest first
 COCO_ANCHORS_PX = [(116, 90), (156, 198), (373, 326), (30, 61), (62, 45), (59, 119), (10, 13), (16, 30), (33, 23)]
 

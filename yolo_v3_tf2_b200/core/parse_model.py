@@ -218,6 +218,14 @@ class ParseModel:
         return Y3Model(graph_mod.load_model_config(model_config_file, nclasses))
 
     @staticmethod
+    def builtin_yolov3_tiny(nclasses):
+        """YOLOv3-tiny from the built-in description (identical graph to config/models/yolov3_tiny/model.yaml)."""
+        from .. import configs
+        model, files = configs.yolov3_tiny_config()
+        return ParseModel().build_model(None, model["sub_models_configs"], model["output_stage"], nclasses=nclasses,
+                                        layer_lists=files)
+
+    @staticmethod
     def builtin_yolov3(nclasses):
         """Darknet-53 YOLOv3 from the built-in description (identical graph to config/models/yolov3/model.yaml)."""
         from .. import configs

@@ -134,4 +134,49 @@ __global__ void upsample2_view_kernel(const ViewArgs v) {   // reference parse_m
     }
 }
 
+// reference parse_model.py:78-99  MaxPooling2D(pool_size, strides, padding): windows are clipped at the border, i.e. the
+// 'same' padding never wins the max (yolov3-tiny: 2x2 stride 2, and 2x2 stride 1 'same' = window {x, x+1} clipped)
+struct PoolArgs {
+    const __nv_bfloat16* a;  long long a_stride;
+    __nv_bfloat16* out;      long long out_stride;
+    long long npix;          // output pixels
+    int C;                   // channels (multiple of 8)
+    int H, W, Ho, Wo;
+    int size, stride, pad_lo;
+};
+
+__global__ void maxpool_view_kernel(const PoolArgs v) {
+    const int c8 = v.C >> 3;
+    const long long total = v.npix * c8;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long pix = e / c8;
+        const int c = (int)(e - pix * c8) << 3;
+        const int hw = v.Ho * v.Wo;
+        const long long n = pix / hw;
+        const int rem = (int)(pix - n * hw);
+        const int yo = rem / v.Wo, xo = rem - yo * v.Wo;
+        const int y0 = yo * v.stride - v.pad_lo, x0 = xo * v.stride - v.pad_lo;
+        __nv_bfloat162 m[4];
+        bool first = true;
+        for (int dy = 0; dy < v.size; ++dy) {
+            const int y = y0 + dy;
+            if (y < 0 || y >= v.H) continue;
+            for (int dx = 0; dx < v.size; ++dx) {
+                const int x = x0 + dx;
+                if (x < 0 || x >= v.W) continue;
+                const uint4 u = *reinterpret_cast<const uint4*>(v.a + ((n * v.H + y) * v.W + x) * v.a_stride + c);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m[i] = first ? h[i] : __hmax2(m[i], h[i]);
+                first = false;
+            }
+        }
+        if (first) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[i] = __floats2bfloat162_rn(0.f, 0.f);
+        }
+        *reinterpret_cast<uint4*>(v.out + pix * v.out_stride + c) = *reinterpret_cast<uint4*>(m);
+    }
+}
+
 }  // namespace y3

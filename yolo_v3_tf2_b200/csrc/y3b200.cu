@@ -416,6 +416,8 @@ namespace {
 
 struct TensorInfo {
     int H = 0, W = 0, C = 0;
+    int Cp = 0;                   // channels as stored (C rounded up to a multiple of 32 for bf16 conv outputs: the extra
+                                  // channels are produced by zero weights + zero bias and read by zero weights)
     int producer = -1;            // layer index, -1 for the input image
     std::vector<int> consumers;   // layer indices
     bool materialized = false;    // some kernel writes it to memory
@@ -433,7 +435,8 @@ struct BufferInfo {
 };
 
 struct ConvWeights {
-    int cin = 0, cout = 0, k = 0, cout_pad = 0;
+    int cin = 0, cout = 0, k = 0, cout_pad = 0;   // cin: as stored (physical); cout: logical filters
+    int cin_logical = 0;
     bool direct = false;
     bool flat_order = false;  // K ordered (channel block, r, s, c) for the flat-patch kernel
     int flat_bk = 0;
@@ -444,7 +447,8 @@ struct ConvWeights {
 };
 
 struct Step {
-    int kind = 0;          // 1 tc conv, 2 direct conv, 3 add, 4 upsample, 5 copy
+    int kind = 0;          // 1 tc conv, 2 direct conv, 3 add, 4 upsample, 5 copy, 6 maxpool
+    int cout_p = 0;        // conv: output channels as stored (>= filters)
     int layer = -1;
     int conv_idx = -1;
     int src = -1, src2 = -1, dst = -1;   // tensor ids
@@ -487,6 +491,7 @@ int plan_net(y3_net& n) {
     n.tensors[0].H = n.H;
     n.tensors[0].W = n.W;
     n.tensors[0].C = 3;
+    n.tensors[0].Cp = 3;
     n.tensors[0].materialized = true;
 
     // ---- shapes + validation ----
@@ -539,8 +544,17 @@ int plan_net(y3_net& n) {
                                                     std::to_string(a.C) + " != 3*(5+nclasses)");
                 t.H = a.H; t.W = a.W; t.C = a.C;
                 break;
-            case Y3_OP_MAXPOOL:
-                return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": maxpool (yolov3-tiny) is not on this path yet");
+            case Y3_OP_MAXPOOL: {
+                // Keras MaxPooling2D: 'same' -> ceil(H / stride), 'valid' -> floor((H - size) / stride) + 1
+                if (d.ksize < 1 || d.ksize > 3 || (d.stride != 1 && d.stride != 2))
+                    return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": maxpool size must be 1..3 and stride 1 or 2");
+                if (d.src0 == 0) return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": op on the raw input image");
+                if (d.pad) { t.H = (a.H + d.stride - 1) / d.stride; t.W = (a.W + d.stride - 1) / d.stride; }
+                else { t.H = (a.H - d.ksize) / d.stride + 1; t.W = (a.W - d.ksize) / d.stride + 1; }
+                if (t.H <= 0 || t.W <= 0) return fail(Y3_ERR_INVALID, "layer " + std::to_string(i) + ": empty output");
+                t.C = a.C;
+                break;
+            }
             default:
                 return fail(Y3_ERR_INVALID, std::to_string(d.op) + " not recognized as layer_conf type");
         }
@@ -549,6 +563,24 @@ int plan_net(y3_net& n) {
         n.plans[i].H = t.H; n.plans[i].W = t.W; n.plans[i].C = t.C;
         n.plans[i].fused_add = -1;
         n.plans[i].buffer = -1;
+    }
+
+    // ---- stored channel counts: bf16 conv outputs are padded to a multiple of 32 channels (yolov3-tiny's 16-filter stem);
+    // everything downstream inherits the padding, heads (fp32 outputs) are never padded ----
+    for (int i = 0; i < L; ++i) {
+        const y3_layer_desc& d = n.layers[i];
+        TensorInfo& t = n.tensors[i + 1];
+        switch (d.op) {
+            case Y3_OP_CONV: t.Cp = (t.C + 31) / 32 * 32; break;
+            case Y3_OP_CONCAT: {
+                const TensorInfo &a = n.tensors[d.src0], &b = n.tensors[d.src1];
+                if (a.Cp != a.C || b.Cp != b.C)
+                    return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": concat of a tensor whose channel count is not a multiple of 32");
+                t.Cp = t.C;
+                break;
+            }
+            default: t.Cp = n.tensors[d.src0].Cp; break;
+        }
     }
 
     // ---- fusion: conv (+shortcut) (+upsample) (+yolo output) ----
@@ -564,7 +596,7 @@ int plan_net(y3_net& n) {
             if (cons.size() == 1 && n.layers[cons[0]].op == Y3_OP_SHORTCUT) {
                 const y3_layer_desc& s = n.layers[cons[0]];
                 const int other = (s.src0 == r) ? s.src1 : s.src0;
-                if (other != r && other != 0 && n.tensors[r].C % 32 == 0) {
+                if (other != r && other != 0) {
                     residual[i] = other;
                     layer_fused[cons[0]] = 1;
                     r = cons[0] + 1;
@@ -573,7 +605,7 @@ int plan_net(y3_net& n) {
         }
         {
             const auto& cons = n.tensors[r].consumers;
-            if (cons.size() == 1 && n.layers[cons[0]].op == Y3_OP_UPSAMPLE && n.tensors[r].C % 32 == 0) {
+            if (cons.size() == 1 && n.layers[cons[0]].op == Y3_OP_UPSAMPLE) {
                 fused_up[i] = 1;
                 layer_fused[cons[0]] = 1;
                 r = cons[0] + 1;
@@ -601,22 +633,26 @@ int plan_net(y3_net& n) {
                 return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": yolo output consumed by another layer");
         } else if ((op == Y3_OP_SHORTCUT || op == Y3_OP_UPSAMPLE) && !layer_fused[i]) {
             n.tensors[i + 1].materialized = true;
+        } else if (op == Y3_OP_MAXPOOL) {
+            n.tensors[i + 1].materialized = true;
         } else if (op == Y3_OP_CONCAT) {
             n.tensors[i + 1].materialized = true;
         }
     }
     if (n.outputs.empty()) return fail(Y3_ERR_INVALID, "network has no yolo output");
+    for (int t = 1; t <= L; ++t)
+        if (n.tensors[t].fp32_output) n.tensors[t].Cp = n.tensors[t].C;
 
     // every non-input bf16 tensor must have C % 8 == 0 (16-byte vector stores / TMA strides)
     for (int t = 1; t <= L; ++t)
-        if (n.tensors[t].materialized && !n.tensors[t].fp32_output && n.tensors[t].C % 8 != 0)
+        if (n.tensors[t].materialized && !n.tensors[t].fp32_output && n.tensors[t].Cp % 8 != 0)
             return fail(Y3_ERR_UNSUPPORTED, "tensor " + std::to_string(t) + ": channel count must be a multiple of 8");
 
     // ---- concat placement: operands are produced directly inside the concat buffer when possible ----
     auto new_buffer = [&](int H, int W, int C) {
         BufferInfo b;
         b.H = H; b.W = W; b.C = C;
-        b.bytes = (int64_t)n.max_batch * H * W * C * 2;
+        b.bytes = (int64_t)n.max_batch * H * W * C * 2;   // C = channels as stored
         n.buffers.push_back(b);
         return (int)n.buffers.size() - 1;
     };
@@ -678,12 +714,12 @@ int plan_net(y3_net& n) {
         TensorInfo& ti = n.tensors[t];
         if (ti.materialized && !ti.fp32_output && ti.buffer < 0) {
             if (ti.padded) {
-                ti.buffer = new_buffer(ti.H + 1, ti.W + 1, ti.C);
+                ti.buffer = new_buffer(ti.H + 1, ti.W + 1, ti.Cp);
             } else {
-                ti.buffer = new_buffer(ti.H, ti.W, ti.C);
+                ti.buffer = new_buffer(ti.H, ti.W, ti.Cp);
             }
             ti.chan_off = 0;
-            ti.pix_stride = ti.C;
+            ti.pix_stride = ti.Cp;
         }
     }
 
@@ -712,8 +748,9 @@ int plan_net(y3_net& n) {
             const TensorInfo& a = n.tensors[d.src0];
             conv_geometry(a.H, a.W, d.ksize, d.stride, d.pad, s.Ho, s.Wo, s.pad_lo, s.pad_hi);
             ConvWeights& w = n.convs[s.conv_idx];
-            w.cin = a.C; w.cout = d.filters; w.k = d.ksize;
-            bool tc_ok = pick_cfg(a.C, d.filters, d.ksize, s.cfg);
+            w.cin = a.Cp; w.cin_logical = a.C; w.cout = d.filters; w.k = d.ksize;
+            s.cout_p = n.tensors[writes[i]].fp32_output ? d.filters : (d.filters + 31) / 32 * 32;
+            bool tc_ok = pick_cfg(a.Cp, s.cout_p, d.ksize, s.cfg);
             if (tc_ok && s.cfg.gather == 2 && (d.src0 != 0 || residual[i] >= 0 || fused_up[i] || n.tensors[writes[i]].fp32_output))
                 tc_ok = false;
             if (tc_ok && s.cfg.gather != 2 && d.src0 == 0) tc_ok = false;
@@ -724,8 +761,8 @@ int plan_net(y3_net& n) {
                 const long long M = (long long)n.max_batch * s.Ho * s.Wo;
                 const long long pairs = ((M + y3::kBlockM - 1) / y3::kBlockM + 1) / 2;
                 const long long clusters = std::max(1, n.ctx->sms / 2);
-                const long long r256 = (pairs * ((d.filters + 255) / 256) + clusters - 1) / clusters;
-                const long long r128 = (pairs * ((d.filters + 127) / 128) + clusters - 1) / clusters;
+                const long long r256 = (pairs * ((s.cout_p + 255) / 256) + clusters - 1) / clusters;
+                const long long r128 = (pairs * ((s.cout_p + 127) / 128) + clusters - 1) / clusters;
                 if ((double)r128 * 0.5 * 1.10 < (double)r256 * 0.97) {
                     s.cfg.block_n = 128;
                     s.cfg.stages = st2(128);
@@ -749,10 +786,8 @@ int plan_net(y3_net& n) {
             }
             if (tc_ok) s.out_padded = n.tensors[writes[i]].padded ? 1 : 0;
             if (tc_ok) {
-                if (!n.tensors[writes[i]].fp32_output && d.filters % 32 != 0)
-                    return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": bf16 conv outputs need filters % 32 == 0");
                 s.kind = 1;
-                w.cout_pad = ((d.filters + s.cfg.block_n - 1) / s.cfg.block_n) * s.cfg.block_n;
+                w.cout_pad = ((s.cout_p + s.cfg.block_n - 1) / s.cfg.block_n) * s.cfg.block_n;
                 w.stem_hilo = (s.cfg.gather == 2);
                 w.flat_order = s.flat != 0;
                 w.flat_bk = s.cfg.swz / 2;
@@ -760,10 +795,10 @@ int plan_net(y3_net& n) {
                 pl.flat = s.flat;
             } else {
                 // direct CUDA-core conv: fp32 NHWC network input with 3 channels, bf16 output, no fusion
-                if (d.src0 != 0 || a.C != 3 || (d.filters != 32 && d.filters != 16) || residual[i] >= 0 || fused_up[i] ||
+                if (d.src0 != 0 || a.C != 3 || d.filters != 32 || residual[i] >= 0 || fused_up[i] ||
                     n.tensors[writes[i]].fp32_output)
                     return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(i) + ": conv with Cin=" + std::to_string(a.C) +
-                                                        " is only supported as the 3-channel stem (16/32 filters)");
+                                                        " is only supported as the 3-channel stem");
                 s.kind = 2;
                 w.direct = true;
                 w.cout_pad = d.filters;
@@ -773,6 +808,20 @@ int plan_net(y3_net& n) {
             pl.fused_upsample = fused_up[i];
             const int step_id = (int)n.steps.size();
             touch(s.src, step_id); touch(s.src2, step_id); touch(s.dst, step_id);
+            n.steps.push_back(s);
+        } else if (d.op == Y3_OP_MAXPOOL) {
+            Step s;
+            s.kind = 6;
+            s.layer = i;
+            s.src = d.src0;
+            s.dst = i + 1;
+            const TensorInfo& a = n.tensors[d.src0];
+            s.Ho = n.tensors[i + 1].H; s.Wo = n.tensors[i + 1].W;
+            // Keras 'same': total padding max((Ho-1)*stride + size - H, 0), the smaller half first
+            s.pad_lo = d.pad ? std::max((s.Ho - 1) * d.stride + d.ksize - a.H, 0) / 2 : 0;
+            pl.kernel = 6;
+            const int step_id = (int)n.steps.size();
+            touch(s.src, step_id); touch(s.dst, step_id);
             n.steps.push_back(s);
         } else if ((d.op == Y3_OP_SHORTCUT || d.op == Y3_OP_UPSAMPLE) && !layer_fused[i]) {
             if (d.src0 == 0 || (d.op == Y3_OP_SHORTCUT && d.src1 == 0))
@@ -865,23 +914,23 @@ int build_maps(y3_net& n) {
         if (s.flat) {
             // haloed-flat input as a [pixels, channels] matrix; negative / past-the-end rows are zero filled by TMA
             const __nv_bfloat16* ap = tensor_ptr(n, s.src);
-            rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * (a.H + 1) * (a.W + 1), a.C, a.pix_stride,
+            rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * (a.H + 1) * (a.W + 1), a.Cp, a.pix_stride,
                              s.box_rows, s.cfg.swz, false);
         } else if (s.cfg.gather == 0) {
             const __nv_bfloat16* ap = tensor_ptr(n, s.src);
             if (s.in_padded) {
-                rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * (a.H + 1) * (a.W + 1), a.C, a.pix_stride,
+                rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * (a.H + 1) * (a.W + 1), a.Cp, a.pix_stride,
                                  y3::kBlockM, s.cfg.swz, false);
             } else if (d.ksize == 1 && d.stride == 1) {
-                rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * a.H * a.W, a.C, a.pix_stride, y3::kBlockM,
+                rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * a.H * a.W, a.Cp, a.pix_stride, y3::kBlockM,
                                  s.cfg.swz, false);
             } else {
-                rc = make_map_im2col(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, a.C, a.pix_stride, d.ksize, d.stride,
+                rc = make_map_im2col(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, a.Cp, a.pix_stride, d.ksize, d.stride,
                                      s.pad_lo, s.pad_hi, s.cfg.swz);
             }
         }
         if (rc) return rc;
-        const uint64_t K = (s.cfg.gather == 2) ? 64 : (uint64_t)d.ksize * d.ksize * a.C;
+        const uint64_t K = (s.cfg.gather == 2) ? 64 : (uint64_t)d.ksize * d.ksize * a.Cp;
         rc = make_map_2d(n.ctx->drv, &s.tmB, w.w, w.cout_pad, K, K, s.cfg.block_n / (s.cfg.gather ? 1 : (s.cfg.cluster >= 2 ? 2 : 1)), s.cfg.swz, true);
         if (rc) return rc;
         const TensorInfo& o = n.tensors[s.dst];
@@ -893,10 +942,10 @@ int build_maps(y3_net& n) {
         if (s.tma_out) {
             const int cw = s.tma_out;
             const uint64_t rows = (uint64_t)n.max_batch * s.Ho * s.Wo;
-            rc = make_map_epi(n.ctx->drv, &s.tmO, tensor_ptr(n, s.dst), rows, d.filters, o.pix_stride, cw);
+            rc = make_map_epi(n.ctx->drv, &s.tmO, tensor_ptr(n, s.dst), rows, s.cout_p, o.pix_stride, cw);
             if (rc) return rc;
             if (s.src2 >= 0) {
-                rc = make_map_epi(n.ctx->drv, &s.tmR, tensor_ptr(n, s.src2), rows, d.filters, n.tensors[s.src2].pix_stride, cw);
+                rc = make_map_epi(n.ctx->drv, &s.tmR, tensor_ptr(n, s.src2), rows, s.cout_p, n.tensors[s.src2].pix_stride, cw);
                 if (rc) return rc;
             }
         }
@@ -921,8 +970,9 @@ y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
         a.num_k_blocks = d.ksize * d.ksize * a.kblocks_per_tap;
     }
     a.tiles_m = (a.M + y3::kBlockM - 1) / y3::kBlockM;
-    a.tiles_n = (d.filters + s.cfg.block_n - 1) / s.cfg.block_n;
-    a.cout = d.filters;
+    const int cout_p = s.cout_p > 0 ? s.cout_p : d.filters;   // channels as stored (zero weights / bias beyond filters)
+    a.tiles_n = (cout_p + s.cfg.block_n - 1) / s.cfg.block_n;
+    a.cout = cout_p;
     a.leaky = d.activation;
     a.upsample = s.fused_up;
     a.it_h = s.Ho; a.it_w = s.Wo;
@@ -1082,7 +1132,9 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
     const bool bn = d.batch_normalize != 0;
     if (bn && !(gamma && beta && mean && var)) return fail(Y3_ERR_INVALID, "conv has batch_normalize: BN vectors required");
     if (!bn && !bias) return fail(Y3_ERR_INVALID, "conv without batch_normalize: bias required");
-    const int k = w.k, cin = w.cin, cout = w.cout;
+    // the caller's kernel is [k][k][cin_logical][cout]; it is packed with the stored channel count (zero weights on the
+    // padding channels of the input, zero rows for the padding channels of the output)
+    const int k = w.k, cin = w.cin, cin_l = w.cin_logical, cout = w.cout;
     const size_t K = (size_t)k * k * cin;
     std::vector<float> scale(cout, 1.0f), shift(w.cout_pad, 0.0f);
     for (int o = 0; o < cout; ++o) {
@@ -1096,6 +1148,7 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
         }
     }
     if (w.direct) {
+        if (cin != cin_l) return fail(Y3_ERR_STATE, "internal: direct conv with padded input channels");
         std::vector<float> packed(K * cout);
         for (size_t kk = 0; kk < K; ++kk)
             for (int o = 0; o < cout; ++o) packed[kk * cout + o] = kernel[kk * cout + o] * scale[o];   // HWIO is already [K][Cout]
@@ -1103,7 +1156,7 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
     } else if (w.stem_hilo) {
         // columns [0,27) multiply bf16(x), columns [32,59) multiply the bf16 remainder x - bf16(x): same weights twice
         std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * 64, __float2bfloat16(0.0f));
-        for (size_t kk = 0; kk < K; ++kk)
+        for (size_t kk = 0; kk < (size_t)k * k * cin_l; ++kk)
             for (int o = 0; o < cout; ++o) {
                 const __nv_bfloat16 v = __float2bfloat16(kernel[kk * cout + o] * scale[o]);
                 packed[(size_t)o * 64 + kk] = v;
@@ -1112,11 +1165,11 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
         Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     } else {
         std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * K, __float2bfloat16(0.0f));
-        for (size_t kk = 0; kk < K; ++kk) {
-            size_t dst = kk;   // HWIO row kk = (tap, channel)
+        for (size_t kk = 0; kk < (size_t)k * k * cin_l; ++kk) {   // HWIO row kk = (tap, logical channel)
+            const size_t tap = kk / cin_l, ch = kk % cin_l;
+            size_t dst = tap * cin + ch;
             if (w.flat_order) {
                 // flat-patch kernel: K ordered (channel block, tap, channel in block) so one patch serves 9 K blocks
-                const size_t tap = kk / cin, ch = kk % cin;
                 dst = ((ch / w.flat_bk) * (size_t)(k * k) + tap) * w.flat_bk + ch % w.flat_bk;
             }
             for (int o = 0; o < cout; ++o) packed[(size_t)o * K + dst] = __float2bfloat16(kernel[kk * cout + o] * scale[o]);
@@ -1177,7 +1230,7 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
             const TensorInfo& a = net->tensors[s.src];
             const TensorInfo& o = net->tensors[s.dst];
             const ConvWeights& w = net->convs[s.conv_idx];
-            y3::ConvArgs ca = conv_args(s, d, a.C, B);
+            y3::ConvArgs ca = conv_args(s, d, a.Cp, B);
             ca.bias = w.bias;
             if (s.src2 >= 0) {
                 ca.residual = tensor_ptr(*net, s.src2);
@@ -1227,6 +1280,21 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
             if (d.filters == 32) y3::conv_first_kernel<3, 32><<<grid, 128, smem, st>>>(fa);
             else y3::conv_first_kernel<3, 16><<<grid, 128, smem, st>>>(fa);
             Y3_CUDA(cudaGetLastError());
+        } else if (s.kind == 6) {
+            const TensorInfo& a = net->tensors[s.src];
+            const TensorInfo& o = net->tensors[s.dst];
+            y3::PoolArgs v{};
+            v.a = tensor_ptr(*net, s.src);
+            v.a_stride = a.pix_stride;
+            v.out = tensor_ptr(*net, s.dst);
+            v.out_stride = o.pix_stride;
+            v.C = a.Cp;
+            v.H = a.H; v.W = a.W; v.Ho = o.H; v.Wo = o.W;
+            v.size = d.ksize; v.stride = d.stride; v.pad_lo = s.pad_lo;
+            v.npix = (long long)B * o.H * o.W;
+            const unsigned grid = grid_for(v.npix * (v.C / 8), 256, sms);
+            y3::maxpool_view_kernel<<<grid, 256, 0, st>>>(v);
+            Y3_CUDA(cudaGetLastError());
         } else {
             const TensorInfo& a = net->tensors[s.src];
             const TensorInfo& o = net->tensors[s.dst];
@@ -1235,7 +1303,7 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
             v.a_stride = a.pix_stride;
             v.out = tensor_ptr(*net, s.dst) + s.dst_chan_extra;
             v.out_stride = o.pix_stride;
-            v.C = a.C;
+            v.C = a.Cp;
             v.Ho = o.H; v.Wo = o.W;
             v.npix = (long long)B * o.H * o.W;
             const unsigned grid = grid_for(v.npix * (v.C / 8), 256, sms);

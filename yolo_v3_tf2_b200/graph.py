@@ -108,6 +108,19 @@ def _conv_layer(conf, src, nclasses, sub_model, yaml_index):
                  activation=1 if conf["activation"] == "leaky" else 0, sub_model=sub_model, yaml_index=yaml_index)
 
 
+def _maxpool_layer(conf, src, sub_model, yaml_index):
+    """reference parse_model.py:78-99: MaxPooling2D(pool_size=size_xy, strides=stride_xy, padding=padding)."""
+    stride_xy = list(map(int, conf["stride_xy"]))
+    size_xy = list(map(int, conf["size_xy"]))
+    padding = str(conf["padding"]).lower()
+    if len(size_xy) != 2 or len(stride_xy) != 2 or size_xy[0] != size_xy[1] or stride_xy[0] != stride_xy[1]:
+        raise _lib.Y3Unsupported(f"maxpool with non-square size/stride {size_xy}/{stride_xy}")
+    if padding not in ("same", "valid"):
+        raise ValueError(f"Invalid maxpool padding: {conf['padding']}")
+    return Layer(op=_lib.OP_MAXPOOL, src0=src, ksize=size_xy[0], stride=stride_xy[0], pad=1 if padding == "same" else 0,
+                 sub_model=sub_model, yaml_index=yaml_index)
+
+
 def _resolve(path, search_dirs):
     """``layers_config_file`` paths are relative to the reference repo root (its CWD); try CWD, then search_dirs."""
     if os.path.isabs(path) and os.path.exists(path):
@@ -179,7 +192,7 @@ def build_graph(sub_models_configs, output_stage="head", nclasses=0, search_dirs
             elif t == "upsample":
                 x = g.add(Layer(op=_lib.OP_UPSAMPLE, src0=x, stride=int(conf["stride"]), sub_model=name, yaml_index=yi))
             elif t == "maxpool":
-                x = g.add(Layer(op=_lib.OP_MAXPOOL, src0=x, sub_model=name, yaml_index=yi))
+                x = g.add(_maxpool_layer(conf, x, name, yi))
             else:
                 raise ValueError("{} not recognized as layer_conf type".format(t))
             layers.append(x)
@@ -232,7 +245,7 @@ def build_graph_legacy(model_config, nclasses=0) -> Graph:
             elif t == "upsample":
                 x = g.add(Layer(op=_lib.OP_UPSAMPLE, src0=x, stride=int(conf["stride"]), sub_model=name, yaml_index=yi))
             elif t == "maxpool":
-                x = g.add(Layer(op=_lib.OP_MAXPOOL, src0=x, sub_model=name, yaml_index=yi))
+                x = g.add(_maxpool_layer(conf, x, name, yi))
             else:
                 raise ValueError("{} not recognized as layer_conf type".format(t))
             tensors.append(x)
