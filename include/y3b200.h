@@ -129,6 +129,14 @@ int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, i
 int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, int max_boxes, float iou_thr,
            float score_thr, int32_t* selected, int32_t* num_valid, int32_t* status, void* stream);
 
+/* Input pre-processing (reference inference.py:157-158, core/load_tfrecords.py:46, core/utils.py:17-28): for each of B
+ * images, tf.image.resize-compatible bilinear resampling (half-pixel centres, no antialias) of a uint8 / float32
+ * [H, W, 3] device image to out_h x out_w, placed at (off_y, off_x) of a zero-filled dst_h x dst_w canvas
+ * (pad_to_bounding_box), optionally divided by 255.  image_descs_dev: device array of B records of 8 int64
+ * {src pointer, H, W, dtype (0 uint8, 1 float32), out_h, out_w, off_y, off_x}.  out: [B, dst_h, dst_w, 3] float32. */
+int y3_preprocess(y3_ctx* ctx, const void* image_descs_dev, int B, int dst_h, int dst_w, int divide_by_255, float* out,
+                  void* stream);
+
 int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_idx, const float* scores,
                          const int32_t* selected, const int32_t* num_valid, int B, int N, int max_boxes,
                          float* out_boxes, int64_t* out_classes, float* out_scores, void* stream);

@@ -156,3 +156,27 @@ def test_maxpool_oracle_tf_same_rule():
     assert v.shape == (1, 1, 2, 2) and v[0, 0, 1, 1] == a[0, 0, 3, 3]
     s3 = net_oracle.maxpool_tf(a, 3, 2, True)      # total padding 2 -> one before, one after
     assert s3.shape == (1, 1, 3, 3) and s3[0, 0, 0, 0] == a[0, 0, 1, 1] and s3[0, 0, 2, 2] == a[0, 0, 4, 4]
+
+
+def test_preprocess_oracle_vs_torch_bilinear():
+    """The numpy restatement of TF2's ResizeBilinear(half_pixel_centers=True) against torch's independent implementation
+    of the same formula (align_corners=False, no antialias): equal up to float32 rounding, up- and down-sampling."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import preprocess_oracle as po
+    rng = np.random.default_rng(0)
+    for (h, w, oh, ow) in [(37, 53, 64, 64), (480, 640, 416, 416), (100, 80, 33, 57), (5, 5, 5, 5)]:
+        img = rng.random((h, w, 3), dtype=np.float32)
+        ours = po.resize_bilinear(img, oh, ow)
+        ref = F.interpolate(torch.from_numpy(img).permute(2, 0, 1)[None], size=(oh, ow), mode="bilinear",
+                            align_corners=False, antialias=False)[0].permute(1, 2, 0).numpy()
+        # the two differ only in how the source coordinate (up to ~640 here, float32 ulp 6e-5) is rounded before the
+        # fractional weight is taken: |diff| <= ulp(coord) * |pixel difference| ~ 3e-5
+        np.testing.assert_allclose(ours, ref, rtol=0, atol=5e-5)
+    # identity resize returns the image; uint8 sources are converted, not rescaled
+    u8 = rng.integers(0, 256, (9, 7, 3), dtype=np.uint8)
+    assert np.array_equal(po.resize_bilinear(u8, 9, 7), u8.astype(np.float32))
+    # aspect-preserving resize + centred zero padding (core/utils.py:17-28)
+    out = po.resize_image(rng.random((50, 100, 3), dtype=np.float32), 64, 64)
+    assert out.shape == (64, 64, 3) and po.aspect_size(50, 100, 64, 64) == (32, 64)
+    assert (out[:16] == 0).all() and (out[48:] == 0).all() and (out[16:48] != 0).any()

@@ -1,0 +1,55 @@
+"""GPU pre-processing vs the numpy oracle: bit-exact (every float32 operation of the
+TensorFlow formula is rounded separately on both sides)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "float32"])
+def test_resize_matches_oracle_bit_exact(cuda, dtype):
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from oracle import preprocess_oracle as po
+    rng = np.random.default_rng(3)
+    shapes = [(480, 640), (333, 500), (416, 416), (37, 53), (1080, 1920)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if dtype == "uint8" else rng.random((h, w, 3), dtype=np.float32)
+            for h, w in shapes]
+    div = dtype == "uint8"
+    out = y3.preprocess_images([torch.from_numpy(i).cuda() for i in imgs], 416, 416, divide_by_255=div)
+    torch.cuda.synchronize()
+    assert out.shape == (len(shapes), 416, 416, 3) and out.dtype == torch.float32
+    for k, img in enumerate(imgs):
+        assert np.array_equal(out[k].cpu().numpy(), po.resize(img, 416, divide_by_255=div)), f"image {k}"
+
+
+def test_resize_image_aspect_preserving(cuda):
+    """reference core/utils.py:17-28: resize with preserve_aspect_ratio, then pad_to_bounding_box (centred, zeros)."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from oracle import preprocess_oracle as po
+    rng = np.random.default_rng(5)
+    for (h, w, th, tw) in [(480, 640, 416, 416), (640, 480, 416, 416), (100, 300, 608, 608), (50, 50, 64, 96)]:
+        img = rng.random((h, w, 3), dtype=np.float32)
+        got = y3.resize_image(torch.from_numpy(img).cuda(), th, tw)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), po.resize_image(img, th, tw)), (h, w, th, tw)
+    batch = rng.integers(0, 256, (3, 120, 200, 3), dtype=np.uint8)
+    got = y3.resize_image(torch.from_numpy(batch).cuda(), 416, 416)
+    for k in range(3):
+        assert np.array_equal(got[k].cpu().numpy(), po.resize_image(batch[k], 416, 416))
+
+
+def test_preprocess_feeds_the_model(cuda):
+    """uint8 frames -> GPU resize / 255 -> model: same grids as feeding the oracle-resized float image."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from oracle import preprocess_oracle as po
+    rng = np.random.default_rng(7)
+    frames = [rng.integers(0, 256, (90, 130, 3), dtype=np.uint8) for _ in range(2)]
+    model = y3.ParseModel.builtin_yolov3_tiny(80).init_weights("variance", seed=1)
+    x = y3.preprocess_images(frames, 96, 96, divide_by_255=True)
+    a = model(x)
+    b = model(np.stack([po.resize(f, 96, divide_by_255=True) for f in frames]))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)

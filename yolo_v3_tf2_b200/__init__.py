@@ -9,7 +9,7 @@ from .core.parse_model import ParseModel  # noqa: F401
 from .core.yolo_decode_layer import yolo_decode  # noqa: F401
 from .core.yolo_nms import yolo_nms  # noqa: F401
 from .core.yolo_nms_layer import YoloNmsLayer  # noqa: F401
-from .core.utils import get_anchors  # noqa: F401
+from .core.utils import get_anchors, resize_image, preprocess_images  # noqa: F401
 from .inference import Inference, Detector  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,4 +1,5 @@
-"""Mirror of the hot-path part of reference core/utils.py."""
+"""Mirror of the hot-path part of reference core/utils.py (anchors, class count) and of the image pre-processing that
+feeds the model (``tf.image.resize`` call sites + ``resize_image``), which runs on the GPU here."""
 import numpy as np
 
 
@@ -17,3 +18,58 @@ def count_file_lines(filename):
     with open(filename, 'r') as fp:
         nlines = len(fp.readlines())
     return nlines
+
+
+def _aspect_size(h, w, target_height, target_width):
+    """tf.image.resize(preserve_aspect_ratio=True): scale = min(th / h, tw / w), new size = round(h * scale), round(w * scale)
+    (float32 arithmetic, round half to even like tf.round)."""
+    sh = np.float32(target_height) / np.float32(h)
+    sw = np.float32(target_width) / np.float32(w)
+    sc = np.minimum(sh, sw)
+    return int(np.round(np.float32(h) * sc)), int(np.round(np.float32(w) * sc))
+
+
+def preprocess_images(images, target_height, target_width, preserve_aspect_ratio=False, divide_by_255=False, out=None):
+    """Resize a list of [H, W, 3] images (torch CUDA tensors, uint8 or float32; numpy arrays are copied to the GPU) to
+    one float32 batch [B, target_height, target_width, 3] with ONE kernel launch.
+    ``preserve_aspect_ratio=False``: ``tf.image.resize(img, (th, tw))`` (inference.py:157-158; with
+    ``divide_by_255`` the tfrecord path core/load_tfrecords.py:46).  ``True``: ``resize_image`` (core/utils.py:17-28):
+    aspect-preserving resize, then centred zero padding."""
+    import torch
+    from .. import _lib
+    ctx = _lib.context()
+    dev = torch.device("cuda", ctx.device)
+    keep, rows = [], []
+    for img in images:
+        if isinstance(img, np.ndarray):
+            img = torch.from_numpy(np.ascontiguousarray(img))
+        if img.dim() != 3 or img.shape[2] != 3:
+            raise ValueError(f"image shape {tuple(img.shape)} is not [H, W, 3]")
+        if img.dtype not in (torch.uint8, torch.float32):
+            img = img.float()
+        img = img.to(dev).contiguous()
+        keep.append(img)
+        h, w = int(img.shape[0]), int(img.shape[1])
+        if preserve_aspect_ratio:
+            oh, ow = _aspect_size(h, w, target_height, target_width)
+            oy, ox = (target_height - oh) // 2, (target_width - ow) // 2
+        else:
+            oh, ow, oy, ox = target_height, target_width, 0, 0
+        rows.append([img.data_ptr(), h, w, 0 if img.dtype == torch.uint8 else 1, oh, ow, oy, ox])
+    B = len(keep)
+    desc = torch.tensor(rows, dtype=torch.int64).to(dev)
+    if out is None:
+        out = torch.empty((B, target_height, target_width, 3), dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().y3_preprocess(ctx.handle, _lib.ptr(desc), B, int(target_height), int(target_width),
+                                        1 if divide_by_255 else 0, _lib.ptr(out), _lib.stream_ptr()))
+    # the kernel reads `keep` and `desc` asynchronously: tie their lifetime to the stream
+    for t in keep + [desc]:
+        t.record_stream(torch.cuda.current_stream())
+    return out
+
+
+def resize_image(img, target_height, target_width):
+    """reference core/utils.py:17-28 for one image [H, W, 3] or a batch [B, H, W, 3] (all images of a batch share H, W)."""
+    if img.ndim == 4:
+        return preprocess_images(list(img), target_height, target_width, preserve_aspect_ratio=True)
+    return preprocess_images([img], target_height, target_width, preserve_aspect_ratio=True)[0]

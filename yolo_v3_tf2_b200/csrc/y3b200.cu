@@ -19,6 +19,7 @@
 #include "conv_flat.cuh"
 #include "decode.cuh"
 #include "nms.cuh"
+#include "preprocess.cuh"
 #include "ptx.cuh"
 
 namespace {
@@ -1423,6 +1424,24 @@ int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_
     y3::gather_detections_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         bboxes, reinterpret_cast<const long long*>(class_idx), scores, selected, num_valid, B, N, max_boxes, out_boxes,
         reinterpret_cast<long long*>(out_classes), out_scores);
+    Y3_CUDA(cudaGetLastError());
+    return Y3_OK;
+}
+
+int y3_preprocess(y3_ctx* ctx, const void* image_descs_dev, int B, int dst_h, int dst_w, int divide_by_255, float* out,
+                  void* stream) {
+    (void)cudaGetLastError();
+    if (!ctx || !image_descs_dev || !out) return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (B <= 0 || dst_h <= 0 || dst_w <= 0) return fail(Y3_ERR_INVALID, "bad shape");
+    y3::PreprocessArgs a{};
+    a.desc = reinterpret_cast<const y3::ImageDesc*>(image_descs_dev);
+    a.out = out;
+    a.B = B; a.dst_h = dst_h; a.dst_w = dst_w;
+    a.use_mul = divide_by_255 ? 1 : 0;
+    a.mul = 1.0f;
+    const unsigned grid = grid_for((long long)B * dst_h * dst_w, 256, ctx->sms);
+    y3::preprocess_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     Y3_CUDA(cudaGetLastError());
     return Y3_OK;
 }
