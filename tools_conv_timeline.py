@@ -12,8 +12,13 @@ NAMES = ["entry", "prologue done", "pdl wait done", "last load issued", "first o
          "first accum done", "epi g0 handoff", "epi g1 handoff", "epi g0 stores done", "epi g1 stores done", "exit"]
 CLK = ["chunk1 start", "out of TMEM", "residual landed", "math+STS issued", "fenced", "store issued", "res prefetch issued",
        "chunk2 out of TMEM"]
+import os
 cases = [("1x1 512->256 @13", 13, 512, 256, 1, 1, False), ("1x1 256->128 @52", 52, 256, 128, 1, 1, False),
-         ("3x3 128->256 @52 +res", 52, 128, 256, 3, 1, True)]
+         ("1x1 512->256 @26", 26, 512, 256, 1, 1, False), ("1x1 1024->512 @13", 13, 1024, 512, 1, 1, False),
+         ("3x3 128->256 @52 +res", 52, 128, 256, 3, 1, True), ("3x3 64->128 @104 +res", 104, 64, 128, 3, 1, True),
+         ("3x3 512->1024 @13", 13, 512, 1024, 3, 1, False)]
+if os.environ.get("Y3_TL_CASES"):
+    cases = [c for i, c in enumerate(cases) if str(i) in os.environ["Y3_TL_CASES"].split(",")]
 ts = torch.zeros(32 * 148, dtype=torch.int64, device="cuda")
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 for name, g, cin, cout, k, stride, res in cases:
@@ -58,6 +63,17 @@ for name, g, cin, cout, k, stride, res in cases:
                 continue
             d = (col - t0) / 1e3
             print(f"   {nm:20s} min {d.min():7.2f}  med {np.median(d):7.2f}  max {d.max():7.2f} us   (n={len(col)})")
+        lead = t[:, 27] > 0
+        if lead.any():
+            tl = t[lead]
+            print(f"   MMA warp (leader CTAs, median cycles): loop {np.median(tl[:, 27]):.0f}, waiting for operands "
+                  f"{np.median(tl[:, 26]):.0f}, waiting for a free accumulator {np.median(tl[:, 25]):.0f}; "
+                  f"producer waiting for a free stage {np.median(t[:, 24]):.0f}")
+        ep = t[:, 28] > 0
+        if ep.any():
+            te = t[ep]
+            print(f"   epilogue warp 4 (median cycles): loop {np.median(te[:, 28]):.0f}, waiting for an accumulator "
+                  f"{np.median(te[:, 29]):.0f}, for a staging slot {np.median(te[:, 30]):.0f}, for the residual {np.median(te[:, 31]):.0f}")
         ok = t[:, 16] > 0
         if ok.any():
             c = t[ok][:, 16:24]

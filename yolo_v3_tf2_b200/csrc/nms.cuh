@@ -8,6 +8,11 @@
 //      zero padded; num_valid = their count.
 //
 // One CTA (1024 threads) per image:
+//   select  : when more than kNmsSortAll candidates pass the score threshold, a 3-pass radix select (12 + 12 + 8 bits,
+//             shared-memory histograms) finds the key of the kNmsTopT-th best candidate and only the candidates at or
+//             above it are sorted and visited: the greedy loop stops at max_boxes survivors long before it runs out of
+//             them (dense worst case: 10 647 candidates, ~600 visited).  If it does run out, the image is redone with
+//             all candidates -- same result, just slower.
 //   sort    : (score key, index) pairs in shared memory, bitonic network with a (key desc, index asc) comparator
 //   suppress: candidates are consumed in sorted order in chunks of 256:
 //             A  every candidate of the chunk is tested against the boxes kept so far (all threads),
@@ -24,6 +29,10 @@ constexpr int kNmsThreads = 1024;
 constexpr int kNmsChunk = 256;
 constexpr int kNmsKeptCap = 1024;
 constexpr int kNmsMaxN = 32768;
+constexpr int kNmsSortAll = 2048;   // up to this many candidates are simply sorted
+constexpr int kNmsTopT = 1024;      // otherwise: the best kNmsTopT (plus ties with the last of them)
+constexpr int kNmsTopCap = 4096;    // more than this many selected (mass ties): sort everything instead
+constexpr int kNmsBins = 4096;
 
 struct NmsArgs {
     const float* boxes;      // [B, N, 4]
@@ -64,8 +73,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     float4* cbox = kept + kNmsKeptCap;                                       // [kNmsChunk]
     uint32_t* mask = reinterpret_cast<uint32_t*>(cbox + kNmsChunk);          // [kNmsChunk][8]
     uint32_t* dead = mask + kNmsChunk * 8;                                   // [8] chunk-level dead bits
+    uint32_t* hist = dead + 8;                                               // [kNmsBins] radix-select histogram
     __shared__ int s_ncand, s_nkept, s_nsel, s_overflow;
     __shared__ int s_warp_cnt[kNmsThreads / 32];
+    __shared__ int s_scan[kNmsThreads / 32];
+    __shared__ uint32_t s_sel_bin, s_sel_above;
 
     const int img = blockIdx.x;
     const int tid = threadIdx.x;
@@ -82,6 +94,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     for (int i = tid; i < a.max_boxes; i += kNmsThreads) sel[i] = 0;
     __syncthreads();
 
+    // attempt 0 may visit only the best candidates; attempt 1 (rare) redoes the image with all of them
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    if (attempt == 1) {
+        if (tid == 0) { s_nkept = 0; s_nsel = 0; s_overflow = 0; }
+        for (int i = tid; i < a.max_boxes; i += kNmsThreads) sel[i] = 0;
+        __syncthreads();
+    }
     // ---------------- candidate list (index order) ----------------
     int ncand;
     if (compact) {
@@ -117,6 +136,81 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
             idxs[i] = (uint16_t)i;
         }
         ncand = a.N;
+    }
+    // ---------------- top-T selection (radix select on the 32-bit keys) ----------------
+    bool partial = false;          // true: keys[0 .. ncand) hold only the best candidates of a longer list
+    if (attempt == 0 && ncand > kNmsSortAll) {
+        uint32_t prefix = 0u, pmask = 0u;
+        int need = kNmsTopT;       // rank (1-based, from the top) of the key we are looking for
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = (pass == 0) ? 20 : (pass == 1 ? 8 : 0);
+            const uint32_t bmask = (pass == 2) ? 0xFFu : 0xFFFu;
+            for (int i = tid; i < kNmsBins; i += kNmsThreads) hist[i] = 0u;
+            __syncthreads();
+            for (int i = tid; i < ncand; i += kNmsThreads) {
+                const uint32_t k = keys[i];
+                if ((k & pmask) == prefix) atomicAdd(&hist[(k >> shift) & bmask], 1u);
+            }
+            __syncthreads();
+            // suffix sums from the top bin: thread t owns bins [4t, 4t+4), highest bins = highest t
+            const uint32_t h0 = hist[4 * tid], h1 = hist[4 * tid + 1], h2 = hist[4 * tid + 2], h3 = hist[4 * tid + 3];
+            const int mine = (int)(h0 + h1 + h2 + h3);
+            // inclusive suffix scan over threads: warp level (lanes above), then warps above
+            int suf = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += v;
+            }
+            if (lane == 0) s_scan[wid] = suf;
+            __syncthreads();
+            int above_warps = 0;
+            for (int w = wid + 1; w < kNmsThreads / 32; ++w) above_warps += s_scan[w];
+            const int incl = suf + above_warps;        // keys in bins >= 4t
+            const int excl = incl - mine;              // keys in bins >= 4t + 4
+            if (excl < need && incl >= need) {
+                // the crossing is in one of my four bins (walk down from the highest)
+                int acc = excl;
+                const uint32_t hb[4] = {h0, h1, h2, h3};
+                for (int b = 3; b >= 0; --b) {
+                    if (acc + (int)hb[b] >= need) { s_sel_bin = (uint32_t)(4 * tid + b); s_sel_above = (uint32_t)acc; break; }
+                    acc += (int)hb[b];
+                }
+            }
+            __syncthreads();
+            need -= (int)s_sel_above;
+            prefix |= s_sel_bin << shift;
+            pmask |= bmask << shift;
+            __syncthreads();
+        }
+        // prefix is now the key of the kNmsTopT-th best candidate: keep every candidate with key >= prefix (ordered
+        // in-place compaction, a tile's reads complete before its writes and writes never pass the reads)
+        int base = 0;
+        for (int t0 = 0; t0 < ncand; t0 += kNmsThreads) {
+            const int i = t0 + tid;
+            const uint32_t k = (i < ncand) ? keys[i] : 0u;
+            const uint16_t x = (i < ncand) ? idxs[i] : (uint16_t)0;
+            const bool pass = (i < ncand) && (k >= prefix);
+            const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) s_warp_cnt[wid] = __popc(bal);
+            __syncthreads();
+            int woff = 0, tot = 0;
+            for (int w = 0; w < kNmsThreads / 32; ++w) {
+                const int c = s_warp_cnt[w];
+                if (w < wid) woff += c;
+                tot += c;
+            }
+            if (pass && base + tot <= kNmsTopCap) {
+                const int pos = base + woff + __popc(bal & ((1u << lane) - 1u));
+                keys[pos] = k;
+                idxs[pos] = x;
+            }
+            base += tot;
+            __syncthreads();
+        }
+        if (base > kNmsTopCap) continue;   // mass ties: the list is damaged, redo with everything (attempt 1)
+        partial = base < ncand;
+        ncand = base;
     }
     // pad to a power of two with entries that sort last
     int np = 32;
@@ -258,6 +352,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
         __syncthreads();
         if (s_nsel >= a.max_boxes || s_overflow) break;
     }
+    // the best-candidates list ran out before max_boxes boxes were selected: lower-scored candidates may still qualify
+    if (partial && s_nsel < a.max_boxes && !s_overflow) continue;
+    break;
+    }   // attempt
     if (tid == 0) {
         a.num_valid[img] = min(s_nsel, a.max_boxes);
         a.status[img] = s_overflow;
