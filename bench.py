@@ -138,7 +138,7 @@ def run_reference(args, rank, world):
         cpu_reference_step(model, anchors, x, cores)
     dt = time.perf_counter() - t0
     v = sample_b * args.steps / dt
-    line = {"impl": "reference", "metric": "images/sec (416^2, backbone+decode+NMS)", "value": v, "unit": "images/s",
+    line = {"impl": "reference", "metric": f"images/sec ({args.size}^2, backbone+decode+NMS)", "value": v, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.size, args.batch), "images_per_gpu": args.batch,
@@ -160,7 +160,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=416)
     ap.add_argument("--ref-batch", type=int, default=2, help="images per step of the CPU reference arm")
-    ap.add_argument("--cpu-baseline-images", type=int, default=4)
+    ap.add_argument("--cpu-baseline-images", type=int, default=96,
+                    help="images of the bounded CPU-baseline sample (about 10 s of host work, processed 8 at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -202,10 +203,12 @@ def main():
     from yolo_v3_tf2_b200.core.yolo_nms import nms_padded
     from yolo_v3_tf2_b200.inference import gather_detections_batched
 
+    no_gather = os.environ.get("Y3_BENCH_NO_GATHER") == "1"   # diagnosis only: N > 1 without the NCCL gather
+
     def step(x):
         """public-API step: local detections, then (N > 1) the NCCL gather of the fixed-size records"""
         local = det.detections(x)
-        if world > 1:
+        if world > 1 and not no_gather:
             y3dist.gather_detections(*local)
         return local
 
@@ -231,7 +234,7 @@ def main():
         bboxes, conf, probs, scores, cls = y3.yolo_decode(grids, anchors, NCLASSES, with_scores=True)
         sel, nv, status = nms_padded(bboxes, scores, mx, 0.5, 0.1)
         ob, oc, os_ = gather_detections_batched(bboxes, cls, scores, sel, nv)
-        if world > 1:
+        if world > 1 and not no_gather:
             y3dist.gather_detections(ob, oc, os_, nv)
     e1.record()
     sync_all()
@@ -297,7 +300,7 @@ def main():
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
         line = {
-            "metric": "images/sec (416^2, backbone+decode+NMS)", "value": value, "unit": "images/s", "n_gpus": world,
+            "metric": f"images/sec ({S}^2, backbone+decode+NMS)", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(S, B), "images_per_gpu": B, "l2": "inputs rotate over 3 device buffers; each step streams a ~1 GB "
@@ -318,10 +321,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             nimg = args.cpu_baseline_images
-            xc = host[0][:nimg].numpy()
+            xc = torch.cat([host[i % nbuf] for i in range((nimg + B - 1) // B)])[:nimg].numpy()
             cpu_reference_step(model, anchors, xc[:1], cores)   # warm-up
             t0 = time.perf_counter()
-            cpu_reference_step(model, anchors, xc, cores)
+            for i0 in range(0, nimg, 8):                       # 8 images at a time bounds the oracle's memory
+                cpu_reference_step(model, anchors, xc[i0:i0 + 8], cores)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": nimg / dt, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"{nimg} images of {S}x{S}, torch-CPU fp32 oracle forward + numpy decode "

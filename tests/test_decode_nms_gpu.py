@@ -146,6 +146,33 @@ def test_nms_edge_cases(cuda):
     _check_nms(b7[None], s7[None], 100, 0.5, 0.1)
 
 
+def test_nms_top_candidate_prefilter_paths(cuda):
+    """More than 2048 passing candidates: the kernel sorts only the best 1024 (radix select).  Exercised here:
+    (a) 608x608 size, N = 22 743 dense (largest shared-memory footprint), (b) the best 1024 collapse to a handful of
+    survivors so the image must be redone with all candidates, (c) > 4096 candidates tied at the selection key."""
+    from oracle import decode_oracle
+    grids = synth_grids(2, (19, 38, 76), 80, seed=5, obj_mean=1.0)
+    bboxes, conf, probs = decode_oracle.yolo_decode(grids, _anchors(), 80)
+    cls, scores = decode_oracle.class_reduce(conf, probs)
+    assert bboxes.shape[1] == 22743 and (scores > 0.05).sum(1).min() > 8000
+    _check_nms(bboxes, scores, 100, 0.5, 0.05)
+    # (b) 1500 near-identical high-scoring boxes (one survivor) + 4000 scattered low-scoring ones (the other 99)
+    rng = np.random.default_rng(17)
+    hot = np.array([0.4, 0.4, 0.6, 0.6], np.float32) + rng.normal(0, 1e-3, (1500, 4)).astype(np.float32)
+    c = rng.random((4000, 2)).astype(np.float32)
+    cold = np.concatenate([c - 0.01, c + 0.01], 1).astype(np.float32)
+    b = np.concatenate([hot, cold])
+    s = np.concatenate([0.8 + 0.1 * rng.random(1500), 0.2 + 0.1 * rng.random(4000)]).astype(np.float32)
+    perm = rng.permutation(len(s))
+    nv = _check_nms(b[perm][None], s[perm][None], 100, 0.5, 0.1)
+    assert nv[0] == 100
+    # (c) 5000 candidates with the same score: ties are broken by the lower index
+    s_tie = np.full(5500, 0.5, np.float32)
+    s_tie[:500] = 0.9
+    _check_nms(b[None], s_tie[None], 100, 0.5, 0.1)
+    _check_nms(b[perm][None], s_tie[None], 100, 0.5, 0.1, "tiled")
+
+
 def test_nms_full_size_batch_properties(cuda):
     """BASELINE config 4 size (N=10647, B=64 here): checked against the C oracle on every image, plus
     size-independent properties: sorted-by-score output, zero padding, survivors mutually below the IoU threshold."""

@@ -73,7 +73,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     float4* cbox = kept + kNmsKeptCap;                                       // [kNmsChunk]
     uint32_t* mask = reinterpret_cast<uint32_t*>(cbox + kNmsChunk);          // [kNmsChunk][8]
     uint32_t* dead = mask + kNmsChunk * 8;                                   // [8] chunk-level dead bits
-    uint32_t* hist = dead + 8;                                               // [kNmsBins] radix-select histogram
+    // radix-select histogram [kNmsBins]: aliases the kept list, which is only used after the sort (16 KB each; at
+    // N = 22 743 (608x608) keys + indices alone take 192 KB of the 227 KB)
+    uint32_t* hist = reinterpret_cast<uint32_t*>(kept);
+    static_assert(kNmsBins * 4 <= kNmsKeptCap * 16, "histogram must fit in the kept list");
     __shared__ int s_ncand, s_nkept, s_nsel, s_overflow;
     __shared__ int s_warp_cnt[kNmsThreads / 32];
     __shared__ int s_scan[kNmsThreads / 32];

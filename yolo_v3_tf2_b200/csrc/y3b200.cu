@@ -1402,8 +1402,7 @@ int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, 
     a.max_boxes = max_boxes;
     a.iou_thr = iou_thr; a.score_thr = score_thr;
     a.selected = selected; a.num_valid = num_valid; a.status = status;
-    const size_t smem = (size_t)np * 6 + (size_t)(y3::kNmsKeptCap + y3::kNmsChunk) * 16 + (size_t)y3::kNmsChunk * 8 * 4 + 32 +
-                        (size_t)y3::kNmsBins * 4;
+    const size_t smem = (size_t)np * 6 + (size_t)(y3::kNmsKeptCap + y3::kNmsChunk) * 16 + (size_t)y3::kNmsChunk * 8 * 4 + 32;
     static size_t configured = 0;   // static shared memory of the kernel counts against the 227 KB limit too
     if (smem > configured) {
         Y3_CUDA(cudaFuncSetAttribute(y3::nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
