@@ -50,3 +50,77 @@ def test_model_without_weights_or_gpu_fails_loudly():
         m.init_weights("keras")
         with pytest.raises(_lib.Y3Error, match="no CPU fallback|no CUDA"):
             m(np.zeros((1, 64, 64, 3), np.float32))
+
+
+def test_tf_checkpoint_roundtrip_object_based(tmp_path):
+    """TensorFlow checkpoint (tensor bundle) written with the reference model's object-based variable names and read
+    back without TensorFlow (inference.py:102 ``model.load_weights(prefix).expect_partial()``)."""
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import tf_checkpoint as tc
+    m = y3.ParseModel.builtin_yolov3_tiny(80).init_weights("variance", seed=4)
+    prefix = str(tmp_path / "yolov3_train_8.tf")
+    m.save_weights(prefix)
+    idx = tc.read_index(prefix + ".index")
+    assert idx[""]["num_shards"] == 1 and idx[""]["endianness"] == 0
+    # sub-models backbone(7 convs), neck0(1), head0(2), neck1(1), head1(2): the first variable of head0's bias-only conv
+    assert "layer_with_weights-0/layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE" in idx
+    assert "layer_with_weights-0/layer_with_weights-1/moving_variance/.ATTRIBUTES/VARIABLE_VALUE" in idx
+    assert "layer_with_weights-2/layer_with_weights-2/bias/.ATTRIBUTES/VARIABLE_VALUE" in idx
+    e = idx["layer_with_weights-0/layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE"]
+    assert e["shape"] == [3, 3, 3, 16] and e["dtype"] == 1 and e["size"] == 3 * 3 * 3 * 16 * 4
+    for path in (prefix, prefix + ".index"):
+        m2 = y3.ParseModel.builtin_yolov3_tiny(80)
+        m2.load_weights(path).expect_partial()
+        for a, b in zip(m.get_weights(), m2.get_weights()):
+            np.testing.assert_array_equal(a, b)
+    # a model with a different head does not silently accept the file
+    with pytest.raises(ValueError, match="kernel shape"):
+        y3.ParseModel.builtin_yolov3_tiny(3).load_weights(prefix)
+    with pytest.raises(FileNotFoundError):
+        y3.ParseModel.builtin_yolov3_tiny(80).load_weights(str(tmp_path / "missing.tf"))
+
+
+def test_tf_checkpoint_format_details(tmp_path):
+    """Many small tensors (several data blocks, prefix-compressed keys), name-based keys, other dtypes, a snappy
+    compressed block and corruption checks."""
+    from yolo_v3_tf2_b200 import tf_checkpoint as tc
+    rng = np.random.default_rng(0)
+    tensors = {f"scope/var_{i:04d}/weights": rng.standard_normal((i % 5 + 1, 3)).astype(np.float32) for i in range(300)}
+    tensors["global_step"] = np.array(12345, np.int64)
+    tensors["flags"] = np.array([True, False, True])
+    prefix = str(tmp_path / "many")
+    tc.write_checkpoint(prefix, tensors, block_entries=17)
+    back = tc.read_checkpoint(prefix)
+    assert set(back) == set(tensors)
+    for k in tensors:
+        np.testing.assert_array_equal(back[k], tensors[k])
+        assert back[k].dtype == tensors[k].dtype
+    # name-based (TF1-style) checkpoint of a conv + BN + biased conv
+    shapes = [(3, 3, 8, True), (1, 8, 6, False)]
+    named = {"conv2d/kernel": rng.standard_normal((3, 3, 3, 8)).astype(np.float32),
+             "batch_normalization/gamma": np.ones(8, np.float32), "batch_normalization/beta": np.zeros(8, np.float32),
+             "batch_normalization/moving_mean": np.full(8, 0.5, np.float32),
+             "batch_normalization/moving_variance": np.full(8, 2.0, np.float32),
+             "conv2d_1/kernel": rng.standard_normal((1, 1, 8, 6)).astype(np.float32), "conv2d_1/bias": np.arange(6, dtype=np.float32)}
+    tc.write_checkpoint(str(tmp_path / "named"), named)
+    ps = tc.params_from_checkpoint(str(tmp_path / "named"), shapes)
+    np.testing.assert_array_equal(ps[0].kernel, named["conv2d/kernel"])
+    np.testing.assert_array_equal(ps[0].var, named["batch_normalization/moving_variance"])
+    np.testing.assert_array_equal(ps[1].bias, named["conv2d_1/bias"])
+    # snappy raw format: literal + overlapping copy
+    comp = bytes([11]) + bytes([(3 - 1) << 2]) + b"abc" + bytes([((8 - 4) << 2) | 1, 3])
+    assert tc._snappy_decompress(comp) == b"abcabcabcab"
+    # crc32c known answer (RFC 3720 test vector: 32 bytes of zeros)
+    assert tc._crc32c(bytes(32)) == 0x8A9136AA
+    # corruption: flipped byte inside the index block, bad magic
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    bad = bytearray(raw)
+    bad[-60] ^= 0xFF
+    open(str(tmp_path / "bad.index"), "wb").write(bytes(bad))
+    with pytest.raises(ValueError, match="checksum"):
+        tc.read_index(str(tmp_path / "bad.index"))
+    bad = bytearray(raw)
+    bad[-1] ^= 0xFF
+    open(str(tmp_path / "bad2.index"), "wb").write(bytes(bad))
+    with pytest.raises(ValueError, match="magic"):
+        tc.read_index(str(tmp_path / "bad2.index"))

@@ -65,24 +65,49 @@ class Y3Model:
         return self
 
     def load_weights(self, path):
-        """Darknet ``.weights`` (reference convert.py) or an ``.npz`` written by ``save_weights``.  TF-checkpoint
-        bundles (``.tf``/``.index``) need TensorFlow's bundle reader and are not supported yet."""
+        """Darknet ``.weights`` (reference convert.py), an ``.npz`` written by ``save_weights``, or a TensorFlow
+        checkpoint prefix as written by the reference's ``model.save_weights(prefix)`` (train.py:93-104) and read by
+        ``model.load_weights(prefix)`` (inference.py:102): ``<prefix>.index`` + ``<prefix>.data-00000-of-00001``, parsed
+        without TensorFlow (yolo_v3_tf2_b200/tf_checkpoint.py)."""
+        from .. import tf_checkpoint
         path = str(path)
         if path.endswith(".weights"):
             self.set_params(weights_mod.read_darknet_weights(path, self.conv_shapes))
         elif path.endswith(".npz"):
             z = np.load(path)
             self.set_weights([z[f"arr_{i}"] for i in range(len(z.files))])
+        elif tf_checkpoint.is_checkpoint(path):
+            self.set_params(tf_checkpoint.params_from_checkpoint(path, self.conv_shapes))
         else:
-            raise _lib.Y3Unsupported("TF-checkpoint weights need a tensor-bundle reader (SURVEY.md f-1); "
-                                     "convert with the reference's convert.py to Darknet .weights or use .npz")
+            raise FileNotFoundError(f"{path}: neither a Darknet .weights file, an .npz, nor a TensorFlow checkpoint prefix "
+                                    f"({path}.index not found)")
         return self
 
     def expect_partial(self):   # Keras load_weights(...).expect_partial() chaining (inference.py:102)
         return self
 
     def save_weights(self, path):
-        np.savez(path, *self.get_weights())
+        """``.npz`` (Keras variable order) or, for any other name, a TensorFlow checkpoint with the object-based
+        variable names the reference's Keras model would use (one sub-model per ``sub_models_configs`` entry)."""
+        path = str(path)
+        if path.endswith(".npz"):
+            np.savez(path, *self.get_weights())
+            return
+        from .. import tf_checkpoint
+        if self._params is None:
+            raise _lib.Y3Error("model has no weights yet")
+        g = self.graph
+        counts = []
+        for name in g.sub_model_names:
+            n = sum(1 for li in g.conv_layers if g.layers[li].sub_model == name)
+            if n:
+                counts.append(n)
+        names = tf_checkpoint.keras_variable_names(counts, self.conv_shapes)
+        tensors = {}
+        for p, nm in zip(self._params, names):
+            for key, arr in zip(nm, p.as_list()):
+                tensors[key] = np.asarray(arr, np.float32)
+        tf_checkpoint.write_checkpoint(path, tensors)
 
     # ---------------- execution ----------------
     def _upload(self, handle):

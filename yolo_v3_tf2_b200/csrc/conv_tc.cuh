@@ -59,6 +59,7 @@ struct ConvArgs {
     const void* src;       // bf16 NHWC view, or the fp32 [B,H,W,3] image for the stem
     long long src_stride;  // elements between consecutive input pixels
     int H, W;              // input spatial size
+    int stages;            // weights-resident kernels only: A-operand pipeline depth (what fits next to the weights)
     int tma_out;           // 0: register-transpose epilogue; 32 / 64: bf16 dense output written with TMA stores in chunks
                            //    of that many columns (epilogue_role_tma); tmO (and tmR when a residual is fused) are
                            //    tensor maps with a 32-row x tma_out-column box

@@ -25,11 +25,22 @@ struct Conv2Smem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * kEpiWarpBytes;
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kConvEpiGroups;
+    static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kConvEpiGroups;
     static constexpr int TOTAL = 1024 + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
+    // weights-resident variant: `stages` A tiles + all K blocks of this CTA's half of the weight tile
+    static constexpr int total_resident(int stages, int num_k_blocks) {
+        return 1024 + stages * A_BYTES + num_k_blocks * B_BYTES + XPOSE_BYTES + BAR_BYTES;
+    }
 };
 
-template <int BLOCK_N, int SWZ, int STAGES>
+// BRES (weights resident): when this CTA's half of the [BLOCK_N x K] weight tile fits in shared memory next to the A
+// pipeline, it is loaded ONCE per launch -- before griddepcontrol.wait, i.e. while the previous layer is still
+// finishing -- instead of once per output tile, and the stage ring carries only the A operand.  The layers it applies
+// to (1x1 with K <= 768, 3x3 64->128) are bound by what the SM can pull from L2 (finding 7c/7d):
+// the re-read weight tile was 25-33 % of that traffic.  Every cluster must then stay on one N tile: the host only
+// picks this variant when the number of clusters is a multiple of tiles_n (tile % tiles_n is then constant).
+// STAGES is the barrier-array size (maximum depth); the depth actually used is p.stages.
+template <int BLOCK_N, int SWZ, int STAGES, bool BRES = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
@@ -43,17 +54,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int nst = BRES ? p.stages : STAGES;                       // pipeline depth in use
+    const uint32_t tile_bytes = BRES ? (uint32_t)(nst * S::A_BYTES + p.num_k_blocks * S::B_BYTES) : (uint32_t)S::TILE_BYTES;
     const uint32_t smem_a = smem_base;
-    const uint32_t smem_b = smem_base + STAGES * S::A_BYTES;
-    const uint32_t bar_base = smem_base + S::TILE_BYTES + S::XPOSE_BYTES;
+    const uint32_t smem_b = smem_base + (uint32_t)(nst * S::A_BYTES);   // BRES: the resident weights, else the B stages
+    const uint32_t bar_base = smem_base + tile_bytes + S::XPOSE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
-    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
+    const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 4);   // resident weights landed (leader's, both CTAs signal it)
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 5);
+    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 5) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
     volatile uint32_t* tmem_ptr_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + S::TILE_BYTES + S::XPOSE_BYTES + 8 * (2 * STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + tile_bytes + S::XPOSE_BYTES + 8 * (2 * STAGES + 5));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -78,6 +92,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_init(tempty_bar(a), 256);
         }
         for (int w = 0; w < kEpiMaxBufs * 4 * kConvEpiGroups; ++w) mbar_init(res_bar(0) + 8u * w, 1);
+        mbar_init(bfull_bar, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -93,6 +108,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    if constexpr (BRES) {
+        // the weights do not depend on the previous layer: fetch this CTA's half of the tile before waiting for it
+        if (warp == 0 && elect_one()) {
+            const int tn = first_tile % p.tiles_n;   // constant for this cluster (host-enforced)
+            const int nb = tn * BLOCK_N + cta_rank * (BLOCK_N / 2);
+            const uint32_t lead_bfull = mapa_shared(bfull_bar, 0);
+            if (is_leader) mbar_arrive_expect_tx(bfull_bar, (uint32_t)(2 * p.num_k_blocks * S::B_BYTES));
+            for (int kb = 0; kb < p.num_k_blocks; ++kb)
+                tma2_load_2d(smem_b + kb * S::B_BYTES, &tmB, lead_bfull, kb * BLOCK_K, nb);
+        }
+    }
     if (threadIdx.x == 0) ts_mark(p.ts, 1);   // prologue done
     // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
     // from here on we touch activations it wrote (and buffers it may still be reading), so wait for it to finish.
@@ -125,15 +151,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                             if (leader_lane) {
                                 const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-                                if (is_leader)
-                                    mbar_arrive_expect_tx(full_bar(stage), (p.dbg & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
-                                if (!(p.dbg & 4))
+                                if constexpr (BRES) {
+                                    if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * S::A_BYTES);
                                     tma2_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, lead_full, c0, cw, ch, cn,
                                                         (uint16_t)sx, (uint16_t)r);
-                                tma2_load_2d(smem_b + stage * S::B_BYTES, &tmB, lead_full, kcoord, nb);
+                                } else {
+                                    if (is_leader)
+                                        mbar_arrive_expect_tx(full_bar(stage), (p.dbg & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
+                                    if (!(p.dbg & 4))
+                                        tma2_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, lead_full, c0, cw, ch, cn,
+                                                            (uint16_t)sx, (uint16_t)r);
+                                    tma2_load_2d(smem_b + stage * S::B_BYTES, &tmB, lead_full, kcoord, nb);
+                                }
                             }
                             kcoord += BLOCK_K;
-                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                            if (++stage == nst) { stage = 0; phase ^= 1u; }
                         }
                     }
                 }
@@ -142,13 +174,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                     if (leader_lane) {
                         const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-                        if (is_leader)
-                            mbar_arrive_expect_tx(full_bar(stage), (p.dbg & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
-                        if (!(p.dbg & 4)) tma2_load_2d(smem_a + stage * S::A_BYTES, &tmA, lead_full, kcoord, m0);
-                        tma2_load_2d(smem_b + stage * S::B_BYTES, &tmB, lead_full, kcoord, nb);
+                        if constexpr (BRES) {
+                            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * S::A_BYTES);
+                            tma2_load_2d(smem_a + stage * S::A_BYTES, &tmA, lead_full, kcoord, m0);
+                        } else {
+                            if (is_leader)
+                                mbar_arrive_expect_tx(full_bar(stage), (p.dbg & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
+                            if (!(p.dbg & 4)) tma2_load_2d(smem_a + stage * S::A_BYTES, &tmA, lead_full, kcoord, m0);
+                            tma2_load_2d(smem_b + stage * S::B_BYTES, &tmB, lead_full, kcoord, nb);
+                        }
                     }
                     kcoord += BLOCK_K;
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == nst) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -164,6 +201,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             int j = 0;
+            if constexpr (BRES) {
+                mbar_wait(bfull_bar, 0, 0x700);   // both halves of the weight tile are resident
+                tc_fence_after();
+            }
             for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
                 const int acc = j & 1;
                 mbar_wait(tempty_bar(acc), (uint32_t)(((j >> 1) & 1) ^ 1), 0x200 + acc);
@@ -175,7 +216,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (j == 0 && kb == 0 && lane == 0) ts_mark(p.ts, 4);   // first operands landed
                     if (leader_lane) {
                         const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
-                        const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (S::B_BYTES >> 4));
+                        const uint64_t bdesc = bdesc0 + (uint64_t)((BRES ? kb : stage) * (S::B_BYTES >> 4));
                         if (!(p.dbg & 8)) {
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
@@ -185,7 +226,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         umma2_commit_mc(empty_bar(stage), 3);               // both producers may refill the stage
                         if (kb == p.num_k_blocks - 1) umma2_commit_mc(tfull_bar(acc), 3);   // both epilogues may drain
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == nst) { stage = 0; phase ^= 1u; }
                 }
             }
             if (lane == 0) ts_mark(p.ts, 5);   // last MMA issued
@@ -195,9 +236,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ===================== epilogue groups (both CTAs, each drains its own 128 TMEM lanes) =====================
         const int eg = (warp - 4) >> 2;
         const int q = warp & 3;
-        float* xp = reinterpret_cast<float*>(smem_gen + S::TILE_BYTES + (warp - 4) * kEpiWarpBytes);
+        float* xp = reinterpret_cast<float*>(smem_gen + tile_bytes + (warp - 4) * kEpiWarpBytes);
         if (p.tma_out) {
-            const uint32_t stg = smem_base + S::TILE_BYTES + (uint32_t)((warp - 4) * kEpiWarpBytes);
+            const uint32_t stg = smem_base + tile_bytes + (uint32_t)((warp - 4) * kEpiWarpBytes);
             const EpiTiles et{first_tile + eg * tile_step, kConvEpiGroups * tile_step, num_tiles, p.tiles_n, 2, cta_rank};
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * BLOCK_N);
             const uint32_t tempty = is_leader ? tempty_bar(eg) : mapa_shared(tempty_bar(eg), 0);

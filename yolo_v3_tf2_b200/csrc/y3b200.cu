@@ -251,24 +251,46 @@ cudaError_t launch_conv_cl(const ConvCfg& c, const CUtensorMap& ta, const CUtens
     return cudaErrorInvalidValue;
 }
 
+// weights-resident variant of the CTA-pair kernel (conv_tc2.cuh: BRES): Y3_BRES=0 disables it
+const bool g_use_bres = []() { const char* e = getenv("Y3_BRES"); return !(e && e[0] == '0'); }();
+
+// A-pipeline depth left next to the resident half weight tile, 0 if the variant does not apply to this launch
+template <int BN>
+int resident_stages(const y3::ConvArgs& a, int clusters) {
+    using S = y3::Conv2Smem<BN, 128, 8>;
+    if (!g_use_bres || a.dbg != 0) return 0;
+    if (a.tiles_n > 1 && clusters % a.tiles_n != 0) return 0;          // every cluster must stay on one N tile
+    const long long fixed = 1024 + S::XPOSE_BYTES + S::BAR_BYTES + (long long)a.num_k_blocks * S::B_BYTES;
+    const long long st = (232448 - fixed) / S::A_BYTES;
+    if (st < 4) return 0;
+    return (int)std::min<long long>(st, 8);
+}
+
 template <int BN, int ST>
 cudaError_t launch_conv2_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                           const y3::ConvArgs& args, int sms, cudaStream_t st) {
+                           const y3::ConvArgs& args_in, int sms, cudaStream_t st) {
     using S = y3::Conv2Smem<BN, 128, ST>;
     static_assert(S::TOTAL <= 232448, "shared memory budget");
-    auto kern = y3::conv_tc2_kernel<BN, 128, ST>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    y3::ConvArgs args = args_in;
     const int work = ((args.tiles_m + 1) / 2) * args.tiles_n;
     int grid = std::max(1, std::min(work, sms / 2)) * 2;
+    const int rst = resident_stages<BN>(args, grid / 2);
+    auto kern = rst ? y3::conv_tc2_kernel<BN, 128, 8, true> : y3::conv_tc2_kernel<BN, 128, ST, false>;
+    int smem = S::TOTAL;
+    if (rst) {
+        args.stages = rst;
+        smem = y3::Conv2Smem<BN, 128, 8>::total_resident(rst, args.num_k_blocks);
+    }
+    static int configured[2] = {0, 0};
+    if (smem > configured[rst ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured[rst ? 1 : 0] = smem;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(y3::kConvThreads);
-    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
