@@ -129,6 +129,14 @@ int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, i
 int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, int max_boxes, float iou_thr,
            float score_thr, int32_t* selected, int32_t* num_valid, int32_t* status, void* stream);
 
+/* Evaluation counters (reference evaluate_detections.py:39-135, EvaluateDetections.evaluate) for a batch: detections
+ * as produced by y3_gather_detections ([B,max_det,4], [B,max_det] int64, num_det [B]), ground truth [B,max_gt,4] (same
+ * corner order), [B,max_gt] int32, num_gt [B].  counters: int32 [5*nclasses + 2] = preds, gts, tp, fp, fn per class,
+ * then examples, errors; accumulated (atomics), the caller zeroes them once. */
+int y3_evaluate(y3_ctx* ctx, const float* det_boxes, const int64_t* det_classes, const int32_t* num_det, int max_det,
+                const float* gt_boxes, const int32_t* gt_classes, const int32_t* num_gt, int max_gt, int B, int nclasses,
+                float iou_thresh, int32_t* counters, void* stream);
+
 /* Input pre-processing (reference inference.py:157-158, core/load_tfrecords.py:46, core/utils.py:17-28): for each of B
  * images, tf.image.resize-compatible bilinear resampling (half-pixel centres, no antialias) of a uint8 / float32
  * [H, W, 3] device image to out_h x out_w, placed at (off_y, off_x) of a zero-filled dst_h x dst_w canvas

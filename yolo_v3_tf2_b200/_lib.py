@@ -60,6 +60,7 @@ SIGNATURES = {
     "y3_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
     "y3_gather_detections": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "y3_preprocess": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "y3_evaluate": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p, _p]),
     "y3_conv_block_n": (_i, [_i, _i]),
     "y3_conv2d_bf16": (_i, [_p, _p, _i, _i, _i, _i, _i64, _p, _p, _i, _i, _i, _i, _p, _i64, _p, _i64, _i, _i, _p]),
     "y3_conv2d_flat_bf16": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _i64, _p, _i64, _p]),

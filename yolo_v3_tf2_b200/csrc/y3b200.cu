@@ -20,6 +20,7 @@
 #include "decode.cuh"
 #include "nms.cuh"
 #include "preprocess.cuh"
+#include "evaluate.cuh"
 #include "ptx.cuh"
 
 namespace {
@@ -1464,6 +1465,26 @@ int y3_preprocess(y3_ctx* ctx, const void* image_descs_dev, int B, int dst_h, in
     a.mul = 1.0f;
     const unsigned grid = grid_for((long long)B * dst_h * dst_w, 256, ctx->sms);
     y3::preprocess_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    Y3_CUDA(cudaGetLastError());
+    return Y3_OK;
+}
+
+int y3_evaluate(y3_ctx* ctx, const float* det_boxes, const int64_t* det_classes, const int32_t* num_det, int max_det,
+                const float* gt_boxes, const int32_t* gt_classes, const int32_t* num_gt, int max_gt, int B, int nclasses,
+                float iou_thresh, int32_t* counters, void* stream) {
+    (void)cudaGetLastError();
+    if (!ctx || !det_boxes || !det_classes || !num_det || !gt_boxes || !gt_classes || !num_gt || !counters)
+        return fail(Y3_ERR_INVALID, "null argument");
+    if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
+    if (B <= 0 || max_det <= 0 || max_gt <= 0 || nclasses <= 0) return fail(Y3_ERR_INVALID, "bad shape");
+    if (max_gt > 8192) return fail(Y3_ERR_UNSUPPORTED, "more than 8192 ground-truth boxes per image");
+    y3::EvalArgs a{};
+    a.det_boxes = det_boxes; a.det_cls = reinterpret_cast<const long long*>(det_classes); a.num_det = num_det;
+    a.gt_boxes = gt_boxes; a.gt_cls = gt_classes; a.num_gt = num_gt;
+    a.B = B; a.max_det = max_det; a.max_gt = max_gt; a.nclasses = nclasses; a.iou_thresh = iou_thresh;
+    a.preds = counters; a.gts = counters + nclasses; a.tp = counters + 2 * nclasses; a.fp = counters + 3 * nclasses;
+    a.fn = counters + 4 * nclasses; a.examples = counters + 5 * nclasses; a.errors = counters + 5 * nclasses + 1;
+    y3::evaluate_kernel<<<B, 128, (size_t)max_gt * 4, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     Y3_CUDA(cudaGetLastError());
     return Y3_OK;
 }
