@@ -433,8 +433,12 @@ struct ConvSmem {
     // epilogue region: per-warp staging ring of the TMA-store epilogue; the register-transpose epilogue (fp32 heads,
     // fused upsample) uses the first 32 x 36 fp32 of each warp's share instead
     static constexpr int XPOSE_BYTES = kConvEpiGroups * 4 * kEpiWarpBytes;
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kConvEpiGroups; // full/empty + tmem full/empty + tmem ptr + residual ring
+    static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kConvEpiGroups; // full/empty + tmem full/empty + weights + tmem ptr + residual ring
     static constexpr int TOTAL = 1024 /*align slack*/ + TILE_BYTES + XPOSE_BYTES + BAR_BYTES;
+    // weights-resident variant (BRES, see conv_tc2.cuh): `stages` A tiles + all K blocks of the weight tile
+    static constexpr int total_resident(int stages, int num_k_blocks) {
+        return 1024 + stages * A_BYTES + num_k_blocks * B_BYTES + XPOSE_BYTES + BAR_BYTES;
+    }
     static_assert(kEpiWarpBytes >= kXposeWarpFloats * 4 && TILE_BYTES % 1024 == 0, "staging rings share the transpose region");
 };
 
@@ -442,11 +446,15 @@ struct ConvSmem {
 // HALF of the weight tile, multicast into both CTAs' shared memory, so every SM issues 128 + BLOCK_N/2 TMA rows per
 // K block instead of 128 + BLOCK_N (the per-SM TMA issue rate is what bounds the 3x3 layers).  A stage may be refilled
 // only after BOTH CTAs' MMAs have read it, so tcgen05.commit arrives on the empty barrier of both CTAs (count 2).
-template <int BLOCK_N, int SWZ, int STAGES, int CLUSTER>
+// BRES (CLUSTER == 1 only): the whole [BLOCK_N x K] weight tile is loaded once per launch, before
+// griddepcontrol.wait, and the stage ring carries only the A operand.  For the Cin = 32 layers (64-byte rows, 9 taps)
+// the TMA unit's row rate is the limit and the weight rows were a third of the rows fetched per output tile.
+template <int BLOCK_N, int SWZ, int STAGES, int CLUSTER, bool BRES = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
     using S = ConvSmem<BLOCK_N, SWZ, STAGES>;
+    static_assert(!BRES || CLUSTER == 1, "weights-resident variant is single-CTA");
     constexpr int BLOCK_K = SWZ / 2;   // bf16 elements per swizzle row
     constexpr int UMMA_K = 16;
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -456,17 +464,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int nst = BRES ? p.stages : STAGES;                       // pipeline depth in use
+    const uint32_t tile_bytes = BRES ? (uint32_t)(nst * S::A_BYTES + p.num_k_blocks * S::B_BYTES) : (uint32_t)S::TILE_BYTES;
     const uint32_t smem_a = smem_base;
-    const uint32_t smem_b = smem_base + STAGES * S::A_BYTES;
-    const uint32_t bar_base = smem_base + S::TILE_BYTES + S::XPOSE_BYTES;
+    const uint32_t smem_b = smem_base + (uint32_t)(nst * S::A_BYTES);   // BRES: the resident weights, else the B stages
+    const uint32_t bar_base = smem_base + tile_bytes + S::XPOSE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
-    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
+    const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 4);    // resident weights landed
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 5);
+    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 5) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
     volatile uint32_t* tmem_ptr_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + S::TILE_BYTES + S::XPOSE_BYTES + 8 * (2 * STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + tile_bytes + S::XPOSE_BYTES + 8 * (2 * STAGES + 5));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -490,6 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(tempty_bar(a), 128);
         }
         for (int w = 0; w < kEpiMaxBufs * 4 * kConvEpiGroups; ++w) mbar_init(res_bar(0) + 8u * w, 1);
+        mbar_init(bfull_bar, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -505,6 +517,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CLUSTER > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    if constexpr (BRES) {
+        // the weights do not depend on the previous layer: fetch the tile before waiting for it
+        if (warp == 0 && elect_one()) {
+            const int n0 = (first_tile % p.tiles_n) * BLOCK_N;   // constant for this CTA (host-enforced)
+            mbar_arrive_expect_tx(bfull_bar, (uint32_t)(p.num_k_blocks * S::B_BYTES));
+            for (int kb = 0; kb < p.num_k_blocks; ++kb)
+                tma_load_2d(smem_b + kb * S::B_BYTES, &tmB, bfull_bar, kb * BLOCK_K, n0);
+        }
+    }
     // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
     // from here on we touch activations it wrote (and buffers it may still be reading), so wait for it to finish.
     pdl_launch_dependents();
@@ -548,13 +569,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int c0 = 0; c0 < p.kblocks_per_tap * BLOCK_K; c0 += BLOCK_K) {
                             mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                             if (leader) {
-                                mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+                                mbar_arrive_expect_tx(full_bar(stage), BRES ? S::A_BYTES : S::STAGE_BYTES);
                                 tma_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), c0, cw, ch, cn,
                                                    (uint16_t)sx, (uint16_t)r);
-                                load_b(stage, kcoord, n0);
+                                if constexpr (!BRES) load_b(stage, kcoord, n0);
                             }
                             kcoord += BLOCK_K;
-                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                            if (++stage == nst) { stage = 0; phase ^= 1u; }
                         }
                     }
                 }
@@ -562,12 +583,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                     if (leader) {
-                        mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+                        mbar_arrive_expect_tx(full_bar(stage), BRES ? S::A_BYTES : S::STAGE_BYTES);
                         tma_load_2d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), kcoord, m0);
-                        load_b(stage, kcoord, n0);
+                        if constexpr (!BRES) load_b(stage, kcoord, n0);
                     }
                     kcoord += BLOCK_K;
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == nst) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -581,6 +602,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         int j = 0;
+        if constexpr (BRES) {
+            mbar_wait(bfull_bar, 0, 0x700);   // the weight tile is resident
+            tc_fence_after();
+        }
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
             const int acc = j & 1;
             mbar_wait(tempty_bar(acc), (uint32_t)(((j >> 1) & 1) ^ 1), 0x200 + acc);
@@ -592,7 +617,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (leader) {
                     // stage s sits s*A_BYTES (s*B_BYTES) further: +bytes>>4 in the descriptor's address field
                     const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
-                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (S::B_BYTES >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)((BRES ? kb : stage) * (S::B_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
@@ -604,7 +629,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     else umma_commit_mc(empty_bar(stage), (uint16_t)((1u << CLUSTER) - 1u));
                     if (kb == p.num_k_blocks - 1) umma_commit(tfull_bar(acc));
                 }
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                if (++stage == nst) { stage = 0; phase ^= 1u; }
             }
         }
         __syncwarp();
@@ -612,9 +637,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue groups =====================
         const int eg = (warp - 4) >> 2;         // group: owns accumulator stage eg
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        float* xp = reinterpret_cast<float*>(smem_gen + S::TILE_BYTES + (warp - 4) * kEpiWarpBytes);
+        float* xp = reinterpret_cast<float*>(smem_gen + tile_bytes + (warp - 4) * kEpiWarpBytes);
         if (p.tma_out) {
-            const uint32_t stg = smem_base + S::TILE_BYTES + (uint32_t)((warp - 4) * kEpiWarpBytes);
+            const uint32_t stg = smem_base + tile_bytes + (uint32_t)((warp - 4) * kEpiWarpBytes);
             const EpiTiles et{first_tile + eg * tile_step, kConvEpiGroups * tile_step, num_tiles, p.tiles_n, CLUSTER, cta_rank};
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * BLOCK_N);
             if (BLOCK_N >= 64 && p.tma_out == 64)

@@ -192,24 +192,44 @@ bool pick_cfg(int cin, int cout, int ksize, ConvCfg& c) {
     return true;
 }
 
+// weights-resident variants of the conv kernels (BRES): Y3_BRES=0 disables them
+const bool g_use_bres = []() { const char* e = getenv("Y3_BRES"); return !(e && e[0] == '0'); }();
+
 template <int BN, int SWZ, int ST, int CL>
 cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                          const y3::ConvArgs& args, int sms, cudaStream_t st) {
+                          const y3::ConvArgs& args_in, int sms, cudaStream_t st) {
     using S = y3::ConvSmem<BN, SWZ, ST>;
     static_assert(S::TOTAL <= 232448, "shared memory budget");
-    auto kern = y3::conv_tc_kernel<BN, SWZ, ST, CL>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    y3::ConvArgs args = args_in;
     const int work = ((args.tiles_m + CL - 1) / CL) * args.tiles_n;   // (groups of CL M tiles) x N tiles
     int grid = std::max(1, std::min(work, sms / CL)) * CL;
+    // weights-resident variant: single CTA, every CTA stays on one N tile, at least 4 A stages next to the weights
+    int rst = 0;
+    if (CL == 1 && g_use_bres && args.dbg == 0 && (args.tiles_n == 1 || grid % args.tiles_n == 0)) {
+        using S8 = y3::ConvSmem<BN, SWZ, 8>;
+        const long long fixed = 1024 + S8::XPOSE_BYTES + S8::BAR_BYTES + (long long)args.num_k_blocks * S8::B_BYTES;
+        const long long n = (232448 - fixed) / S8::A_BYTES;
+        if (n >= 4) rst = (int)std::min<long long>(n, 8);
+    }
+    int smem = S::TOTAL;
+    const void* kern = (const void*)y3::conv_tc_kernel<BN, SWZ, ST, CL, false>;
+    if constexpr (CL == 1) {
+        if (rst) {
+            kern = (const void*)y3::conv_tc_kernel<BN, SWZ, 8, 1, true>;
+            args.stages = rst;
+            smem = y3::ConvSmem<BN, SWZ, 8>::total_resident(rst, args.num_k_blocks);
+        }
+    }
+    static int configured[2] = {0, 0};
+    if (smem > configured[rst ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured[rst ? 1 : 0] = smem;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(y3::kConvThreads);
-    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -220,7 +240,8 @@ cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, args);
+    void* kargs[5] = {(void*)&ta, (void*)&tb, (void*)&to, (void*)&tr, (void*)&args};
+    return cudaLaunchKernelExC(&cfg, kern, kargs);
 }
 
 // deepest pipeline (at most 8 stages) that fits next to the transpose tiles, barriers and alignment slack
@@ -251,9 +272,6 @@ cudaError_t launch_conv_cl(const ConvCfg& c, const CUtensorMap& ta, const CUtens
     }
     return cudaErrorInvalidValue;
 }
-
-// weights-resident variant of the CTA-pair kernel (conv_tc2.cuh: BRES): Y3_BRES=0 disables it
-const bool g_use_bres = []() { const char* e = getenv("Y3_BRES"); return !(e && e[0] == '0'); }();
 
 // A-pipeline depth left next to the resident half weight tile, 0 if the variant does not apply to this launch
 template <int BN>
