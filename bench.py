@@ -220,22 +220,46 @@ def main():
     # ---------------- device-resident timing (value) ----------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for i in range(max(args.warmup, 3)):
+    # W untimed warm-up steps as asked, and never fewer than 20: a fresh process needs a few hundred milliseconds of load
+    # before the SM clock has settled (short runs measured 10 % low in the first timed loop otherwise)
+    nwarm = max(args.warmup, 20)
+    t_w = time.perf_counter()
+    for i in range(nwarm):
         step(xs[i % nbuf])
     sync_all()
+    # ... then about 2 s of steady load: the first CUDA process on a fresh box needs that long before its clocks settle
+    # (the first nwarm steps mostly pay one-time initialisation, so the step time is taken from a second batch of 20)
+    t_w = time.perf_counter()
+    for i in range(20):
+        step(xs[i % nbuf])
+    sync_all()
+    dt_w = max(time.perf_counter() - t_w, 1e-3)
+    nwarm += 20
+    extra = min(2000, int(2.0 / dt_w) * 20)
+    if world > 1:   # every rank must issue the same number of collectives
+        tw = torch.tensor([extra], dtype=torch.int64, device=dev)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        extra = int(tw.item())
+    for i in range(extra):
+        step(xs[i % nbuf])
+    nwarm += extra
+    sync_all()
+    # The timed steps call the public serving entry point Detector.detections_graphed(): the ~80 launches of a step are
+    # replayed from a CUDA graph, so the number does not depend on how fast this box's host can issue launches (the
+    # eager loop measured anything between 5.3 and 7.9 ms/step on different boxes for a 5.4 ms GPU step).
+    def gstep(x):
+        local = det.detections_graphed(x)
+        if world > 1 and not no_gather:
+            y3dist.gather_detections(*local)
+        return local
+
+    for i in range(3):
+        gstep(xs[i % nbuf])
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0.record()
     for i in range(args.steps):
-        x = xs[i % nbuf]
-        fwd_ev[i][0].record()
-        grids = model(x)
-        fwd_ev[i][1].record()
-        bboxes, conf, probs, scores, cls = y3.yolo_decode(grids, anchors, NCLASSES, with_scores=True)
-        sel, nv, status = nms_padded(bboxes, scores, mx, 0.5, 0.1)
-        ob, oc, os_ = gather_detections_batched(bboxes, cls, scores, sel, nv)
-        if world > 1 and not no_gather:
-            y3dist.gather_detections(ob, oc, os_, nv)
+        gstep(xs[i % nbuf])
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -244,7 +268,38 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max / 1e3)
-    fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / args.steps
+
+    # roofline of the conv stack: the forward pass alone (75 conv launches, also replayed from a graph), timed with CUDA
+    # events for the same number of steps right after the timed region, same clocks / power state
+    fx = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)
+    fx.copy_(xs[0])
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fouts = model(fx, padded=True)
+    torch.cuda.current_stream().wait_stream(side)
+    fgraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(fgraph):
+        model(fx, padded=True, outs=fouts)
+    for i in range(3):
+        fgraph.replay()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        fx.copy_(xs[i % nbuf], non_blocking=True)     # a different input every pass, as in the timed steps
+        fgraph.replay()
+    f1.record()
+    torch.cuda.synchronize()
+    copy_ms = 0.0
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(args.steps):
+        fx.copy_(xs[i % nbuf], non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    copy_ms = c0.elapsed_time(c1)
+    fwd_ms = (f0.elapsed_time(f1) - copy_ms) / args.steps
     achieved_tflops = flops_img * B / (fwd_ms / 1e3) / 1e12
 
     # ---------------- end to end through the public API with host buffers (e2e) ----------------
@@ -271,7 +326,10 @@ def main():
                     xin[nxt].copy_(host[(i + 1) % nbuf], non_blocking=True)
                     ready[nxt].record(copy_stream)
             main_stream.wait_event(ready[cur])
-            ob, oc, os_, nv = step(xin[cur])
+            # the public serving call: the whole step replayed from a CUDA graph (one launch), then the NCCL gather
+            ob, oc, os_, nv = det.detections_graphed(xin[cur])
+            if world > 1 and not no_gather:
+                y3dist.gather_detections(ob, oc, os_, nv)
             free[cur].record(main_stream)
             rec = y3dist.pack_detections(ob, oc, os_, nv)
             out_host[cur].copy_(rec, non_blocking=True)
@@ -301,14 +359,15 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
         line = {
             "metric": f"images/sec ({S}^2, backbone+decode+NMS)", "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "steps": args.steps, "warmup": nwarm, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(S, B), "images_per_gpu": B, "l2": "inputs rotate over 3 device buffers; each step streams a ~1 GB "
                                                   "activation arena (>> 126 MB L2) so no step starts with a warm L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 3 * 4,
                     "d2h_bytes_per_step": B * (mx * 6 + 1) * 4,
-                    "note": "Detector.detections() on pinned host batches, double-buffered H2D on a copy stream"},
+                    "note": "Detector.detections_graphed() (the step replayed from a CUDA graph) on pinned host batches, "
+                            "double-buffered H2D on a copy stream, detections copied back to pinned host memory every step"},
             "gpu_launches": args.steps * (launches_fwd + 3),
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak, "traffic": conv_traffic_bytes(S, B), "peak_source": peak_src,

@@ -110,6 +110,13 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel_hwio_host, c
 /* x: [B,H,W,3] fp32 NHWC in [0,1].  outs[k]: [B,gh_k,gw_k,3,5+C] fp32 for every output in model order. */
 int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream);
 
+/* Same, with a pixel pitch (in floats) per output: out k is [B, gh, gw, out_pitch[k]] with the 3*(5+C) logits of a pixel
+ * at its start.  A pitch that is a multiple of 4 floats (e.g. 256 for C = 80) lets the head convs write through the
+ * TMA-store epilogue instead of unaligned 255-float rows; y3_decode_pitched reads that layout.  pitch == 3*(5+C) is
+ * y3_net_forward. */
+int y3_net_forward_pitched(y3_net* net, const float* x, int B, float* const* outs, const int* out_pitch, int n_outs,
+                           void* stream);
+
 /* Profiling aid: same as y3_net_forward with a CUDA event between kernels; after the call ms_host[i] is the device time
  * of kernel i and layer_host[i] the layer index it implements (n_steps = y3_net_num_steps). Synchronises the stream. */
 int y3_net_num_steps(y3_net* net);
@@ -121,6 +128,11 @@ int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs,
 int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, int n_scales,
               const float* anchors_host, int B, int nclasses, float* bboxes, float* conf, float* probs, float* scores,
               int64_t* class_idx, void* stream);
+
+/* y3_decode on grids stored with a pixel pitch (floats) per scale, as written by y3_net_forward_pitched. */
+int y3_decode_pitched(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, const int* pix_pitch,
+                      int n_scales, const float* anchors_host, int B, int nclasses, float* bboxes, float* conf,
+                      float* probs, float* scores, int64_t* class_idx, void* stream);
 
 int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, int N, int nclasses, float* scores,
                     int64_t* class_idx, void* stream);

@@ -97,6 +97,27 @@ def test_forward_batch_invariance_and_rebatch(cuda):
         assert torch.equal(allb[k], torch.cat([o[k] for o in one], 0))
 
 
+@pytest.mark.parametrize("C", [80, 38, 3])
+def test_pitched_head_outputs_equal_dense(cuda, C):
+    """``model(x, padded=True)`` (fp32 TMA-store epilogue in the head convs, pixel pitch rounded up to 4 floats) holds
+    exactly the numbers of ``model(x)``, and ``yolo_decode`` of the pitched grids equals the decode of the dense ones."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    model = y3.ParseModel.builtin_yolov3(C).init_weights("variance", seed=13)
+    x = torch.rand((3, 128, 128, 3), device="cuda")
+    dense = model(x)
+    pitched = model(x, padded=True)
+    F = 5 + C
+    for d, p in zip(dense, pitched):
+        assert p.shape[:3] == d.shape[:3] and p.shape[3] == (3 * F + 3) // 4 * 4
+        assert torch.equal(p[..., :3 * F].reshape(d.shape), d)
+    a = y3.yolo_decode(dense, configs.coco_anchors(), C, with_scores=True)
+    b = y3.yolo_decode(pitched, configs.coco_anchors(), C, with_scores=True)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
 def test_detector_end_to_end(cuda):
     """model -> decode -> NMS (inference.py:109-117): fused and reference-sequence paths agree bit for bit, and NMS on
     the GPU's own decoded tensors equals the oracle NMS on those same tensors."""
@@ -118,6 +139,23 @@ def test_detector_end_to_end(cuda):
         n = int(nv[b])
         assert torch.equal(ob[b, :n], fused[0][b][fused[3][b, :n].long()])
         assert (ob[b, n:] == 0).all() and (os_[b, n:] == 0).all()
+
+
+def test_graphed_detections_equal_eager(cuda):
+    """The CUDA-graph replay of a step (75 PDL-chained cluster launches + decode + NMS + gather) returns exactly what
+    the eager call returns, for successive different inputs."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    model = y3.ParseModel.builtin_yolov3(80).init_weights("variance", seed=21)
+    det = y3.Detector(model, configs.coco_anchors(), 80)
+    for seed in range(3):
+        x = torch.rand((2, 96, 96, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed))
+        eager = [t.clone() for t in det.detections(x)]
+        graphed = det.detections_graphed(x)
+        torch.cuda.synchronize()
+        for a, b in zip(eager, graphed):
+            assert torch.equal(a, b)
 
 
 def test_reference_yaml_and_darknet_weights_roundtrip(cuda, tmp_path):

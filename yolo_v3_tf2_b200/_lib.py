@@ -53,9 +53,11 @@ SIGNATURES = {
     "y3_net_output_shape": (_i, [_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "y3_net_load_conv": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _f]),
     "y3_net_forward": (_i, [_p, _p, _i, C.POINTER(_p), _i, _p]),
+    "y3_net_forward_pitched": (_i, [_p, _p, _i, C.POINTER(_p), C.POINTER(_i), _i, _p]),
     "y3_net_num_steps": (_i, [_p]),
     "y3_net_forward_timed": (_i, [_p, _p, _i, C.POINTER(_p), _i, _p, _p, _p, _i]),
     "y3_decode": (_i, [_p, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "y3_decode_pitched": (_i, [_p, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "y3_class_reduce": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "y3_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
     "y3_gather_detections": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),

@@ -156,8 +156,11 @@ class Y3Model:
         ctx.close()
         return out
 
-    def __call__(self, x, training=False, outs=None):
-        """x: [B, H, W, 3] float32 NHWC in [0, 1] (torch CUDA tensor; numpy / CPU tensors are copied to the GPU)."""
+    def __call__(self, x, training=False, outs=None, padded=False):
+        """x: [B, H, W, 3] float32 NHWC in [0, 1] (torch CUDA tensor; numpy / CPU tensors are copied to the GPU).
+        ``padded=True`` (used by ``Detector``): each output is [B, gh, gw, P] with P = 3*(5+C) rounded up to a multiple
+        of 4 floats and the logits of a pixel at its start -- the head convs then store through TMA and ``yolo_decode``
+        reads the pitched layout directly."""
         if self._params is None:
             raise _lib.Y3Error("model has no weights: call load_weights / set_weights / init_weights first")
         if isinstance(x, np.ndarray):
@@ -169,6 +172,15 @@ class Y3Model:
         x = x.contiguous().float()
         B, H, W, _ = x.shape
         ent = self._net(H, W, B, x.device.index)
+        if padded:
+            if outs is None:
+                outs = [torch.empty((B, gh, gw, (ch + 3) // 4 * 4), dtype=torch.float32, device=x.device)
+                        for gh, gw, ch in ent["out_shapes"]]
+            op = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+            pitch = (C.c_int * len(outs))(*[int(o.shape[3]) for o in outs])
+            _lib.check(_lib.lib().y3_net_forward_pitched(ent["handle"], _lib.ptr(x), int(B), op, pitch, len(outs),
+                                                         _lib.stream_ptr()))
+            return outs
         if outs is None:
             outs = [torch.empty((B, gh, gw, 3, ch // 3), dtype=torch.float32, device=x.device)
                     for gh, gw, ch in ent["out_shapes"]]

@@ -31,8 +31,13 @@ def yolo_decode(model_output_grids, anchors_table, nclasses, with_scores=False):
     if ns < 1 or ns > 3:
         raise _lib.Y3Unsupported("1..3 output grids supported")
     F = 5 + int(nclasses)
+    # 4-D grids [B, gh, gw, P >= 3*F] are the pitched layout of ``model(x, padded=True)``
+    pitched = all(g.dim() == 4 for g in grids)
     for g in grids:
-        if g.dim() != 5 or g.shape[3] != 3 or g.shape[4] != F:
+        if pitched:
+            if g.shape[3] < 3 * F or g.shape[3] % 4 != 0:
+                raise ValueError(f"pitched grid shape {tuple(g.shape)}: pitch must be >= {3 * F} and a multiple of 4")
+        elif g.dim() != 5 or g.shape[3] != 3 or g.shape[4] != F:
             raise ValueError(f"grid shape {tuple(g.shape)} is not [B, gh, gw, 3, {F}]")
     B = grids[0].shape[0]
     anchors = np.ascontiguousarray(np.asarray(
@@ -50,9 +55,15 @@ def yolo_decode(model_output_grids, anchors_table, nclasses, with_scores=False):
     gp = (C.c_void_p * ns)(*[g.data_ptr() for g in grids])
     gh = (C.c_int * ns)(*[int(g.shape[1]) for g in grids])
     gw = (C.c_int * ns)(*[int(g.shape[2]) for g in grids])
-    _lib.check(_lib.lib().y3_decode(ctx.handle, gp, gh, gw, ns, anchors.ctypes.data_as(C.c_void_p), B, int(nclasses),
-                                    _lib.ptr(bboxes), _lib.ptr(conf), _lib.ptr(probs), _lib.ptr(scores), _lib.ptr(cls),
-                                    _lib.stream_ptr()))
+    if pitched:
+        pp = (C.c_int * ns)(*[int(g.shape[3]) for g in grids])
+        _lib.check(_lib.lib().y3_decode_pitched(ctx.handle, gp, gh, gw, pp, ns, anchors.ctypes.data_as(C.c_void_p), B,
+                                                int(nclasses), _lib.ptr(bboxes), _lib.ptr(conf), _lib.ptr(probs),
+                                                _lib.ptr(scores), _lib.ptr(cls), _lib.stream_ptr()))
+    else:
+        _lib.check(_lib.lib().y3_decode(ctx.handle, gp, gh, gw, ns, anchors.ctypes.data_as(C.c_void_p), B, int(nclasses),
+                                        _lib.ptr(bboxes), _lib.ptr(conf), _lib.ptr(probs), _lib.ptr(scores), _lib.ptr(cls),
+                                        _lib.stream_ptr()))
     if with_scores:
         return bboxes, conf, probs, scores, cls
     return bboxes, conf, probs

@@ -290,19 +290,22 @@ struct EpiCursor {     // walks (tile, chunk) in processing order
     }
 };
 
-template <int CW, int NBUF>
+// F32 = true: fp32 output (the head convs when the caller provides a 16-byte aligned pixel pitch): CW = 32 floats per
+// 128-byte staging row, no residual.
+template <int CW, int NBUF, bool F32 = false>
 __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUtensorMap* tmO, const CUtensorMap* tmR,
                                                   int block_n, const EpiTiles et, uint32_t t_acc, int q, int lane,
                                                   uint32_t stg, uint32_t res_bar0, uint32_t tfull_bar,
                                                   uint32_t tempty_addr, bool tempty_remote, unsigned long long* ts,
                                                   int ts_slot) {
-    static_assert((CW == 64 || CW == 32) && NBUF >= 2 && NBUF <= kEpiMaxBufs && NBUF * 32 * CW * 2 <= kEpiWarpBytes, "ring");
-    constexpr uint32_t ROW_BYTES = CW * 2;
+    static_assert((CW == 64 || CW == 32) && NBUF >= 2 && NBUF <= kEpiMaxBufs &&
+                  NBUF * 32 * CW * (F32 ? 4 : 2) <= kEpiWarpBytes && (!F32 || CW == 32), "ring");
+    constexpr uint32_t ROW_BYTES = CW * (F32 ? 4 : 2);
     constexpr uint32_t BUF_BYTES = 32 * ROW_BYTES;
     const bool drain_only = (p.dbg & 1) != 0;
-    const bool has_res = (p.residual != nullptr) && !drain_only;
+    const bool has_res = !F32 && (p.residual != nullptr) && !drain_only;
     const float slope = p.leaky ? 0.1f : 1.0f;   // LeakyReLU(0.1)(x) = max(x, 0.1x); slope 1 makes it the identity
-    const uint32_t sw = (CW == 64) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+    const uint32_t sw = (ROW_BYTES == 128) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
     const uint32_t row_off = (uint32_t)lane * ROW_BYTES;
 
     EpiCursor<CW> pr, pf;    // chunk being processed / chunk whose residual is fetched next
@@ -377,6 +380,14 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
                 f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], slope * f[e]);
+                if constexpr (F32) {
+                    // 8 floats = two 16-byte pieces of the 128-byte row
+                    const uint32_t a0 = buf + row_off + ((((uint32_t)(2 * j)) ^ sw) << 4);
+                    const uint32_t a1 = buf + row_off + ((((uint32_t)(2 * j + 1)) ^ sw) << 4);
+                    st_shared_v4_relaxed(a0, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+                    st_shared_v4_relaxed(a1, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+                    continue;
+                }
                 const uint32_t addr = buf + row_off + ((((uint32_t)j) ^ sw) << 4);
                 if (has_res) {
                     const uint4 r = ld_shared_v4_relaxed(addr);   // ordered after the residual barrier wait (both volatile)
@@ -645,6 +656,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (BLOCK_N >= 64 && p.tma_out == 64)
                 epilogue_role_tma<64, 2>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
                                          tempty_bar(eg), false, nullptr, 7 + eg);
+            else if (p.out_fp32)
+                epilogue_role_tma<32, 2, true>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
+                                               tempty_bar(eg), false, nullptr, 7 + eg);
             else
                 epilogue_role_tma<32, 4>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
                                          tempty_bar(eg), false, nullptr, 7 + eg);

@@ -245,6 +245,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (p.tma_out == 64)
                 epilogue_role_tma<64, 2>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
                                          tempty, !is_leader, p.ts, 7 + eg);
+            else if (p.out_fp32)
+                epilogue_role_tma<32, 2, true>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
+                                               tempty, !is_leader, p.ts, 7 + eg);
             else
                 epilogue_role_tma<32, 4>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
                                          tempty, !is_leader, p.ts, 7 + eg);

@@ -23,6 +23,8 @@ struct DecodeArgs {
     int gh[3], gw[3];
     int rec_off[3];        // first record of scale s inside one image
     int chunk_begin[4];    // prefix sum of per-scale chunk counts
+    int pitch[3];          // floats between consecutive pixels (3*(5+C) dense, or the padded pitch of the head convs)
+    int recs[3];           // records per chunk (kDecodeRecs; a multiple of 3 = whole pixels when the pitch is padded)
     float anchors[18];     // [3 scales][3 anchors][w, h]
     int B, C, N;
     float* bboxes;
@@ -30,6 +32,7 @@ struct DecodeArgs {
     float* probs;
     float* scores;         // optional
     long long* cls;        // optional
+    int stage_bytes;       // size of the record staging buffer (the record-index array follows it)
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -37,8 +40,8 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + e
 __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs a) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const int F = 5 + a.C;
-    float* rec = reinterpret_cast<float*>(dsm);                         // [kDecodeRecs * F]
-    int* out_rec = reinterpret_cast<int*>(rec + ((kDecodeRecs * F + 3) & ~3));   // [kDecodeRecs] global record index
+    float* rec = reinterpret_cast<float*>(dsm);                         // staged records (pixel pitch as in memory)
+    int* out_rec = reinterpret_cast<int*>(dsm + a.stage_bytes);         // [kDecodeRecs] global record index
     __shared__ __align__(8) uint64_t bar;
 
     int s = 0;
@@ -47,11 +50,16 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     const int chunk = blockIdx.x - a.chunk_begin[s];
     const int per_img = a.gh[s] * a.gw[s] * 3;
     const long long total = (long long)a.B * per_img;
-    const long long r0 = (long long)chunk * kDecodeRecs;
-    const int nrec = (int)min((long long)kDecodeRecs, total - r0);
-    const float* src = a.in[s] + r0 * F;
-    const int nfl = nrec * F;
+    const int recs = a.recs[s];
+    const int pitch = a.pitch[s];
+    const bool padded = pitch != 3 * F;       // then recs % 3 == 0 and a chunk starts at a pixel boundary
+    const long long r0 = (long long)chunk * recs;
+    const int nrec = (int)min((long long)recs, total - r0);
+    const float* src = padded ? a.in[s] + (r0 / 3) * pitch : a.in[s] + r0 * F;
+    const int nfl = padded ? (nrec / 3) * pitch : nrec * F;
     const uint32_t bulk_bytes = ((uint32_t)nfl * 4u) & ~15u;
+    // record t of the chunk inside the staging buffer
+    auto rec_at = [&](int t) { return padded ? rec + (t / 3) * pitch + (t % 3) * F : rec + t * F; };
 
     const uint32_t bar_s = smem_u32(&bar);
     if (threadIdx.x == 0) {
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         const int gj = cell - gi * a.gw[s];
         const long long orec = (long long)b * a.N + a.rec_off[s] + local;
         out_rec[t] = (int)orec;
-        const float* r = rec + t * F;
+        float* r = rec_at(t);
         const float sx = sigmoidf_acc(r[0]);
         const float sy = sigmoidf_acc(r[1]);
         const float w = expf(r[2]) * a.anchors[(s * 3 + anc) * 2 + 0];
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         box.w = __fadd_rn(cy, hh);
         reinterpret_cast<float4*>(a.bboxes)[orec] = box;
         a.conf[orec] = obj;
-        rec[t * F + 4] = obj;   // kept for the fused score in phase (3)
+        r[4] = obj;   // kept for the fused score in phase (3)
     }
     __syncthreads();
 
@@ -111,24 +119,24 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         for (int e = threadIdx.x; e < n4; e += kDecodeThreads) {
             const int ri = e / c4;
             const int c = (e - ri * c4) << 2;
-            const float* r = rec + ri * F + 5 + c;
+            float* r = rec_at(ri) + 5 + c;
             float4 o;
             o.x = sigmoidf_acc(r[0]);
             o.y = sigmoidf_acc(r[1]);
             o.z = sigmoidf_acc(r[2]);
             o.w = sigmoidf_acc(r[3]);
             *reinterpret_cast<float4*>(a.probs + (long long)out_rec[ri] * C + c) = o;
-            float* w = rec + ri * F + 5 + c;
-            w[0] = o.x; w[1] = o.y; w[2] = o.z; w[3] = o.w;
+            r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = o.w;
         }
     } else {
         const int n1 = nrec * C;
         for (int e = threadIdx.x; e < n1; e += kDecodeThreads) {
             const int ri = e / C;
             const int c = e - ri * C;
-            const float pc = sigmoidf_acc(rec[ri * F + 5 + c]);
+            float* r = rec_at(ri) + 5 + c;
+            const float pc = sigmoidf_acc(*r);
             a.probs[(long long)out_rec[ri] * C + c] = pc;
-            rec[ri * F + 5 + c] = pc;
+            *r = pc;
         }
     }
 
@@ -136,7 +144,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     if (a.scores != nullptr) {
         __syncthreads();
         if ((int)threadIdx.x < nrec) {
-            const float* r = rec + threadIdx.x * F;
+            const float* r = rec_at((int)threadIdx.x);
             float best = r[5];
             int bi = 0;
             for (int c = 1; c < C; ++c) {

@@ -104,6 +104,19 @@ int make_map_epi(const Driver& d, CUtensorMap* tm, const void* base, uint64_t ro
     return Y3_OK;
 }
 
+// fp32 output view [rows][cols] with a 16-byte aligned row pitch (head convs with a padded pixel pitch): 32 x 32 boxes
+int make_map_epi_f32(const Driver& d, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = d.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 epilogue view) failed: " + std::to_string((int)r));
+    return Y3_OK;
+}
+
 // chunk width of the TMA-store epilogue: 64 columns (two 4 KB staging buffers per warp) wherever the tile is at least
 // 64 wide, else 32 columns (four 2 KB buffers).  Measured on the whole net: 64 everywhere 4.98 ms, 32 for the layers
 // with a fused residual (deeper residual prefetch, twice the chunks) 5.06 ms, 32 everywhere 5.26 ms.  Y3_EPI_CW forces one.
@@ -1223,11 +1236,17 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
     return Y3_OK;
 }
 
-static int net_forward_impl(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream,
-                            std::vector<cudaEvent_t>* evs);
+static int net_forward_impl(y3_net* net, const float* x, int B, float* const* outs, const int* out_pitch, int n_outs,
+                            void* stream, std::vector<cudaEvent_t>* evs);
 
 int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream) {
-    return net_forward_impl(net, x, B, outs, n_outs, stream, nullptr);
+    return net_forward_impl(net, x, B, outs, nullptr, n_outs, stream, nullptr);
+}
+
+int y3_net_forward_pitched(y3_net* net, const float* x, int B, float* const* outs, const int* out_pitch, int n_outs,
+                           void* stream) {
+    if (!out_pitch) return fail(Y3_ERR_INVALID, "out_pitch is null");
+    return net_forward_impl(net, x, B, outs, out_pitch, n_outs, stream, nullptr);
 }
 
 int y3_net_num_steps(y3_net* net) { return net ? (int)net->steps.size() : 0; }
@@ -1237,7 +1256,7 @@ int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs,
     if (!net || !ms_host || n_steps != (int)net->steps.size()) return fail(Y3_ERR_INVALID, "bad timing buffers");
     std::vector<cudaEvent_t> evs(net->steps.size() + 1);
     for (auto& e : evs) Y3_CUDA(cudaEventCreate(&e));
-    int rc = net_forward_impl(net, x, B, outs, n_outs, stream, &evs);
+    int rc = net_forward_impl(net, x, B, outs, nullptr, n_outs, stream, &evs);
     if (rc == Y3_OK) {
         cudaError_t e = cudaEventSynchronize(evs.back());
         if (e != cudaSuccess) rc = fail(Y3_ERR_CUDA, std::string("cudaEventSynchronize: ") + cudaGetErrorString(e));
@@ -1252,8 +1271,8 @@ int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs,
     return rc;
 }
 
-static int net_forward_impl(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream,
-                            std::vector<cudaEvent_t>* evs) {
+static int net_forward_impl(y3_net* net, const float* x, int B, float* const* outs, const int* out_pitch, int n_outs,
+                            void* stream, std::vector<cudaEvent_t>* evs) {
     (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!net || !x || !outs) return fail(Y3_ERR_INVALID, "null argument");
     if (net->ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
@@ -1278,15 +1297,30 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
                 ca.residual = tensor_ptr(*net, s.src2);
                 ca.res_stride = net->tensors[s.src2].pix_stride;
             }
+            CUtensorMap tmo_local;
+            const CUtensorMap* tmo = &s.tmO;
+            ca.tma_out = s.tma_out;
             if (o.fp32_output) {
                 ca.out = outs[o.out_index];
                 ca.out_stride = o.C;
                 ca.out_fp32 = 1;
+                const int pitch = out_pitch ? out_pitch[o.out_index] : o.C;
+                if (pitch != o.C) {
+                    // padded pixel pitch: 16-byte aligned rows, written by the fp32 TMA-store epilogue
+                    if (pitch < o.C || pitch % 4 != 0 || (reinterpret_cast<uintptr_t>(ca.out) & 15) != 0)
+                        return fail(Y3_ERR_INVALID, "output pitch must be >= channels, a multiple of 4 floats, and the buffer 16-byte aligned");
+                    if (!g_use_tma_epi || s.fused_up || s.flat || s.in_padded || s.cfg.gather)
+                        return fail(Y3_ERR_UNSUPPORTED, "padded head outputs need the TMA-store epilogue");
+                    int rc2 = make_map_epi_f32(net->ctx->drv, &tmo_local, ca.out, (uint64_t)B * s.Ho * s.Wo, o.C, pitch);
+                    if (rc2) return rc2;
+                    tmo = &tmo_local;
+                    ca.out_stride = pitch;
+                    ca.tma_out = 32;
+                }
             } else {
                 ca.out = tensor_ptr(*net, s.dst);
                 ca.out_stride = o.pix_stride;
             }
-            ca.tma_out = s.tma_out;
             if (s.flat) {
                 FlatGeom g;
                 flat_geometry(a.W + 1, s.cfg.swz, s.cfg.block_n, g);
@@ -1300,9 +1334,9 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
                     ca.src = tensor_ptr(*net, s.src);
                     ca.src_stride = a.pix_stride;
                 }
-                Y3_CUDA(launch_gather(s.cfg, s.tmB, s.tmO, s.tmR, ca, sms, st));
+                Y3_CUDA(launch_gather(s.cfg, s.tmB, *tmo, s.tmR, ca, sms, st));
             } else {
-                Y3_CUDA(launch_conv(s.cfg, s.tmA, s.tmB, s.tmO, s.tmR, ca, sms, st));
+                Y3_CUDA(launch_conv(s.cfg, s.tmA, s.tmB, *tmo, s.tmR, ca, sms, st));
             }
         } else if (s.kind == 2) {
             const TensorInfo& a = net->tensors[s.src];
@@ -1365,9 +1399,28 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
     return Y3_OK;
 }
 
+static int decode_impl(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, const int* pix_pitch,
+                       int n_scales, const float* anchors_host, int B, int nclasses, float* bboxes, float* conf,
+                       float* probs, float* scores, int64_t* class_idx, void* stream);
+
 int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, int n_scales,
               const float* anchors_host, int B, int nclasses, float* bboxes, float* conf, float* probs, float* scores,
               int64_t* class_idx, void* stream) {
+    return decode_impl(ctx, grids, gh, gw, nullptr, n_scales, anchors_host, B, nclasses, bboxes, conf, probs, scores,
+                       class_idx, stream);
+}
+
+int y3_decode_pitched(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, const int* pix_pitch,
+                      int n_scales, const float* anchors_host, int B, int nclasses, float* bboxes, float* conf,
+                      float* probs, float* scores, int64_t* class_idx, void* stream) {
+    if (!pix_pitch) return fail(Y3_ERR_INVALID, "pix_pitch is null");
+    return decode_impl(ctx, grids, gh, gw, pix_pitch, n_scales, anchors_host, B, nclasses, bboxes, conf, probs, scores,
+                       class_idx, stream);
+}
+
+static int decode_impl(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, const int* pix_pitch,
+                       int n_scales, const float* anchors_host, int B, int nclasses, float* bboxes, float* conf,
+                       float* probs, float* scores, int64_t* class_idx, void* stream) {
     (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!ctx || !grids || !gh || !gw || !anchors_host || !bboxes || !conf || !probs) return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
@@ -1375,18 +1428,28 @@ int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* 
     if (B <= 0 || nclasses <= 0) return fail(Y3_ERR_INVALID, "bad B / nclasses");
     if ((scores == nullptr) != (class_idx == nullptr)) return fail(Y3_ERR_INVALID, "scores and class_idx go together");
     y3::DecodeArgs a{};
-    int off = 0, chunks = 0;
+    const int F = 5 + nclasses;
+    int off = 0, chunks = 0, max_pitch = 3 * F;
     for (int s = 0; s < 3; ++s) {
         a.chunk_begin[s] = chunks;
+        a.pitch[s] = 3 * F;
+        a.recs[s] = y3::kDecodeRecs;
         if (s < n_scales) {
             if (!grids[s] || gh[s] <= 0 || gw[s] <= 0) return fail(Y3_ERR_INVALID, "bad grid");
             if ((reinterpret_cast<uintptr_t>(grids[s]) & 15) != 0) return fail(Y3_ERR_INVALID, "grid pointers must be 16-byte aligned");
+            if (pix_pitch && pix_pitch[s] != 3 * F) {
+                // padded pixel pitch (y3_net_forward_pitched): a chunk is a whole number of pixels
+                if (pix_pitch[s] < 3 * F || pix_pitch[s] % 4 != 0) return fail(Y3_ERR_INVALID, "pixel pitch must be >= 3*(5+C) and a multiple of 4");
+                a.pitch[s] = pix_pitch[s];
+                a.recs[s] = y3::kDecodeRecs / 3 * 3;
+                max_pitch = std::max(max_pitch, pix_pitch[s]);
+            }
             a.in[s] = grids[s];
             a.gh[s] = gh[s]; a.gw[s] = gw[s];
             a.rec_off[s] = off;
             const long long recs = (long long)B * gh[s] * gw[s] * 3;
             off += gh[s] * gw[s] * 3;
-            chunks += (int)((recs + y3::kDecodeRecs - 1) / y3::kDecodeRecs);
+            chunks += (int)((recs + a.recs[s] - 1) / a.recs[s]);
         } else {
             a.in[s] = nullptr; a.gh[s] = 1; a.gw[s] = 1; a.rec_off[s] = off;
         }
@@ -1399,8 +1462,8 @@ int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* 
     if ((long long)B * off > 0x7fffffffLL) return fail(Y3_ERR_UNSUPPORTED, "B*N exceeds int32 record indexing");
     a.bboxes = bboxes; a.conf = conf; a.probs = probs; a.scores = scores;
     a.cls = reinterpret_cast<long long*>(class_idx);
-    const int F = 5 + nclasses;
-    const size_t smem = (size_t)((y3::kDecodeRecs * F + 3) & ~3) * 4 + y3::kDecodeRecs * 4;
+    a.stage_bytes = (((y3::kDecodeRecs / 3 + 1) * max_pitch + 3) & ~3) * 4;
+    const size_t smem = (size_t)a.stage_bytes + y3::kDecodeRecs * 4;
     if (smem > 200 * 1024) return fail(Y3_ERR_UNSUPPORTED, "nclasses too large for the decode tile");
     static size_t configured = 48 * 1024;
     if (smem > configured) {

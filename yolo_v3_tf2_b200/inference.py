@@ -81,12 +81,14 @@ class Detector:
         return det
 
     def detect(self, x):
-        grids = self.model(x)
         if self.fused:
+            # pitched head outputs (pixel pitch rounded up to 4 floats): TMA-store epilogue in the head convs
+            grids = self.model(x, padded=True)
             bboxes, conf, probs, scores, cls = yolo_decode(grids, self.anchors, self.nclasses, with_scores=True)
             sel, nvalid, status = nms_padded(bboxes, scores, self.max_boxes, self.iou_thr, self.score_thr)
             self.last_status = status
             return bboxes, cls, scores, sel, nvalid
+        grids = self.model(x)
         decoded = yolo_decode(grids, self.anchors, self.nclasses)
         return self.nms_layer(decoded)
 
@@ -98,3 +100,29 @@ class Detector:
         bboxes, cls, scores, sel, nvalid = self.detect(x)
         ob, oc, os_ = gather_detections_batched(bboxes, cls, scores, sel, nvalid)
         return ob, oc, os_, nvalid
+
+    def detections_graphed(self, x):
+        """``detections`` replayed from a CUDA graph: the ~80 launches of a step (75 convs with their programmatic
+        dependencies, decode, NMS, gather) are captured once per input shape and then cost one launch, which takes the
+        host out of the loop.  ``x`` is copied into the graph's static input; the returned tensors are the graph's
+        static outputs (overwritten by the next call)."""
+        key = (tuple(x.shape), x.device.index)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        ent = graphs.get(key)
+        if ent is None:
+            static_x = torch.empty_like(x, dtype=torch.float32).contiguous()
+            static_x.copy_(x)
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):            # warm-up outside the capture: lazy function attributes, arenas
+                for _ in range(2):
+                    self.detections(static_x)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = self.detections(static_x)
+            ent = graphs[key] = (g, static_x, outs)
+        g, static_x, outs = ent
+        static_x.copy_(x, non_blocking=True)
+        g.replay()
+        return outs
