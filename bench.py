@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--cpu-baseline-images", type=int, default=96,
                     help="images of the bounded CPU-baseline sample (about 10 s of host work, processed 8 at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true",
+                    help="profiling mode for runs under ncu: eager launches, no CUDA graphs, only W warm-up steps "
+                         "(numbers printed in this mode are not benchmark values)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,7 +225,7 @@ def main():
     sampler.start()
     # W untimed warm-up steps as asked, and never fewer than 20: a fresh process needs a few hundred milliseconds of load
     # before the SM clock has settled (short runs measured 10 % low in the first timed loop otherwise)
-    nwarm = max(args.warmup, 20)
+    nwarm = max(args.warmup, 3) if args.ncu else max(args.warmup, 20)
     t_w = time.perf_counter()
     for i in range(nwarm):
         step(xs[i % nbuf])
@@ -230,12 +233,12 @@ def main():
     # ... then about 2 s of steady load: the first CUDA process on a fresh box needs that long before its clocks settle
     # (the first nwarm steps mostly pay one-time initialisation, so the step time is taken from a second batch of 20)
     t_w = time.perf_counter()
-    for i in range(20):
+    for i in range(0 if args.ncu else 20):
         step(xs[i % nbuf])
     sync_all()
     dt_w = max(time.perf_counter() - t_w, 1e-3)
-    nwarm += 20
-    extra = min(2000, int(2.0 / dt_w) * 20)
+    nwarm += 0 if args.ncu else 20
+    extra = 0 if args.ncu else min(2000, int(2.0 / dt_w) * 20)
     if world > 1:   # every rank must issue the same number of collectives
         tw = torch.tensor([extra], dtype=torch.int64, device=dev)
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
@@ -248,7 +251,7 @@ def main():
     # replayed from a CUDA graph, so the number does not depend on how fast this box's host can issue launches (the
     # eager loop measured anything between 5.3 and 7.9 ms/step on different boxes for a 5.4 ms GPU step).
     def gstep(x):
-        local = det.detections_graphed(x)
+        local = det.detections(x) if args.ncu else det.detections_graphed(x)
         if world > 1 and not no_gather:
             y3dist.gather_detections(*local)
         return local
@@ -278,9 +281,16 @@ def main():
     with torch.cuda.stream(side):
         fouts = model(fx, padded=True)
     torch.cuda.current_stream().wait_stream(side)
-    fgraph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(fgraph):
-        model(fx, padded=True, outs=fouts)
+    class _Eager:
+        def replay(self):
+            model(fx, padded=True, outs=fouts)
+
+    if args.ncu:
+        fgraph = _Eager()
+    else:
+        fgraph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fgraph):
+            model(fx, padded=True, outs=fouts)
     for i in range(3):
         fgraph.replay()
     torch.cuda.synchronize()
@@ -327,7 +337,7 @@ def main():
                     ready[nxt].record(copy_stream)
             main_stream.wait_event(ready[cur])
             # the public serving call: the whole step replayed from a CUDA graph (one launch), then the NCCL gather
-            ob, oc, os_, nv = det.detections_graphed(xin[cur])
+            ob, oc, os_, nv = det.detections(xin[cur]) if args.ncu else det.detections_graphed(xin[cur])
             if world > 1 and not no_gather:
                 y3dist.gather_detections(ob, oc, os_, nv)
             free[cur].record(main_stream)

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     const int F = 5 + a.C;
     float* rec = reinterpret_cast<float*>(dsm);                         // staged records (pixel pitch as in memory)
     int* out_rec = reinterpret_cast<int*>(dsm + a.stage_bytes);         // [kDecodeRecs] global record index
+    int* rec_base = out_rec + kDecodeRecs;                               // [kDecodeRecs] float offset of the record in `rec`
     __shared__ __align__(8) uint64_t bar;
 
     int s = 0;
@@ -58,8 +59,16 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     const float* src = padded ? a.in[s] + (r0 / 3) * pitch : a.in[s] + r0 * F;
     const int nfl = padded ? (nrec / 3) * pitch : nrec * F;
     const uint32_t bulk_bytes = ((uint32_t)nfl * 4u) & ~15u;
-    // record t of the chunk inside the staging buffer
-    auto rec_at = [&](int t) { return padded ? rec + (t / 3) * pitch + (t % 3) * F : rec + t * F; };
+    // record t of the chunk inside the staging buffer (offsets are tabulated once: the probability loop below is bound
+    // by its instruction count, a division per element cost 50 % there)
+    // A pixel pitch that is a multiple of 32 floats would put record (pixel, anchor) of every pixel in the same three
+    // banks (11-way conflicts in the per-record phases: measured 135 vs 92 us); such pixels are staged 4 floats further apart.
+    const int spitch = (padded && (pitch & 31) == 0) ? pitch + 4 : pitch;
+    if ((int)threadIdx.x < kDecodeRecs) {
+        const int t = threadIdx.x;
+        rec_base[t] = padded ? (t / 3) * spitch + (t - (t / 3) * 3) * F : t * F;
+    }
+    auto rec_at = [&](int t) { return rec + rec_base[t]; };
 
     const uint32_t bar_s = smem_u32(&bar);
     if (threadIdx.x == 0) {
@@ -69,7 +78,12 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(bar_s, bulk_bytes);
-        if (bulk_bytes) bulk_load_1d(smem_u32(rec), src, bulk_bytes, bar_s);
+        if (spitch != pitch) {
+            for (int px = 0; px < nrec / 3; ++px)     // one copy per pixel (pitch * 4 bytes, a multiple of 16)
+                bulk_load_1d(smem_u32(rec + px * spitch), src + (long long)px * pitch, (uint32_t)pitch * 4u, bar_s);
+        } else if (bulk_bytes) {
+            bulk_load_1d(smem_u32(rec), src, bulk_bytes, bar_s);
+        }
     }
     // the (at most 3) floats past the last 16-byte multiple
     for (int i = (int)(bulk_bytes >> 2) + threadIdx.x; i < nfl; i += kDecodeThreads) rec[i] = src[i];

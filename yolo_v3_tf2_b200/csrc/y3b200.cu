@@ -1462,8 +1462,8 @@ static int decode_impl(y3_ctx* ctx, const float* const* grids, const int* gh, co
     if ((long long)B * off > 0x7fffffffLL) return fail(Y3_ERR_UNSUPPORTED, "B*N exceeds int32 record indexing");
     a.bboxes = bboxes; a.conf = conf; a.probs = probs; a.scores = scores;
     a.cls = reinterpret_cast<long long*>(class_idx);
-    a.stage_bytes = (((y3::kDecodeRecs / 3 + 1) * max_pitch + 3) & ~3) * 4;
-    const size_t smem = (size_t)a.stage_bytes + y3::kDecodeRecs * 4;
+    a.stage_bytes = (((y3::kDecodeRecs / 3 + 1) * (max_pitch + 4) + 3) & ~3) * 4;   // +4: bank-conflict padding of the staging pitch
+    const size_t smem = (size_t)a.stage_bytes + 2 * y3::kDecodeRecs * 4;
     if (smem > 200 * 1024) return fail(Y3_ERR_UNSUPPORTED, "nclasses too large for the decode tile");
     static size_t configured = 48 * 1024;
     if (smem > configured) {
