@@ -251,10 +251,16 @@ def main():
     # replayed from a CUDA graph, so the number does not depend on how fast this box's host can issue launches (the
     # eager loop measured anything between 5.3 and 7.9 ms/step on different boxes for a 5.4 ms GPU step).
     def gstep(x):
-        local = det.detections(x) if args.ncu else det.detections_graphed(x)
+        if args.ncu:
+            local = det.detections(x)
+            if world > 1 and not no_gather:
+                y3dist.gather_detections(*local)
+            return local
         if world > 1 and not no_gather:
-            y3dist.gather_detections(*local)
-        return local
+            local = det.detections_graphed(x, packed=True)     # records packed inside the graph
+            y3dist.gather_packed(local[4])                      # the only launch outside it: one NCCL all-gather
+            return local[:4]
+        return det.detections_graphed(x)
 
     for i in range(3):
         gstep(xs[i % nbuf])
@@ -337,11 +343,14 @@ def main():
                     ready[nxt].record(copy_stream)
             main_stream.wait_event(ready[cur])
             # the public serving call: the whole step replayed from a CUDA graph (one launch), then the NCCL gather
-            ob, oc, os_, nv = det.detections(xin[cur]) if args.ncu else det.detections_graphed(xin[cur])
+            if args.ncu:
+                ob, oc, os_, nv = det.detections(xin[cur])
+                rec = y3dist.pack_detections(ob, oc, os_, nv)
+            else:
+                rec = det.detections_graphed(xin[cur], packed=True)[4]
             if world > 1 and not no_gather:
-                y3dist.gather_detections(ob, oc, os_, nv)
+                y3dist.gather_packed(rec)
             free[cur].record(main_stream)
-            rec = y3dist.pack_detections(ob, oc, os_, nv)
             out_host[cur].copy_(rec, non_blocking=True)
         torch.cuda.synchronize()
 

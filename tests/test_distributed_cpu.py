@@ -37,6 +37,10 @@ def _worker(rank, world, port, global_batch, q):
     out = y3dist.gather_detections(*_fake_detections(lo, hi))
     ref = _fake_detections(0, global_batch)
     ok = all(torch.equal(a, b) for a, b in zip(out, ref))
+    # the packed variant (what the graphed serving step sends): one collective on pre-packed records
+    rec = y3dist.pack_detections(*_fake_detections(lo, hi))
+    out2 = y3dist.unpack_detections(y3dist.gather_packed(rec))
+    ok = ok and all(torch.equal(a, b) for a, b in zip(out2, ref))
     q.put((rank, lo, hi, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
@@ -68,3 +72,5 @@ def test_shard_range_and_pack_roundtrip():
     # single process: gather is the identity
     same = y3dist.gather_detections(*d)
     assert all(x is y for x, y in zip(same, d))
+    rec = y3dist.pack_detections(*d)
+    assert y3dist.gather_packed(rec) is rec

@@ -33,6 +33,18 @@ def unpack_detections(rec):
     return r[..., 0:4], r[..., 5].to(torch.int64), r[..., 4], rec[:, mx * 6].to(torch.int32)
 
 
+def gather_packed(rec, group=None):
+    """All-gather of already packed detection records ``[B, max*6 + 1]`` (``Detector.detections_graphed(x, packed=True)``):
+    one collective, no other launches; ``unpack_detections`` of the result is views plus two small casts.
+    Single-process: returns ``rec``."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rec
+    world = dist.get_world_size(group)
+    out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    return out
+
+
 def gather_detections(boxes, classes, scores, num_valid, group=None):
     """All ranks end up with the detections of the whole global batch, ordered by global image index (rank-major,
     which is image order for ``shard_range`` shards).  Single-process: returns the inputs."""

@@ -101,12 +101,14 @@ class Detector:
         ob, oc, os_ = gather_detections_batched(bboxes, cls, scores, sel, nvalid)
         return ob, oc, os_, nvalid
 
-    def detections_graphed(self, x):
+    def detections_graphed(self, x, packed=False):
         """``detections`` replayed from a CUDA graph: the ~80 launches of a step (75 convs with their programmatic
         dependencies, decode, NMS, gather) are captured once per input shape and then cost one launch, which takes the
         host out of the loop.  ``x`` is copied into the graph's static input; the returned tensors are the graph's
-        static outputs (overwritten by the next call)."""
-        key = (tuple(x.shape), x.device.index)
+        static outputs (overwritten by the next call).  ``packed=True`` appends the packed record tensor
+        ``[B, max*6 + 1]`` of ``distributed.pack_detections`` (built inside the graph), which is what the multi-GPU gather
+        sends."""
+        key = (tuple(x.shape), x.device.index, bool(packed))
         graphs = self.__dict__.setdefault("_graphs", {})
         ent = graphs.get(key)
         if ent is None:
@@ -121,6 +123,9 @@ class Detector:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 outs = self.detections(static_x)
+                if packed:
+                    from .distributed import pack_detections
+                    outs = tuple(outs) + (pack_detections(*outs),)
             ent = graphs[key] = (g, static_x, outs)
         g, static_x, outs = ent
         static_x.copy_(x, non_blocking=True)
