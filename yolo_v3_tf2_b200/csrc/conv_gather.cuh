@@ -174,7 +174,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         } else {
             for (int j = eg; j < my_tiles; j += NEPI) {
                 const int acc = j & 1;
-                const int tile = blockIdx.x + j * gridDim.x;
+                const int tile = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles);
                 mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -193,7 +193,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             // flight while the current one is converted and stored
             const float* src = reinterpret_cast<const float*>(p.src);
             auto load27 = [&](int j, float (&v)[27]) {
-                const int m = (blockIdx.x + j * gridDim.x) * kBlockM + row;
+                const int m = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + row;
                 const bool valid = (j < my_tiles) && (m < p.M);
                 const int n = m / hw;
                 const int rem = m - n * hw;
@@ -252,7 +252,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < my_tiles; ++j) {
-                const int m = (blockIdx.x + j * gridDim.x) * kBlockM + row;
+                const int m = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + row;
                 const bool valid = m < p.M;
                 const int n = m / hw;
                 const int rem = m - n * hw;

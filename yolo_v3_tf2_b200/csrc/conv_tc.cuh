@@ -59,6 +59,9 @@ struct ConvArgs {
     const void* src;       // bf16 NHWC view, or the fp32 [B,H,W,3] image for the stem
     long long src_stride;  // elements between consecutive input pixels
     int H, W;              // input spatial size
+    int rev;               // 1: walk the output tiles from the last to the first.  The planner alternates the direction from
+                           //    layer to layer so that a layer starts on the pixels its predecessor wrote LAST, which are
+                           //    still in L2 (each 52x52 tensor is 88 MB of a 126 MB L2)
     int stages;            // weights-resident kernels only: A-operand pipeline depth (what fits next to the weights)
     int tma_out;           // 0: register-transpose epilogue; 32 / 64: bf16 dense output written with TMA stores in chunks
                            //    of that many columns (epilogue_role_tma); tmO (and tmR when a residual is fused) are
@@ -67,6 +70,9 @@ struct ConvArgs {
     int dbg;               // profiling knobs (env Y3_DBG): 1 epilogue drains TMEM only, 2 no global stores,
                            // 4 producer skips the A loads, 8 no MMAs are issued (results are garbage)
 };
+
+// position in a CTA's tile sequence -> tile id (see ConvArgs::rev)
+__device__ __forceinline__ int tile_id(const ConvArgs& p, int seq, int num_tiles) { return p.rev ? num_tiles - 1 - seq : seq; }
 
 constexpr int kConvEpiGroups = 2;   // epilogue warp groups; group g drains accumulator stage g (tiles j % 2 == g)
 constexpr int kConvThreads = 32 * (4 + 4 * kConvEpiGroups);
@@ -272,7 +278,8 @@ struct EpiCursor {     // walks (tile, chunk) in processing order
     __device__ __forceinline__ void load(const ConvArgs& p, const EpiTiles& et, int block_n, int q) {
         valid = tile < et.end;
         if (!valid) return;
-        const int tmg = tile / et.tiles_n, tn = tile - tmg * et.tiles_n;
+        const int tid_ = tile_id(p, tile, et.end);
+        const int tmg = tid_ / et.tiles_n, tn = tid_ - tmg * et.tiles_n;
         const int tm = tmg * et.cl + et.cta_rank;
         const int n_base = tn * block_n;
         nch = min(block_n / CW, (p.cout - n_base + CW - 1) / CW);
@@ -535,7 +542,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (BRES) {
         // the weights do not depend on the previous layer: fetch the tile before waiting for it
         if (warp == 0 && elect_one()) {
-            const int n0 = (first_tile % p.tiles_n) * BLOCK_N;   // constant for this CTA (host-enforced)
+            const int n0 = (tile_id(p, first_tile, num_tiles) % p.tiles_n) * BLOCK_N;   // constant for this CTA (host-enforced)
             mbar_arrive_expect_tx(bfull_bar, (uint32_t)(p.num_k_blocks * S::B_BYTES));
             for (int kb = 0; kb < p.num_k_blocks; ++kb)
                 tma_load_2d(smem_b + kb * S::B_BYTES, &tmB, bfull_bar, kb * BLOCK_K, n0);
@@ -567,7 +574,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         };
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-            const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
+            const int tid_ = tile_id(p, tile, num_tiles);
+            const int tmg = tid_ / p.tiles_n, tn = tid_ - tmg * p.tiles_n;
             const int tm = tmg * CLUSTER + cta_rank;
             const int m0 = tm * kBlockM;
             const int n0 = tn * BLOCK_N;
@@ -671,7 +679,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
                 if ((j % kConvEpiGroups) != eg) continue;
                 const int acc = j & 1;
-                const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
+                const int tid_ = tile_id(p, tile, num_tiles);
+                const int tmg = tid_ / p.tiles_n, tn = tid_ - tmg * p.tiles_n;
                 const int tm = tmg * CLUSTER + cta_rank;
                 mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
                 tc_fence_after();

@@ -111,7 +111,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if constexpr (BRES) {
         // the weights do not depend on the previous layer: fetch this CTA's half of the tile before waiting for it
         if (warp == 0 && elect_one()) {
-            const int tn = first_tile % p.tiles_n;   // constant for this cluster (host-enforced)
+            const int tn = tile_id(p, first_tile, num_tiles) % p.tiles_n;   // constant for this cluster (host-enforced)
             const int nb = tn * BLOCK_N + cta_rank * (BLOCK_N / 2);
             const uint32_t lead_bfull = mapa_shared(bfull_bar, 0);
             if (is_leader) mbar_arrive_expect_tx(bfull_bar, (uint32_t)(2 * p.num_k_blocks * S::B_BYTES));
@@ -133,7 +133,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t phase = 0;
         const int hw = p.Ho * p.Wo;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-            const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
+            const int tid_ = tile_id(p, tile, num_tiles);
+            const int tmg = tid_ / p.tiles_n, tn = tid_ - tmg * p.tiles_n;
             const int tm = tmg * 2 + cta_rank;
             const int m0 = tm * kBlockM;
             const int nb = tn * BLOCK_N + cta_rank * (BLOCK_N / 2);   // this CTA's half of the weight rows
@@ -256,7 +257,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++j) {
                 if ((j % kConvEpiGroups) != eg) continue;
                 const int acc = j & 1;
-                const int tmg = tile / p.tiles_n, tn = tile - tmg * p.tiles_n;
+                const int tid_ = tile_id(p, tile, num_tiles);
+                const int tmg = tid_ / p.tiles_n, tn = tid_ - tmg * p.tiles_n;
                 const int tm = tmg * 2 + cta_rank;
                 mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
                 tc_fence_after();

@@ -516,6 +516,7 @@ struct Step {
     int out_padded = 0;    // output stored haloed-flat
     int patch_boxes = 0, box_rows = 0, pst = 0, bst = 0;
     int tma_out = 0;       // epilogue writes through tmO (and reads the residual through tmR)
+    int rev = 0;           // walk the output tiles backwards (alternates from conv to conv, see ConvArgs::rev)
     CUtensorMap tmA, tmB, tmO, tmR;
 };
 
@@ -858,6 +859,9 @@ int plan_net(y3_net& n) {
                 w.direct = true;
                 w.cout_pad = d.filters;
             }
+            // alternate the tile direction from conv to conv (Y3_REV=0 disables): the next layer starts where this one ended
+            static const bool use_rev = []() { const char* e = getenv("Y3_REV"); return !(e && e[0] == '0'); }();
+            s.rev = (use_rev && s.kind == 1 && !s.flat) ? (s.conv_idx & 1) : 0;
             pl.kernel = s.kind;
             pl.fused_add = residual[i];
             pl.fused_upsample = fused_up[i];
@@ -1049,6 +1053,7 @@ y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
     static const int dbg = []() { const char* e = getenv("Y3_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = dbg;
     a.ts = g_ts_ptr;
+    a.rev = s.rev;
     return a;
 }
 
