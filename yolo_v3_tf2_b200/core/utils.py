@@ -29,6 +29,28 @@ def _aspect_size(h, w, target_height, target_width):
     return int(np.round(np.float32(h) * sc)), int(np.round(np.float32(w) * sc))
 
 
+_DESC_RING = {}
+
+
+def _descriptor_upload(rows, dev, slots=8):
+    """Image descriptors -> device without a blocking pageable copy: a small ring of pinned host buffers per device, each
+    guarded by an event so that a slot is not rewritten while its previous upload is still in flight."""
+    import torch
+    ring = _DESC_RING.setdefault(dev.index, {"i": 0, "bufs": [None] * slots, "events": [None] * slots})
+    i = ring["i"] = (ring["i"] + 1) % slots
+    n = len(rows)
+    if ring["bufs"][i] is None or ring["bufs"][i].shape[0] < n:
+        ring["bufs"][i] = torch.empty((max(n, 64), 8), dtype=torch.int64).pin_memory()
+        ring["events"][i] = torch.cuda.Event()
+    else:
+        ring["events"][i].synchronize()
+    host = ring["bufs"][i][:n]
+    host.numpy()[:] = np.asarray(rows, dtype=np.int64)
+    desc = host.to(dev, non_blocking=True)
+    ring["events"][i].record(torch.cuda.current_stream())
+    return desc
+
+
 def preprocess_images(images, target_height, target_width, preserve_aspect_ratio=False, divide_by_255=False, out=None):
     """Resize a list of [H, W, 3] images (torch CUDA tensors, uint8 or float32; numpy arrays are copied to the GPU) to
     one float32 batch [B, target_height, target_width, 3] with ONE kernel launch.
@@ -57,7 +79,7 @@ def preprocess_images(images, target_height, target_width, preserve_aspect_ratio
             oh, ow, oy, ox = target_height, target_width, 0, 0
         rows.append([img.data_ptr(), h, w, 0 if img.dtype == torch.uint8 else 1, oh, ow, oy, ox])
     B = len(keep)
-    desc = torch.tensor(rows, dtype=torch.int64).to(dev)
+    desc = _descriptor_upload(rows, dev)
     if out is None:
         out = torch.empty((B, target_height, target_width, 3), dtype=torch.float32, device=dev)
     _lib.check(_lib.lib().y3_preprocess(ctx.handle, _lib.ptr(desc), B, int(target_height), int(target_width),
