@@ -152,8 +152,9 @@ int y3_evaluate(y3_ctx* ctx, const float* det_boxes, const int64_t* det_classes,
 /* Input pre-processing (reference inference.py:157-158, core/load_tfrecords.py:46, core/utils.py:17-28): for each of B
  * images, tf.image.resize-compatible bilinear resampling (half-pixel centres, no antialias) of a uint8 / float32
  * [H, W, 3] device image to out_h x out_w, placed at (off_y, off_x) of a zero-filled dst_h x dst_w canvas
- * (pad_to_bounding_box), optionally divided by 255.  image_descs_dev: device array of B records of 8 int64
- * {src pointer, H, W, dtype (0 uint8, 1 float32), out_h, out_w, off_y, off_x}.  out: [B, dst_h, dst_w, 3] float32. */
+ * (pad_to_bounding_box), optionally divided by 255.  image_descs_dev: device array of B records of 10 int64
+ * {src pointer, H, W, dtype (0 uint8, 1 float32), out_h, out_w, off_y, off_x, bits of float32(H)/float32(out_h),
+ * bits of float32(W)/float32(out_w)}.  out: [B, dst_h, dst_w, 3] float32. */
 int y3_preprocess(y3_ctx* ctx, const void* image_descs_dev, int B, int dst_h, int dst_w, int divide_by_255, float* out,
                   void* stream);
 

@@ -40,7 +40,8 @@ for (h, w) in [(480, 640), (1080, 1920)]:
     ms = timeit(lambda: y3.preprocess_images(frames, 416, 416, preserve_aspect_ratio=True, out=out))
     rows.append((f"resize_image (aspect + pad) {B} x {h}x{w} -> 416x416", ms * 1e3, byt / ms / 1e6, f"{B / ms * 1e3:.0f} img/s"))
     # the kernel alone (descriptors prebuilt on the device): what the HBM roofline applies to
-    desc = torch.tensor([[f.data_ptr(), h, w, 0, 416, 416, 0, 0] for f in frames], dtype=torch.int64).cuda()
+    sy, sx = int((np.float32(h) / np.float32(416)).view(np.int32)), int((np.float32(w) / np.float32(416)).view(np.int32))
+    desc = torch.tensor([[f.data_ptr(), h, w, 0, 416, 416, 0, 0, sy, sx] for f in frames], dtype=torch.int64).cuda()
     ctx = _lib.context()
     ms = timeit(lambda: _lib.check(_lib.lib().y3_preprocess(ctx.handle, _lib.ptr(desc), B, 416, 416, 1, _lib.ptr(out), _lib.stream_ptr())))
     rows.append((f"  ... preprocess_kernel alone", ms * 1e3, byt / ms / 1e6, ""))

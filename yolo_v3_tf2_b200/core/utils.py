@@ -40,7 +40,7 @@ def _descriptor_upload(rows, dev, slots=8):
     i = ring["i"] = (ring["i"] + 1) % slots
     n = len(rows)
     if ring["bufs"][i] is None or ring["bufs"][i].shape[0] < n:
-        ring["bufs"][i] = torch.empty((max(n, 64), 8), dtype=torch.int64).pin_memory()
+        ring["bufs"][i] = torch.empty((max(n, 64), 10), dtype=torch.int64).pin_memory()
         ring["events"][i] = torch.cuda.Event()
     else:
         ring["events"][i].synchronize()
@@ -77,8 +77,12 @@ def preprocess_images(images, target_height, target_width, preserve_aspect_ratio
             oy, ox = (target_height - oh) // 2, (target_width - ow) // 2
         else:
             oh, ow, oy, ox = target_height, target_width, 0, 0
-        rows.append([img.data_ptr(), h, w, 0 if img.dtype == torch.uint8 else 1, oh, ow, oy, ox])
+        rows.append([img.data_ptr(), h, w, 0 if img.dtype == torch.uint8 else 1, oh, ow, oy, ox, 0, 0])
     B = len(keep)
+    rows = np.asarray(rows, dtype=np.int64)
+    # the scale factors of ResizeBilinear, float32 in / float32 out, passed as bit patterns
+    rows[:, 8] = (rows[:, 1].astype(np.float32) / rows[:, 4].astype(np.float32)).view(np.int32)
+    rows[:, 9] = (rows[:, 2].astype(np.float32) / rows[:, 5].astype(np.float32)).view(np.int32)
     desc = _descriptor_upload(rows, dev)
     if out is None:
         out = torch.empty((B, target_height, target_width, 3), dtype=torch.float32, device=dev)

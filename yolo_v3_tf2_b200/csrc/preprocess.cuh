@@ -13,12 +13,13 @@
 
 namespace y3 {
 
-struct ImageDesc {          // one per image, device memory (8 x int64)
+struct ImageDesc {          // one per image, device memory (10 x int64)
     long long src;          // device pointer: uint8 or float32 [H, W, 3]
     long long H, W;
     long long dtype;        // 0 uint8, 1 float32
     long long out_h, out_w; // resized size (== canvas size without aspect preservation)
     long long off_y, off_x; // top-left corner inside the canvas (pad_to_bounding_box)
+    long long scale_y, scale_x;   // float32 bit patterns of H / out_h and W / out_w (IEEE division done once on the host)
 };
 
 struct PreprocessArgs {
@@ -34,38 +35,59 @@ __device__ __forceinline__ float load_px(const ImageDesc& d, long long idx) {
     return reinterpret_cast<const float*>(d.src)[idx];
 }
 
-__global__ void preprocess_kernel(const PreprocessArgs a) {
-    const long long per = (long long)a.dst_h * a.dst_w;
-    const long long total = per * a.B;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(e / per);
-        const int rem = (int)(e - (long long)b * per);
-        const int y = rem / a.dst_w, x = rem - y * a.dst_w;
-        const ImageDesc d = a.desc[b];
-        float r[3] = {0.f, 0.f, 0.f};
-        const int yy = y - (int)d.off_y, xx = x - (int)d.off_x;
-        if (yy >= 0 && yy < d.out_h && xx >= 0 && xx < d.out_w) {
-            const float sy = __fdiv_rn((float)d.H, (float)d.out_h), sx = __fdiv_rn((float)d.W, (float)d.out_w);
-            const float fy = __fsub_rn(__fmul_rn(__fadd_rn((float)yy, 0.5f), sy), 0.5f);
-            const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)xx, 0.5f), sx), 0.5f);
-            const float fly = floorf(fy), flx = floorf(fx);
-            const long long y0 = max((long long)fly, 0LL), y1 = min((long long)ceilf(fy), d.H - 1);
-            const long long x0 = max((long long)flx, 0LL), x1 = min((long long)ceilf(fx), d.W - 1);
-            const float ly = __fsub_rn(fy, fly), lx = __fsub_rn(fx, flx);
+// grid = (ceil(dst_h * dst_w / 256), B): blockIdx.y is the image, so no 64-bit division per pixel; the image's
+// descriptor is read once per block into shared memory.
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessArgs a) {
+    __shared__ ImageDesc sd;
+    const int b = blockIdx.y;
+    if (threadIdx.x < (int)(sizeof(ImageDesc) / 8))
+        reinterpret_cast<long long*>(&sd)[threadIdx.x] = reinterpret_cast<const long long*>(a.desc + b)[threadIdx.x];
+    __syncthreads();
+    const int per = a.dst_h * a.dst_w;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= per) return;
+    const int y = idx / a.dst_w, x = idx - y * a.dst_w;
+    const int H = (int)sd.H, W = (int)sd.W, out_h = (int)sd.out_h, out_w = (int)sd.out_w;
+    float r[3] = {0.f, 0.f, 0.f};
+    const int yy = y - (int)sd.off_y, xx = x - (int)sd.off_x;
+    if (yy >= 0 && yy < out_h && xx >= 0 && xx < out_w) {
+        const float sy = __int_as_float((int)sd.scale_y), sx = __int_as_float((int)sd.scale_x);
+        const float fy = __fsub_rn(__fmul_rn(__fadd_rn((float)yy, 0.5f), sy), 0.5f);
+        const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)xx, 0.5f), sx), 0.5f);
+        const float fly = floorf(fy), flx = floorf(fx);
+        const int y0 = max((int)fly, 0), y1 = min((int)ceilf(fy), H - 1);
+        const int x0 = max((int)flx, 0), x1 = min((int)ceilf(fx), W - 1);
+        const float ly = __fsub_rn(fy, fly), lx = __fsub_rn(fx, flx);
+        const long long r0 = (long long)y0 * W, r1 = (long long)y1 * W;
+        float tl[3], tr[3], bl[3], br[3];
+        if (sd.dtype == 0) {
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(sd.src);
+            const uint8_t *ptl = p + (r0 + x0) * 3, *ptr_ = p + (r0 + x1) * 3, *pbl = p + (r1 + x0) * 3, *pbr = p + (r1 + x1) * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float tl = load_px(d, (y0 * d.W + x0) * 3 + c), tr = load_px(d, (y0 * d.W + x1) * 3 + c);
-                const float bl = load_px(d, (y1 * d.W + x0) * 3 + c), br = load_px(d, (y1 * d.W + x1) * 3 + c);
-                const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
-                const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
-                float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
-                if (a.use_mul) v = __fdiv_rn(v, 255.0f);   // the reference divides: resize(...) / 255
-                r[c] = v;
+                tl[c] = (float)__ldg(ptl + c); tr[c] = (float)__ldg(ptr_ + c);
+                bl[c] = (float)__ldg(pbl + c); br[c] = (float)__ldg(pbr + c);
+            }
+        } else {
+            const float* p = reinterpret_cast<const float*>(sd.src);
+            const float *ptl = p + (r0 + x0) * 3, *ptr_ = p + (r0 + x1) * 3, *pbl = p + (r1 + x0) * 3, *pbr = p + (r1 + x1) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                tl[c] = __ldg(ptl + c); tr[c] = __ldg(ptr_ + c);
+                bl[c] = __ldg(pbl + c); br[c] = __ldg(pbr + c);
             }
         }
-        float* o = a.out + e * 3;
-        o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float top = __fadd_rn(tl[c], __fmul_rn(__fsub_rn(tr[c], tl[c]), lx));
+            const float bot = __fadd_rn(bl[c], __fmul_rn(__fsub_rn(br[c], bl[c]), lx));
+            float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+            if (a.use_mul) v = __fdiv_rn(v, 255.0f);   // the reference divides: resize(...) / 255
+            r[c] = v;
+        }
     }
+    float* o = a.out + ((long long)b * per + idx) * 3;
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
 }
 
 }  // namespace y3

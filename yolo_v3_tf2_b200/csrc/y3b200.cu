@@ -1549,7 +1549,8 @@ int y3_preprocess(y3_ctx* ctx, const void* image_descs_dev, int B, int dst_h, in
     a.B = B; a.dst_h = dst_h; a.dst_w = dst_w;
     a.use_mul = divide_by_255 ? 1 : 0;
     a.mul = 1.0f;
-    const unsigned grid = grid_for((long long)B * dst_h * dst_w, 256, ctx->sms);
+    if (B > 65535) return fail(Y3_ERR_UNSUPPORTED, "more than 65535 images per call");
+    const dim3 grid((unsigned)(((long long)dst_h * dst_w + 255) / 256), (unsigned)B);
     y3::preprocess_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     Y3_CUDA(cudaGetLastError());
     return Y3_OK;
