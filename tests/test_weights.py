@@ -124,3 +124,29 @@ def test_tf_checkpoint_format_details(tmp_path):
     open(str(tmp_path / "bad2.index"), "wb").write(bytes(bad))
     with pytest.raises(ValueError, match="magic"):
         tc.read_index(str(tmp_path / "bad2.index"))
+
+
+def test_anchor_generation_roundtrip(tmp_path):
+    """utilities/create_yolov3_anchors.py mirror: k-means over (w, h), ascending area order, '%10.5f' file format that
+    get_anchors (core/utils.py:31-37) reads back as [n_scales, 3, 2]."""
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200.utilities import create_yolov3_anchors as ca
+    rng = np.random.default_rng(0)
+    centers = np.array([[0.05, 0.06], [0.1, 0.2], [0.2, 0.12], [0.3, 0.35], [0.5, 0.4], [0.7, 0.8]], np.float32)
+    wh = np.concatenate([c + rng.normal(0, 0.004, (200, 2)).astype(np.float32) for c in centers])
+    xy = rng.random((len(wh), 2)).astype(np.float32) * 0.1
+    labels = np.concatenate([xy, xy + wh, np.ones((len(wh), 1), np.float32)], axis=1)
+    labels = np.concatenate([labels, np.zeros((50, 5), np.float32)])          # zero padding rows are ignored
+    anchors = ca.creat_yolo_anchors(labels.reshape(-1, 10, 5), 6, random_state=0)
+    assert anchors.shape == (6, 2) and anchors.dtype == np.float32
+    areas = anchors[:, 0] * anchors[:, 1]
+    assert (np.diff(areas) > 0).all()
+    np.testing.assert_allclose(anchors, centers[np.argsort(centers[:, 0] * centers[:, 1])], atol=0.01)
+    path = str(tmp_path / "anchors" / "a.txt")
+    ca.save_anchors(path, anchors)
+    assert all(len(line.split(",")) == 2 for line in open(path).read().strip().splitlines())
+    back = y3.get_anchors(path)
+    assert back.shape == (2, 3, 2)
+    np.testing.assert_allclose(back.reshape(6, 2), anchors, atol=1e-5)
+    ca.save_anchors(path, anchors, descending=True)
+    np.testing.assert_allclose(y3.get_anchors(path).reshape(6, 2), anchors[::-1], atol=1e-5)
