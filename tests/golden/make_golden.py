@@ -67,8 +67,40 @@ def golden_net():
                             w74_sum=np.float64(m._params[74].kernel.astype(np.float64).sum()))
 
 
+def golden_next_rows():
+    """Small vectors for the 'next' rows: YOLOv3-tiny forward (maxpool), pre-processing, evaluation counters."""
+    from oracle import evaluate_oracle, preprocess_oracle
+    m = y3.ParseModel.builtin_yolov3_tiny(80).init_weights("variance", seed=11)
+    x = np.random.default_rng(7).random((1, 64, 64, 3), dtype=np.float32)
+    outs = net_oracle.forward(m.graph.layers, m.graph.outputs, m._params, x)
+    np.savez_compressed(os.path.join(HERE, "tiny64_variance.npz"), x=x, seed=np.int64(11), g0=outs[0], g1=outs[1])
+    rng = np.random.default_rng(9)
+    u8 = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    f32 = rng.random((48, 30, 3), dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "preprocess_small.npz"), u8=u8, f32=f32,
+                        u8_resized_div255=preprocess_oracle.resize(u8, 32, divide_by_255=True),
+                        f32_resized=preprocess_oracle.resize(f32, 40),
+                        u8_aspect=preprocess_oracle.resize_image(u8, 32, 48),
+                        f32_aspect=preprocess_oracle.resize_image(f32, 64, 64))
+    nclasses = 5
+    det = rng.random((6, 12, 2)).astype(np.float32)
+    det = np.concatenate([det, det + rng.random((6, 12, 2)).astype(np.float32) * 0.3 + 0.05], -1)
+    gt = det[:, :8] + rng.normal(0, 0.02, (6, 8, 4)).astype(np.float32)
+    dcls = rng.integers(0, nclasses, (6, 12)).astype(np.int64)
+    gcls = np.where(rng.random((6, 8)) < 0.7, dcls[:, :8], rng.integers(0, nclasses, (6, 8))).astype(np.int32)
+    dn = rng.integers(0, 13, 6).astype(np.int32)
+    gn = rng.integers(0, 9, 6).astype(np.int32)
+    c = evaluate_oracle.new_counters(nclasses)
+    for b in range(6):
+        evaluate_oracle.evaluate(c, nclasses, 0.5, det[b, :dn[b]], dcls[b, :dn[b]], gt[b, :gn[b]], gcls[b, :gn[b]])
+    np.savez_compressed(os.path.join(HERE, "evaluate_small.npz"), det=det, dcls=dcls, dn=dn, gt=gt, gcls=gcls, gn=gn,
+                        nclasses=np.int64(nclasses), preds=c["preds"], gts=c["gts"], tp=c["tp"], fp=c["fp"], fn=c["fn"],
+                        examples=np.int64(c["examples"]))
+
+
 if __name__ == "__main__":
     golden_decode()
     golden_nms()
     golden_net()
+    golden_next_rows()
     print("golden vectors written to", HERE)

@@ -180,3 +180,28 @@ def test_preprocess_oracle_vs_torch_bilinear():
     out = po.resize_image(rng.random((50, 100, 3), dtype=np.float32), 64, 64)
     assert out.shape == (64, 64, 3) and po.aspect_size(50, 100, 64, 64) == (32, 64)
     assert (out[:16] == 0).all() and (out[48:] == 0).all() and (out[16:48] != 0).any()
+
+
+def test_next_rows_golden():
+    """The oracles of the 'next' rows against their committed vectors (tests/golden/make_golden.py: golden_next_rows)."""
+    import yolo_v3_tf2_b200 as y3
+    from oracle import evaluate_oracle, net_oracle, preprocess_oracle
+    z = np.load(os.path.join(GOLD, "tiny64_variance.npz"))
+    m = y3.ParseModel.builtin_yolov3_tiny(80).init_weights("variance", seed=int(z["seed"]))
+    outs = net_oracle.forward(m.graph.layers, m.graph.outputs, m._params, z["x"])
+    for o, k in zip(outs, ("g0", "g1")):
+        np.testing.assert_allclose(o, z[k], rtol=2e-4, atol=2e-4)
+    z = np.load(os.path.join(GOLD, "preprocess_small.npz"))
+    assert np.array_equal(preprocess_oracle.resize(z["u8"], 32, divide_by_255=True), z["u8_resized_div255"])
+    assert np.array_equal(preprocess_oracle.resize(z["f32"], 40), z["f32_resized"])
+    assert np.array_equal(preprocess_oracle.resize_image(z["u8"], 32, 48), z["u8_aspect"])
+    assert np.array_equal(preprocess_oracle.resize_image(z["f32"], 64, 64), z["f32_aspect"])
+    z = np.load(os.path.join(GOLD, "evaluate_small.npz"))
+    n = int(z["nclasses"])
+    c = evaluate_oracle.new_counters(n)
+    for b in range(len(z["dn"])):
+        evaluate_oracle.evaluate(c, n, 0.5, z["det"][b, :z["dn"][b]], z["dcls"][b, :z["dn"][b]], z["gt"][b, :z["gn"][b]],
+                                 z["gcls"][b, :z["gn"][b]])
+    for k in ("preds", "gts", "tp", "fp", "fn"):
+        assert np.array_equal(c[k], z[k]), k
+    assert c["examples"] == int(z["examples"])
