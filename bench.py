@@ -257,11 +257,12 @@ def main():
             if world > 1 and not no_gather:
                 y3dist.gather_detections(*local)
             return local
+        # static_input: the loop rotates over a fixed set of device input buffers, one graph per buffer reads it in place
         if world > 1 and not no_gather:
-            local = det.detections_graphed(x, packed=True)     # records packed inside the graph
+            local = det.detections_graphed(x, packed=True, static_input=True)   # records packed inside the graph
             y3dist.gather_packed(local[4])                      # the only launch outside it: one NCCL all-gather
             return local[:4]
-        return det.detections_graphed(x)
+        return det.detections_graphed(x, static_input=True)
 
     for i in range(3):
         gstep(xs[i % nbuf])
@@ -348,7 +349,7 @@ def main():
                 ob, oc, os_, nv = det.detections(xin[cur])
                 rec = y3dist.pack_detections(ob, oc, os_, nv)
             else:
-                rec = det.detections_graphed(xin[cur], packed=True)[4]
+                rec = det.detections_graphed(xin[cur], packed=True, static_input=True)[4]
             if world > 1 and not no_gather:
                 y3dist.gather_packed(rec)
             free[cur].record(main_stream)

@@ -156,6 +156,15 @@ def test_graphed_detections_equal_eager(cuda):
         torch.cuda.synchronize()
         for a, b in zip(eager, graphed):
             assert torch.equal(a, b)
+    # static_input: the graph reads the caller's buffer in place; refilling that buffer changes the next replay
+    buf = torch.rand((2, 96, 96, 3), device="cuda")
+    first = [t.clone() for t in det.detections_graphed(buf, static_input=True)]
+    for a, b in zip(first, det.detections(buf.clone())):
+        assert torch.equal(a, b)
+    buf.copy_(torch.rand((2, 96, 96, 3), device="cuda"))
+    second = det.detections_graphed(buf, static_input=True)
+    for a, b in zip(second, det.detections(buf.clone())):
+        assert torch.equal(a, b)
 
 
 def test_reference_yaml_and_darknet_weights_roundtrip(cuda, tmp_path):

@@ -101,19 +101,24 @@ class Detector:
         ob, oc, os_ = gather_detections_batched(bboxes, cls, scores, sel, nvalid)
         return ob, oc, os_, nvalid
 
-    def detections_graphed(self, x, packed=False):
+    def detections_graphed(self, x, packed=False, static_input=False):
         """``detections`` replayed from a CUDA graph: the ~80 launches of a step (75 convs with their programmatic
         dependencies, decode, NMS, gather) are captured once per input shape and then cost one launch, which takes the
         host out of the loop.  ``x`` is copied into the graph's static input; the returned tensors are the graph's
         static outputs (overwritten by the next call).  ``packed=True`` appends the packed record tensor
         ``[B, max*6 + 1]`` of ``distributed.pack_detections`` (built inside the graph), which is what the multi-GPU gather
-        sends."""
-        key = (tuple(x.shape), x.device.index, bool(packed))
+        sends.  ``static_input=True``: the caller promises to reuse this very tensor (same memory) for later batches --
+        a serving loop that rotates a few device input buffers -- so the graph reads it in place and the copy into a
+        static input (133 MB per 64-image batch) is skipped; one graph is kept per such buffer."""
+        if static_input and not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise ValueError("static_input needs a contiguous float32 CUDA tensor")
+        key = (tuple(x.shape), x.device.index, bool(packed), x.data_ptr() if static_input else None)
         graphs = self.__dict__.setdefault("_graphs", {})
         ent = graphs.get(key)
         if ent is None:
-            static_x = torch.empty_like(x, dtype=torch.float32).contiguous()
-            static_x.copy_(x)
+            static_x = x if static_input else torch.empty_like(x, dtype=torch.float32).contiguous()
+            if not static_input:
+                static_x.copy_(x)
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):            # warm-up outside the capture: lazy function attributes, arenas
@@ -128,6 +133,7 @@ class Detector:
                     outs = tuple(outs) + (pack_detections(*outs),)
             ent = graphs[key] = (g, static_x, outs)
         g, static_x, outs = ent
-        static_x.copy_(x, non_blocking=True)
+        if not static_input:
+            static_x.copy_(x, non_blocking=True)
         g.replay()
         return outs
