@@ -52,20 +52,28 @@ def test_decode_accepts_numpy_and_checks_shapes(cuda):
         y3.yolo_decode(grids, _anchors(), 6)
 
 
-@pytest.mark.parametrize("C", [80, 38, 5])
-def test_class_reduce_vs_oracle(cuda, C):
+@pytest.mark.parametrize("C,N,misalign", [(80, 1000, 0), (38, 1000, 0), (5, 1001, 0), (81, 777, 0), (600, 131, 0),
+                                          (80, 333, 1), (20000, 7, 0)])
+def test_class_reduce_vs_oracle(cuda, C, N, misalign):
+    """staged kernel (C % 4 == 0 vector scan, even / odd scalar scans, partial last chunk with a ragged 16-byte tail,
+    wide class vectors) and the warp-per-record fallback (class_probs not 16-byte aligned, C too wide to stage)"""
     import torch
     import yolo_v3_tf2_b200 as y3
     from oracle import decode_oracle
     rng = np.random.default_rng(C)
-    B, N = 3, 1000
+    B = 3
     probs = rng.random((B, N, C)).astype(np.float32)
     probs[0, :50, :] = 0.25            # all-equal rows: first index must win
     probs[1, 5, C - 1] = probs[1, 5, 3] = 2.0   # duplicated max: lower index wins
+    probs[2, 6, 1:] = probs[2, 6, 0]   # maximum at index 0 tied with every later class
     conf = rng.random((B, N, 1)).astype(np.float32)
     boxes = np.zeros((B, N, 4), np.float32)
-    out = y3.yolo_nms((torch.from_numpy(boxes).cuda(), torch.from_numpy(conf).cuda(), torch.from_numpy(probs).cuda()),
-                      10, 0.5, 0.1)
+    pd = torch.from_numpy(probs).cuda()
+    if misalign:
+        flat = torch.empty(pd.numel() + 4, dtype=torch.float32, device="cuda")
+        pd = flat[misalign:misalign + pd.numel()].copy_(pd.reshape(-1)).view(B, N, C)
+        assert pd.data_ptr() % 16 != 0
+    out = y3.yolo_nms((torch.from_numpy(boxes).cuda(), torch.from_numpy(conf).cuda(), pd), 10, 0.5, 0.1)
     cls_ref, sc_ref = decode_oracle.class_reduce(conf, probs)
     assert out[1].dtype == torch.int64
     assert np.array_equal(out[1].cpu().numpy(), cls_ref)

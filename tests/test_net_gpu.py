@@ -21,7 +21,8 @@ def _compare(grids, ref, rel_tol=2e-2):
 
 
 @pytest.mark.parametrize("init,size,B,C", [("variance", 64, 2, 80), ("keras", 96, 1, 80), ("variance", 128, 3, 38),
-                                           ("variance", 416, 1, 80), ("variance", 96, 2, 37)])
+                                           ("variance", 416, 1, 80), ("variance", 96, 2, 37),
+                                           ("variance", 608, 1, 80), ("keras", 416, 1, 37)])
 def test_forward_vs_oracle(cuda, init, size, B, C):
     import torch
     import yolo_v3_tf2_b200 as y3
@@ -95,6 +96,32 @@ def test_forward_batch_invariance_and_rebatch(cuda):
     allb = model(x)
     for k in range(3):
         assert torch.equal(allb[k], torch.cat([o[k] for o in one], 0))
+
+
+@pytest.mark.parametrize("size,B,C", [(416, 64, 80), (608, 32, 80), (416, 128, 37)])
+def test_full_size_batches_are_image_independent(cuda, size, B, C):
+    """BASELINE.json configs 2 / 3 (the 8-GPU shard) / 5 at their full per-GPU sizes, where the CPU oracle would take
+    minutes: the size-independent property is that images are independent -- every probed row of the full batch is
+    bit-identical to the same image run alone (which test_forward_vs_oracle ties to the oracle at B = 1), through the
+    forward pass and through decode + NMS + gather."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    model = y3.ParseModel.builtin_yolov3(C).init_weights("variance", seed=17)
+    x = torch.rand((B, size, size, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(size + B))
+    det = y3.Detector(model, configs.coco_anchors(), C)
+    grids = [g.clone() for g in model(x)]
+    full = [t.clone() for t in det.detections(x)]
+    assert [tuple(g.shape) for g in grids] == [(B, size // s, size // s, 3, 5 + C) for s in (32, 16, 8)]
+    for i in (0, B // 2 - 1, B - 1):
+        one = model(x[i:i + 1].contiguous())
+        for k in range(3):
+            assert torch.equal(one[k][0], grids[k][i]), (i, k)
+        d1 = det.detections(x[i:i + 1].contiguous())
+        for a, b in zip(d1, full):
+            assert torch.equal(a[0], b[i]), i
+    from yolo_v3_tf2_b200 import _lib
+    assert _lib.context().watchdog_code() == 0
 
 
 @pytest.mark.parametrize("C", [80, 38, 3])

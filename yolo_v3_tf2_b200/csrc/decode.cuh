@@ -174,9 +174,69 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
 
 // ------------------------------------------------------------------------------------------------
 // Class reduce for the stand-alone yolo_nms entry point (reference core/yolo_nms.py:18-24):
-// class_idx = argmax_c probs (first max wins), score = conf * max_c probs.  One warp per record, coalesced.
+// class_idx = argmax_c probs (first max wins), score = conf * max_c probs.
+//
+// HBM-bound: N*C*4 bytes in per image, 12 bytes per record out.  Each CTA brings a contiguous run of `recs` records
+// into shared memory with ONE 1-D bulk copy (no register staging, several CTAs per SM keep ~200 KB in flight), then
+// one thread per record scans its C values out of shared memory.  The scan starts at a per-thread skewed class so the
+// 32 lanes of a warp (record stride C floats) hit different banks; ties keep the lowest class index whatever the order.
+// (The first version, one warp per record with a shuffle reduction, was bound by instruction issue: 0.28 of the copy
+// bandwidth; it is kept below for unaligned pointers and very large C.)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) class_reduce_kernel(const float* __restrict__ probs,
+constexpr int kReduceThreads = 128;
+
+__global__ void __launch_bounds__(kReduceThreads) class_reduce_kernel(const float* __restrict__ probs,
+                                                                      const float* __restrict__ conf, long long nrec,
+                                                                      int C, int recs, float* __restrict__ scores,
+                                                                      long long* __restrict__ cls) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    float* rec = reinterpret_cast<float*>(dsm);
+    __shared__ __align__(8) uint64_t bar;
+    const long long r0 = (long long)blockIdx.x * recs;
+    const int n = (int)min((long long)recs, nrec - r0);
+    const float* src = probs + r0 * C;          // 16-byte aligned: recs % 4 == 0 and the base is (host-checked)
+    const int nfl = n * C;
+    const uint32_t bulk_bytes = ((uint32_t)nfl * 4u) & ~15u;
+    const uint32_t bar_s = smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_s, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar_s, bulk_bytes);
+        if (bulk_bytes) bulk_load_1d(smem_u32(rec), src, bulk_bytes, bar_s);
+    }
+    for (int i = (int)(bulk_bytes >> 2) + threadIdx.x; i < nfl; i += kReduceThreads) rec[i] = src[i];
+    __syncthreads();                            // barrier init visible to the waiters, tail floats written
+    mbar_wait(bar_s, 0, 0x680);
+    for (int t = threadIdx.x; t < n; t += kReduceThreads) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        auto upd = [&](float v, int c) {
+            if (v > best || (v == best && c < bi)) { best = v; bi = c; }
+        };
+        if ((C & 3) == 0) {
+            const float4* r4 = reinterpret_cast<const float4*>(rec + (size_t)t * C);
+            const int n4 = C >> 2;
+            int j = t % n4;
+            for (int i = 0; i < n4; ++i) {
+                const float4 v = r4[j];
+                upd(v.x, 4 * j); upd(v.y, 4 * j + 1); upd(v.z, 4 * j + 2); upd(v.w, 4 * j + 3);
+                if (++j == n4) j = 0;
+            }
+        } else {
+            const float* r = rec + (size_t)t * C;
+            int j = (C & 1) ? 0 : t % C;        // odd C: the record stride is already conflict-free
+            for (int i = 0; i < C; ++i) {
+                upd(r[j], j);
+                if (++j == C) j = 0;
+            }
+        }
+        scores[r0 + t] = __fmul_rn(__ldg(conf + r0 + t), best);
+        cls[r0 + t] = (long long)(bi == 0x7fffffff ? 0 : bi);
+    }
+}
+
+// fallback: one warp per record, coalesced scalar loads, shuffle reduction
+__global__ void __launch_bounds__(256) class_reduce_warp_kernel(const float* __restrict__ probs,
                                                            const float* __restrict__ conf, long long nrec, int C,
                                                            float* __restrict__ scores, long long* __restrict__ cls) {
     const int lane = threadIdx.x & 31;

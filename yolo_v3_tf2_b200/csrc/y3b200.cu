@@ -1487,9 +1487,26 @@ int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, i
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (B <= 0 || N <= 0 || nclasses <= 0) return fail(Y3_ERR_INVALID, "bad shape");
     const long long nrec = (long long)B * N;
-    const unsigned grid = grid_for(nrec * 32, 256, ctx->sms);
-    y3::class_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        probs, conf, nrec, nclasses, scores, reinterpret_cast<long long*>(class_idx));
+    // records per CTA: 128 (one per thread) while they fit in 64 KB of shared memory, fewer (a multiple of 4, so every
+    // chunk starts 16-byte aligned) for wide class vectors
+    const long long rec_bytes = (long long)nclasses * 4;
+    int recs = y3::kReduceThreads;
+    if (recs * rec_bytes > 64 * 1024) recs = (int)((64 * 1024 / rec_bytes) & ~3LL);
+    const long long ctas = recs > 0 ? (nrec + recs - 1) / recs : 0;
+    if (recs >= 4 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0 && ctas <= 0x7fffffffLL) {
+        const size_t smem = (size_t)(recs * rec_bytes);
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            Y3_CUDA(cudaFuncSetAttribute(y3::class_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        y3::class_reduce_kernel<<<(unsigned)ctas, y3::kReduceThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+            probs, conf, nrec, nclasses, recs, scores, reinterpret_cast<long long*>(class_idx));
+    } else {
+        const unsigned grid = grid_for(nrec * 32, 256, ctx->sms);
+        y3::class_reduce_warp_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            probs, conf, nrec, nclasses, scores, reinterpret_cast<long long*>(class_idx));
+    }
     Y3_CUDA(cudaGetLastError());
     return Y3_OK;
 }
