@@ -5,9 +5,11 @@
 //     fp32 image loses no precision); the weights are duplicated for both halves.
 //   * 3x3 convs with Cin == 32 (64-byte rows): one K block per filter tap.
 // Same tcgen05/TMEM pipeline and the same epilogue as conv_tc_kernel; only the producer differs:
-//   warps 8-11 (128 threads, one output pixel each) load the tap's channels with 16-byte loads (or 27 scalar loads for
-//   the stem), write them into the swizzled K-major tile the UMMA descriptor expects, fence the async proxy and
-//   arrive on the stage's mbarrier.  Warp 0 loads all K blocks of the weights once with TMA.
+//   the producer warps (128 threads per group) build the swizzled K-major tile the UMMA descriptor expects -- the stem
+//   with 27 scalar loads per output pixel, the Cin == 32 layers with 16-byte cp.async (4 lanes per 64-byte row) --
+//   fence the async proxy and arrive on the stage's mbarrier.  Warp 0 loads all K blocks of the weights once with TMA.
+// The Cin == 32 path is opt-in (Y3_GATHER_CIN32=1): measured 0.45 ms (one producer group) / 0.38 ms (two) per layer
+// against 0.27 ms for the TMA im2col kernel, so the planner keeps TMA for those layers.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -48,16 +50,15 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BLOCK_N, int SWZ, int STAGES, bool STEM>
-__global__ void __launch_bounds__(gather_threads<STEM ? 2 : 1>(), 1)
+template <int BLOCK_N, int SWZ, int STAGES, bool STEM, int NPROD_ = (STEM ? 2 : 1)>
+__global__ void __launch_bounds__(gather_threads<NPROD_>(), 1)
 conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
     using S = GatherSmem<BLOCK_N, SWZ, STAGES>;
     constexpr int NEPI = kGatherEpiGroups;
-    constexpr int NPROD = STEM ? 2 : 1;
+    constexpr int NPROD = NPROD_;
     constexpr int BLOCK_K = SWZ / 2;
     constexpr int UMMA_K = 16;
-    constexpr int CHUNKS = SWZ / 16;   // 16-byte chunks per row
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
     static_assert(!STEM || SWZ == 128, "stem uses one 64-wide K block");
@@ -246,31 +247,52 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                 mbar_arrive(full_bar(stage));
             }
         } else {
-            // bf16 input, Cin == BLOCK_K: one K block per filter tap, copied with cp.async straight into the swizzled
-            // stage (no register staging, up to STAGES taps in flight per thread)
+            // bf16 input, Cin == BLOCK_K == 32 (64-byte rows): one K block per filter tap, copied with cp.async straight
+            // into the swizzled stage (no register staging, up to STAGES taps in flight).
+            // Lane mapping: 4 lanes x 16 bytes cover ONE 64-byte row, a warp instruction covers 8 consecutive rows, and
+            // a thread handles rows sr, sr + 8, sr + 16, sr + 24 of its warp's 32-row block.  (The first version gave
+            // every thread one whole row: a warp instruction then touched 32 different rows -- half-used 32-byte
+            // sectors on the global side and 4-way bank conflicts on the swizzled shared-memory side; adding producer
+            // warps made it slower, 0.47 -> 0.63 ms.)
+            // With NPROD producer groups the K blocks (taps) are dealt round-robin: group pg fills every NPROD-th stage.
+            static_assert(STEM || SWZ == 64, "lane mapping assumes 4 chunks per row");
             const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.src);
-            int stage = 0;
+            const int wrow = (row & ~31) + (lane >> 2);      // first of this thread's 4 rows
+            const int jc = lane & 3;
+            int stage = 0, turn = 0;
             uint32_t phase = 0;
             for (int j = 0; j < my_tiles; ++j) {
-                const int m = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + row;
-                const bool valid = m < p.M;
-                const int n = m / hw;
-                const int rem = m - n * hw;
-                const int po = rem / p.Wo;
-                const int qo = rem - po * p.Wo;
-                const int y0 = po * p.stride + p.lower;
-                const int x0 = qo * p.stride + p.lower;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const int r = kb / p.ksize, sx = kb - r * p.ksize;
-                    const int y = y0 + r, x = x0 + sx;
-                    const bool ok = valid && y >= 0 && y < p.H && x >= 0 && x < p.W;
-                    const __nv_bfloat16* px = ok ? src + (((long long)n * p.H + y) * p.W + x) * p.src_stride : src;
-                    mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
-                    const uint32_t a_s = smem_a + stage * S::A_BYTES;
+                const int m0 = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + wrow;
+                const __nv_bfloat16* base[4];
+                int y0[4], x0[4];
+                uint32_t dst[4];
 #pragma unroll
-                    for (int jc = 0; jc < CHUNKS; ++jc)
-                        cp_async_16(a_s + swz_off<SWZ>(row, jc), px + jc * 8, ok ? 16u : 0u);
-                    cp_async_arrive_noinc(full_bar(stage));
+                for (int i = 0; i < 4; ++i) {
+                    const int m = m0 + 8 * i;
+                    const int n = m / hw;
+                    const int rem = m - n * hw;
+                    const int po = rem / p.Wo;
+                    const int qo = rem - po * p.Wo;
+                    // rows past M: push y0 out of range so that every tap is zero filled
+                    y0[i] = (m < p.M) ? po * p.stride + p.lower : -4;
+                    x0[i] = qo * p.stride + p.lower;
+                    base[i] = src + (((long long)n * p.H + y0[i]) * p.W + x0[i]) * p.src_stride + jc * 8;
+                    dst[i] = swz_off<64>(wrow + 8 * i, jc);
+                }
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (turn == pg) {
+                        const int r = kb / p.ksize, sx = kb - r * p.ksize;
+                        const long long tap = ((long long)r * p.W + sx) * p.src_stride;
+                        mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
+                        const uint32_t a_s = smem_a + stage * S::A_BYTES;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const bool ok = (unsigned)(y0[i] + r) < (unsigned)p.H && (unsigned)(x0[i] + sx) < (unsigned)p.W;
+                            cp_async_16(a_s + dst[i], ok ? (const void*)(base[i] + tap) : (const void*)src, ok ? 16u : 0u);
+                        }
+                        cp_async_arrive_noinc(full_bar(stage));
+                    }
+                    if (++turn == NPROD) turn = 0;
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }

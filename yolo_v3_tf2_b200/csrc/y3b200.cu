@@ -346,11 +346,11 @@ cudaError_t launch_conv(const ConvCfg& c, const CUtensorMap& ta, const CUtensorM
     return c.cluster == 2 ? launch_conv_cl<2>(c, ta, tb, to, tr, a, sms, st) : launch_conv_cl<1>(c, ta, tb, to, tr, a, sms, st);
 }
 
-template <int BN, int SWZ, int ST, bool STEM>
+template <int BN, int SWZ, int ST, bool STEM, int NPROD = (STEM ? 2 : 1)>
 cudaError_t launch_gather_t(const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const y3::ConvArgs& args,
                             int sms, cudaStream_t st) {
     using S = y3::GatherSmem<BN, SWZ, ST>;
-    auto kern = y3::conv_gather_kernel<BN, SWZ, ST, STEM>;
+    auto kern = y3::conv_gather_kernel<BN, SWZ, ST, STEM, NPROD>;
     const int smem = S::total(args.num_k_blocks);
     if (smem > 232448) return cudaErrorInvalidValue;
     static int configured = 0;
@@ -362,7 +362,7 @@ cudaError_t launch_gather_t(const CUtensorMap& tb, const CUtensorMap& to, const 
     const int grid = std::max(1, std::min(args.tiles_m, sms));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(y3::gather_threads<STEM ? 2 : 1>());
+    cfg.blockDim = dim3(y3::gather_threads<NPROD>());
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -379,7 +379,13 @@ cudaError_t launch_gather(const ConvCfg& c, const CUtensorMap& tb, const CUtenso
     if (c.gather == 2) return launch_gather_t<32, 128, 8, true>(tb, to, tr, a, sms, st);
     switch (c.block_n) {
         case 32: return launch_gather_t<32, 64, 8, false>(tb, to, tr, a, sms, st);
-        case 64: return launch_gather_t<64, 64, 8, false>(tb, to, tr, a, sms, st);
+        case 64: {
+            // experiment knob: producer groups (taps copied concurrently) for the Cin = 32 -> 64 layers
+            static const int nprod = []() { const char* e = getenv("Y3_GATHER_NPROD"); return e ? atoi(e) : 1; }();
+            if (nprod == 2) return launch_gather_t<64, 64, 12, false, 2>(tb, to, tr, a, sms, st);
+            if (nprod == 3) return launch_gather_t<64, 64, 12, false, 3>(tb, to, tr, a, sms, st);
+            return launch_gather_t<64, 64, 8, false>(tb, to, tr, a, sms, st);
+        }
         case 128: return launch_gather_t<128, 64, 8, false>(tb, to, tr, a, sms, st);
     }
     return cudaErrorInvalidValue;
