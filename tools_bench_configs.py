@@ -48,9 +48,9 @@ def config4(B=512, C=80):
     F = 5 + C
     anchors = configs.coco_anchors()
     print("\n## Config 4: decode + NMS only, N = %d x C = %d, batch %d (one GPU)\n" % (N, C, B))
-    print("| stage | us / batch | algorithmic GB/s | of measured HBM peak (%.0f GB/s) | images/s |" % HBM)
-    print("|---|---|---|---|---|")
     for name, mean in (("dense (obj ~ N(0,2))", 0.0), ("sparse (obj ~ N(-6,2))", -6.0)):
+        print("| stage | us / batch | algorithmic GB/s | of measured HBM peak (%.0f GB/s) | images/s |" % HBM)
+        print("|---|---|---|---|---|")
         grids = gen_grids(B, sizes, C, mean, 0)
         t = timeit(lambda: y3.yolo_decode(grids, anchors, C))
         by = 2.0 * N * F * 4 * B
@@ -80,7 +80,7 @@ def config4(B=512, C=80):
                 t = timeit(lambda: nms_padded(bboxes, scores, 100, iou, sthr), n=10, warm=2)
                 cells.append("%.0f (%.2f M img/s) [%.0f / %.1f]" % (t, B / t, npass, nv.float().mean().item()))
             print("| %.3f | %s |" % (sthr, " | ".join(cells)))
-        print("\n| stage | us / batch | algorithmic GB/s | of measured HBM peak | images/s |\n|---|---|---|---|---|")
+        print("")
         del dec, bboxes, conf, probs, scores, cls
         torch.cuda.empty_cache()
 

@@ -23,9 +23,9 @@ constexpr int kGatherEpiGroups = 2;
 template <int NPROD>
 constexpr int gather_threads() { return 32 * (4 + 4 * kGatherEpiGroups + 4 * NPROD); }
 
-template <int BLOCK_N, int SWZ, int STAGES>
+template <int BLOCK_N, int SWZ, int STAGES, int KBLK = 1>   // KBLK: K blocks held by one A stage
 struct GatherSmem {
-    static constexpr int A_BYTES = kBlockM * SWZ;
+    static constexpr int A_BYTES = kBlockM * SWZ * KBLK;
     static constexpr int B_BYTES = BLOCK_N * SWZ;
     static constexpr int XPOSE_BYTES = kGatherEpiGroups * 4 * kEpiWarpBytes;
     static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kGatherEpiGroups;
@@ -50,11 +50,14 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BLOCK_N, int SWZ, int STAGES, bool STEM, int NPROD_ = (STEM ? 2 : 1)>
+// COL (stride-1 stem only): the column-sharing producer described at the producer role below; one A stage then holds
+// two K blocks (72 used columns) and a tile is one stage.
+template <int BLOCK_N, int SWZ, int STAGES, bool STEM, int NPROD_ = (STEM ? 2 : 1), bool COL = false>
 __global__ void __launch_bounds__(gather_threads<NPROD_>(), 1)
 conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
-    using S = GatherSmem<BLOCK_N, SWZ, STAGES>;
+    using S = GatherSmem<BLOCK_N, SWZ, STAGES, COL ? 2 : 1>;
+    static_assert(!COL || (STEM && SWZ == 128), "column producer is a stem variant");
     constexpr int NEPI = kGatherEpiGroups;
     constexpr int NPROD = NPROD_;
     constexpr int BLOCK_K = SWZ / 2;
@@ -109,6 +112,13 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         tmem_alloc(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish();
     }
+    if constexpr (COL) {
+        // columns 72..79 of every row are read by the last MMA but never written by the producers: clear the stages
+        // once (stale shared memory could hold NaN patterns, and NaN x 0-weight is NaN)
+        for (uint32_t o = threadIdx.x * 16u; o < (uint32_t)(STAGES * S::A_BYTES); o += blockDim.x * 16u)
+            st_shared_v4(smem_a + o, make_uint4(0u, 0u, 0u, 0u));
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -139,6 +149,23 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             mbar_wait(tempty_bar(acc), (uint32_t)(((j >> 1) & 1) ^ 1), 0x200 + acc);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            if constexpr (COL) {
+                // one stage = the tile's two K blocks: 64 columns (4 MMAs) + columns 64..79 (1 MMA)
+                mbar_wait(full_bar(stage), phase, 0x300 + stage);
+                fence_proxy_async_smem();
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
+                    umma_bf16(d_tmem, adesc + (uint64_t)((kBlockM * SWZ) >> 4), bdesc0 + (uint64_t)(S::B_BYTES >> 4), idesc, 1u);
+                    umma_commit(empty_bar(stage));
+                    umma_commit(tfull_bar(acc));
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                continue;
+            }
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(full_bar(stage), phase, 0x300 + stage);
                 fence_proxy_async_smem();   // producer writes came through the generic proxy (st.shared / cp.async)
@@ -189,7 +216,97 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         const int pg = (warp - 4 - 4 * NEPI) >> 2;
         const int row = (int)threadIdx.x - 32 * (4 + 4 * NEPI) - 128 * pg;
         const int hw = p.Ho * p.Wo;
-        if constexpr (STEM) {
+        if constexpr (COL) {
+            // Column-sharing stem producer (3x3, stride 1, pad 1).  The one-thread-per-output-pixel producer below loads
+            // and converts 27 values per pixel although horizontally adjacent pixels share 18 of them, and the kernel
+            // is bound by instructions issued per tile (finding 15).  Here a thread loads and converts only
+            // the 3 rows x 3 channels of ITS pixel column (9 values -> 9 hi + 9 lo bf16 = three 16-byte pieces) and
+            // stores the pieces three times: as filter column s = 1 of its own tile row, s = 2 of the row of the pixel
+            // to its left and s = 0 of the row of the pixel to its right.  K layout (weights packed to match): column
+            // s*24 + i = bf16(x_i), s*24 + 9 + i = bf16(x_i - bf16(x_i)), i = r*3 + c; columns 64..71 live in the
+            // stage's second K block.  Every (row, s) slot has exactly one writer: the neighbour in the same image row
+            // and tile, else the row's own thread (zeros at the image border, or the halo column of a tile edge).
+            const float* src = reinterpret_cast<const float*>(p.src);
+            const int W = p.W;
+            auto loadcol = [&](long long pix, int y, bool valid, float (&v)[9]) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int yy = y - 1 + r;
+                    const bool ok = valid && yy >= 0 && yy < p.H;
+                    const float* px = src + (pix + (long long)(r - 1) * W) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[r * 3 + c] = ok ? __ldg(px + c) : 0.0f;
+                }
+            };
+            auto convert = [&](const float (&v)[9], uint4& p0, uint4& p1, uint4& p2) {
+                __nv_bfloat162 h[4], l[4];
+                float f[9];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                    const float2 t = __bfloat1622float2(h[i]);
+                    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+                }
+                const __nv_bfloat16 h8 = __float2bfloat16_rn(v[8]);
+                f[8] = __bfloat162float(h8);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(v[0] - f[0]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) l[i] = __floats2bfloat162_rn(v[2 * i + 1] - f[2 * i + 1], v[2 * i + 2] - f[2 * i + 2]);
+                const __nv_bfloat162 mid = __halves2bfloat162(h8, l0);
+                p0 = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                                *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+                p1 = make_uint4(*reinterpret_cast<const uint32_t*>(&mid), *reinterpret_cast<uint32_t*>(&l[0]),
+                                *reinterpret_cast<uint32_t*>(&l[1]), *reinterpret_cast<uint32_t*>(&l[2]));
+                p2 = make_uint4(*reinterpret_cast<uint32_t*>(&l[3]), 0u, 0u, 0u);
+            };
+            // pixel of this thread in tile j, its column (and the halo column the tile-edge threads need)
+            struct Pix { long long m; int y, x; bool valid, halo; };
+            auto locate = [&](int j) {
+                Pix q;
+                q.m = (long long)tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + row;
+                q.valid = (j < my_tiles) && (q.m < p.M) && !(p.dbg & 4);
+                const int n = (int)(q.m / hw);
+                const int rem = (int)(q.m - (long long)n * hw);
+                q.y = rem / W;
+                q.x = rem - q.y * W;
+                q.halo = (row == 0 && q.x > 0) || (row == kBlockM - 1 && q.x < W - 1);
+                return q;
+            };
+            Pix qn = locate(pg);
+            float vn[9], hn[9];
+            loadcol(qn.m, qn.y, qn.valid, vn);
+            if (qn.halo) loadcol(qn.m + (row == 0 ? -1 : 1), qn.y, qn.valid, hn);
+            for (int j = pg; j < my_tiles; j += NPROD) {
+                const Pix q = qn;
+                uint4 c0, c1, c2, e0, e1, e2;
+                convert(vn, c0, c1, c2);
+                if (q.halo) convert(hn, e0, e1, e2);
+                qn = locate(j + NPROD);
+                loadcol(qn.m, qn.y, qn.valid, vn);
+                if (qn.halo) loadcol(qn.m + (row == 0 ? -1 : 1), qn.y, qn.valid, hn);
+                const int stage = j % STAGES;                      // one stage (two K blocks) per tile
+                const uint32_t phase = (uint32_t)((j / STAGES) & 1);
+                mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
+                const uint32_t a_s = smem_a + stage * S::A_BYTES;
+                auto put = [&](int drow, int sx, const uint4& p0, const uint4& p1, const uint4& p2) {
+                    st_shared_v4(a_s + swz_off<128>(drow, 3 * sx), p0);
+                    st_shared_v4(a_s + swz_off<128>(drow, 3 * sx + 1), p1);
+                    if (sx < 2) st_shared_v4(a_s + swz_off<128>(drow, 3 * sx + 2), p2);
+                    else st_shared_v4(a_s + (uint32_t)(kBlockM * SWZ) + swz_off<128>(drow, 0), p2);
+                };
+                if (!(p.dbg & 32)) {
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    put(row, 1, c0, c1, c2);
+                    if (row > 0 && q.x > 0) put(row - 1, 2, c0, c1, c2);
+                    if (row < kBlockM - 1 && q.x < W - 1) put(row + 1, 0, c0, c1, c2);
+                    if (q.x == 0) put(row, 0, z, z, z);
+                    if (q.x == W - 1) put(row, 2, z, z, z);
+                    if (q.halo) put(row, row == 0 ? 0 : 2, e0, e1, e2);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(full_bar(stage));
+            }
+        } else if constexpr (STEM) {
             // 27 fp32 inputs -> hi/lo bf16 halves of one 64-wide K block; the loads of the group's next tile are in
             // flight while the current one is converted and stored
             const float* src = reinterpret_cast<const float*>(p.src);
