@@ -23,9 +23,9 @@ constexpr int kGatherEpiGroups = 2;
 template <int NPROD>
 constexpr int gather_threads() { return 32 * (4 + 4 * kGatherEpiGroups + 4 * NPROD); }
 
-template <int BLOCK_N, int SWZ, int STAGES, int KBLK = 1>   // KBLK: K blocks held by one A stage
+template <int BLOCK_N, int SWZ, int STAGES>
 struct GatherSmem {
-    static constexpr int A_BYTES = kBlockM * SWZ * KBLK;
+    static constexpr int A_BYTES = kBlockM * SWZ;
     static constexpr int B_BYTES = BLOCK_N * SWZ;
     static constexpr int XPOSE_BYTES = kGatherEpiGroups * 4 * kEpiWarpBytes;
     static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kGatherEpiGroups;
@@ -50,13 +50,12 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// COL (stride-1 stem only): the column-sharing producer described at the producer role below; one A stage then holds
-// two K blocks (72 used columns) and a tile is one stage.
+// COL (stride-1 stem only): the column-sharing producer described at the producer role below.
 template <int BLOCK_N, int SWZ, int STAGES, bool STEM, int NPROD_ = (STEM ? 2 : 1), bool COL = false>
 __global__ void __launch_bounds__(gather_threads<NPROD_>(), 1)
 conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
-    using S = GatherSmem<BLOCK_N, SWZ, STAGES, COL ? 2 : 1>;
+    using S = GatherSmem<BLOCK_N, SWZ, STAGES>;
     static_assert(!COL || (STEM && SWZ == 128), "column producer is a stem variant");
     constexpr int NEPI = kGatherEpiGroups;
     constexpr int NPROD = NPROD_;
@@ -113,8 +112,8 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         tmem_relinquish();
     }
     if constexpr (COL) {
-        // columns 72..79 of every row are read by the last MMA but never written by the producers: clear the stages
-        // once (stale shared memory could hold NaN patterns, and NaN x 0-weight is NaN)
+        // columns 54..63 of every row are read by the MMAs but never written by the producers: clear the stages once
+        // (stale shared memory could hold NaN patterns, and NaN x 0-weight is NaN)
         for (uint32_t o = threadIdx.x * 16u; o < (uint32_t)(STAGES * S::A_BYTES); o += blockDim.x * 16u)
             st_shared_v4(smem_a + o, make_uint4(0u, 0u, 0u, 0u));
         fence_proxy_async_smem();
@@ -149,23 +148,6 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             mbar_wait(tempty_bar(acc), (uint32_t)(((j >> 1) & 1) ^ 1), 0x200 + acc);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-            if constexpr (COL) {
-                // one stage = the tile's two K blocks: 64 columns (4 MMAs) + columns 64..79 (1 MMA)
-                mbar_wait(full_bar(stage), phase, 0x300 + stage);
-                fence_proxy_async_smem();
-                tc_fence_after();
-                if (leader) {
-                    const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * 2), idesc, (uint32_t)(k != 0));
-                    umma_bf16(d_tmem, adesc + (uint64_t)((kBlockM * SWZ) >> 4), bdesc0 + (uint64_t)(S::B_BYTES >> 4), idesc, 1u);
-                    umma_commit(empty_bar(stage));
-                    umma_commit(tfull_bar(acc));
-                }
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                continue;
-            }
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(full_bar(stage), phase, 0x300 + stage);
                 fence_proxy_async_smem();   // producer writes came through the generic proxy (st.shared / cp.async)
@@ -220,12 +202,13 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             // Column-sharing stem producer (3x3, stride 1, pad 1).  The one-thread-per-output-pixel producer below loads
             // and converts 27 values per pixel although horizontally adjacent pixels share 18 of them, and the kernel
             // is bound by instructions issued per tile (finding 15).  Here a thread loads and converts only
-            // the 3 rows x 3 channels of ITS pixel column (9 values -> 9 hi + 9 lo bf16 = three 16-byte pieces) and
-            // stores the pieces three times: as filter column s = 1 of its own tile row, s = 2 of the row of the pixel
-            // to its left and s = 0 of the row of the pixel to its right.  K layout (weights packed to match): column
-            // s*24 + i = bf16(x_i), s*24 + 9 + i = bf16(x_i - bf16(x_i)), i = r*3 + c; columns 64..71 live in the
-            // stage's second K block.  Every (row, s) slot has exactly one writer: the neighbour in the same image row
-            // and tile, else the row's own thread (zeros at the image border, or the halo column of a tile edge).
+            // the 3 rows x 3 channels of ITS pixel column (9 values -> 9 hi + 9 lo bf16 = two 16-byte pieces + 4 bytes)
+            // and stores them three times: as filter column s = 1 of its own tile row, s = 2 of the row of the pixel to
+            // its left and s = 0 of the row of the pixel to its right.  K layout of a row (weights packed to match), with
+            // i = r*3 + c, hi = bf16(x), lo = bf16(x - hi): columns s*16 + [0,9) = hi_i, s*16 + 9 + [0,7) = lo_0..lo_6,
+            // columns 48 + 2s, 49 + 2s = lo_7, lo_8; columns 54..63 are zero.  Every (row, s) slot has exactly one
+            // writer: the neighbour in the same image row and tile, else the row's own thread (zeros at the image border,
+            // or the halo column at a tile edge).
             const float* src = reinterpret_cast<const float*>(p.src);
             const int W = p.W;
             auto loadcol = [&](long long pix, int y, bool valid, float (&v)[9]) {
@@ -238,7 +221,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                     for (int c = 0; c < 3; ++c) v[r * 3 + c] = ok ? __ldg(px + c) : 0.0f;
                 }
             };
-            auto convert = [&](const float (&v)[9], uint4& p0, uint4& p1, uint4& p2) {
+            auto convert = [&](const float (&v)[9], uint4& p0, uint4& p1, uint32_t& p2) {
                 __nv_bfloat162 h[4], l[4];
                 float f[9];
 #pragma unroll
@@ -257,16 +240,16 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                                 *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
                 p1 = make_uint4(*reinterpret_cast<const uint32_t*>(&mid), *reinterpret_cast<uint32_t*>(&l[0]),
                                 *reinterpret_cast<uint32_t*>(&l[1]), *reinterpret_cast<uint32_t*>(&l[2]));
-                p2 = make_uint4(*reinterpret_cast<uint32_t*>(&l[3]), 0u, 0u, 0u);
+                p2 = *reinterpret_cast<uint32_t*>(&l[3]);
             };
             // pixel of this thread in tile j, its column (and the halo column the tile-edge threads need)
-            struct Pix { long long m; int y, x; bool valid, halo; };
+            struct Pix { int m, y, x; bool valid, halo; };
             auto locate = [&](int j) {
                 Pix q;
-                q.m = (long long)tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + row;
+                q.m = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + row;   // < 2^31 (host-checked)
                 q.valid = (j < my_tiles) && (q.m < p.M) && !(p.dbg & 4);
-                const int n = (int)(q.m / hw);
-                const int rem = (int)(q.m - (long long)n * hw);
+                const int n = q.m / hw;
+                const int rem = q.m - n * hw;
                 q.y = rem / W;
                 q.x = rem - q.y * W;
                 q.halo = (row == 0 && q.x > 0) || (row == kBlockM - 1 && q.x < W - 1);
@@ -278,29 +261,29 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             if (qn.halo) loadcol(qn.m + (row == 0 ? -1 : 1), qn.y, qn.valid, hn);
             for (int j = pg; j < my_tiles; j += NPROD) {
                 const Pix q = qn;
-                uint4 c0, c1, c2, e0, e1, e2;
+                uint4 c0, c1, e0, e1;
+                uint32_t c2, e2;
                 convert(vn, c0, c1, c2);
                 if (q.halo) convert(hn, e0, e1, e2);
                 qn = locate(j + NPROD);
                 loadcol(qn.m, qn.y, qn.valid, vn);
                 if (qn.halo) loadcol(qn.m + (row == 0 ? -1 : 1), qn.y, qn.valid, hn);
-                const int stage = j % STAGES;                      // one stage (two K blocks) per tile
+                const int stage = j % STAGES;                      // one K block per tile
                 const uint32_t phase = (uint32_t)((j / STAGES) & 1);
                 mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                 const uint32_t a_s = smem_a + stage * S::A_BYTES;
-                auto put = [&](int drow, int sx, const uint4& p0, const uint4& p1, const uint4& p2) {
-                    st_shared_v4(a_s + swz_off<128>(drow, 3 * sx), p0);
-                    st_shared_v4(a_s + swz_off<128>(drow, 3 * sx + 1), p1);
-                    if (sx < 2) st_shared_v4(a_s + swz_off<128>(drow, 3 * sx + 2), p2);
-                    else st_shared_v4(a_s + (uint32_t)(kBlockM * SWZ) + swz_off<128>(drow, 0), p2);
+                auto put = [&](int drow, int sx, const uint4& p0, const uint4& p1, uint32_t p2) {
+                    st_shared_v4(a_s + swz_off<128>(drow, 2 * sx), p0);
+                    st_shared_v4(a_s + swz_off<128>(drow, 2 * sx + 1), p1);
+                    st_shared_u32(a_s + swz_off<128>(drow, 6) + 4u * (uint32_t)sx, p2);
                 };
                 if (!(p.dbg & 32)) {
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                     put(row, 1, c0, c1, c2);
                     if (row > 0 && q.x > 0) put(row - 1, 2, c0, c1, c2);
                     if (row < kBlockM - 1 && q.x < W - 1) put(row + 1, 0, c0, c1, c2);
-                    if (q.x == 0) put(row, 0, z, z, z);
-                    if (q.x == W - 1) put(row, 2, z, z, z);
+                    if (q.x == 0) put(row, 0, z, z, 0u);
+                    if (q.x == W - 1) put(row, 2, z, z, 0u);
                     if (q.halo) put(row, row == 0 ? 0 : 2, e0, e1, e2);
                 }
                 fence_proxy_async_smem();

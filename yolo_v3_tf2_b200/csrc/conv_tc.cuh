@@ -62,7 +62,7 @@ struct ConvArgs {
     int rev;               // 1: walk the output tiles from the last to the first.  The planner alternates the direction from
                            //    layer to layer so that a layer starts on the pixels its predecessor wrote LAST, which are
                            //    still in L2 (each 52x52 tensor is 88 MB of a 126 MB L2)
-    int stem_col;          // stem only: column-sharing producer (conv_gather.cuh), weights packed [cout][128]
+    int stem_col;          // stem only: column-sharing producer (conv_gather.cuh), weights in its K order
     int stages;            // weights-resident kernels only: A-operand pipeline depth (what fits next to the weights)
     int tma_out;           // 0: register-transpose epilogue; 32 / 64: bf16 dense output written with TMA stores in chunks
                            //    of that many columns (epilogue_role_tma); tmO (and tmR when a residual is fused) are

@@ -207,6 +207,12 @@ bool pick_cfg(int cin, int cout, int ksize, ConvCfg& c) {
 
 // column-sharing stem producer (conv_gather.cuh, COL): Y3_STEM_COL=0 falls back to the one-thread-per-pixel producer
 const bool g_stem_col = []() { const char* e = getenv("Y3_STEM_COL"); return !(e && e[0] == '0'); }();
+// K column of value i = r*3 + c of filter column sx in a row built by that producer: hi part bf16(x), lo part the
+// bf16 remainder.  [sx*16, sx*16+9) hi_0..8, [sx*16+9, sx*16+16) lo_0..6, 48+2sx / 49+2sx lo_7 / lo_8.
+__host__ __device__ inline int stem_col_k(int sx, int i, bool lo) {
+    if (!lo) return sx * 16 + i;
+    return i < 7 ? sx * 16 + 9 + i : 48 + 2 * sx + (i - 7);
+}
 
 // weights-resident variants of the conv kernels (BRES): Y3_BRES=0 disables them
 const bool g_use_bres = []() { const char* e = getenv("Y3_BRES"); return !(e && e[0] == '0'); }();
@@ -352,7 +358,7 @@ cudaError_t launch_conv(const ConvCfg& c, const CUtensorMap& ta, const CUtensorM
 template <int BN, int SWZ, int ST, bool STEM, int NPROD = (STEM ? 2 : 1), bool COL = false>
 cudaError_t launch_gather_t(const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const y3::ConvArgs& args,
                             int sms, cudaStream_t st) {
-    using S = y3::GatherSmem<BN, SWZ, ST, COL ? 2 : 1>;
+    using S = y3::GatherSmem<BN, SWZ, ST>;
     auto kern = y3::conv_gather_kernel<BN, SWZ, ST, STEM, NPROD, COL>;
     const int smem = S::total(args.num_k_blocks);
     if (smem > 232448) return cudaErrorInvalidValue;
@@ -379,7 +385,7 @@ cudaError_t launch_gather_t(const CUtensorMap& tb, const CUtensorMap& to, const 
 cudaError_t launch_gather(const ConvCfg& c, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                           const y3::ConvArgs& a, int sms, cudaStream_t st) {
     if (a.tiles_n != 1) return cudaErrorInvalidValue;
-    if (c.gather == 2 && a.stem_col) return launch_gather_t<32, 128, 4, true, 2, true>(tb, to, tr, a, sms, st);
+    if (c.gather == 2 && a.stem_col) return launch_gather_t<32, 128, 8, true, 2, true>(tb, to, tr, a, sms, st);
     if (c.gather == 2) return launch_gather_t<32, 128, 8, true>(tb, to, tr, a, sms, st);
     switch (c.block_n) {
         case 32: return launch_gather_t<32, 64, 8, false>(tb, to, tr, a, sms, st);
@@ -506,8 +512,8 @@ struct ConvWeights {
     bool flat_order = false;  // K ordered (channel block, r, s, c) for the flat-patch kernel
     int flat_bk = 0;
     bool stem_hilo = false;   // tensor-core stem: [cout_pad][64] = 27 weights, 5 zeros, the same 27 weights, 5 zeros
-    bool stem_col = false;    // ... or, for the column-sharing producer (stride 1): [cout_pad][128], column
-                              // s*24 + r*3 + c and s*24 + 9 + r*3 + c = weight of tap (r, s), channel c
+    bool stem_col = false;    // ... or, for the column-sharing producer (stride 1): [cout_pad][64] in the K order
+                              // of conv_gather.cuh (stem_col_k below)
     void* w = nullptr;     // bf16 [cout_pad][k*k*cin]  or fp32 [k*k*cin][cout] for the direct kernel
     float* bias = nullptr; // fp32 [cout_pad]
     bool loaded = false;
@@ -1004,7 +1010,7 @@ int build_maps(y3_net& n) {
             }
         }
         if (rc) return rc;
-        const uint64_t K = (s.cfg.gather == 2) ? (s.stem_col ? 128 : 64) : (uint64_t)d.ksize * d.ksize * a.Cp;
+        const uint64_t K = (s.cfg.gather == 2) ? 64 : (uint64_t)d.ksize * d.ksize * a.Cp;
         rc = make_map_2d(n.ctx->drv, &s.tmB, w.w, w.cout_pad, K, K, s.cfg.block_n / (s.cfg.gather ? 1 : (s.cfg.cluster >= 2 ? 2 : 1)), s.cfg.swz, true);
         if (rc) return rc;
         const TensorInfo& o = n.tensors[s.dst];
@@ -1039,7 +1045,7 @@ y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
     a.stem_col = s.stem_col;
     if (s.cfg.gather == 2) {
         a.kblocks_per_tap = 1;
-        a.num_k_blocks = s.stem_col ? 2 : 1;
+        a.num_k_blocks = 1;
     } else {
         a.kblocks_per_tap = cin / (s.cfg.swz / 2);
         a.num_k_blocks = d.ksize * d.ksize * a.kblocks_per_tap;
@@ -1084,16 +1090,17 @@ unsigned grid_for(long long work, int threads, int sms) {
 // C ABI
 // ------------------------------------------------------------------------------------------------
 namespace {
-// [32][64] (27 weights, 5 zeros, the same 27, 5 zeros; K = (r*3 + s)*3 + c) -> [32][128] of the column-sharing producer
-__global__ void stem_repack_kernel(const __nv_bfloat16* __restrict__ w64, __nv_bfloat16* __restrict__ w128) {
-    const int o = blockIdx.x, k = threadIdx.x;
-    __nv_bfloat16 v = __float2bfloat16(0.0f);
-    const int sx = k / 24, i = k - sx * 24;          // filter column, position inside its 24-column group
-    if (sx < 3 && i < 18) {
-        const int rc = i % 9, r = rc / 3, c = rc - r * 3;
-        v = w64[o * 64 + (r * 3 + sx) * 3 + c];
+// [32][64] (27 weights, 5 zeros, the same 27, 5 zeros; K = (r*3 + s)*3 + c) -> the K order of the column-sharing producer
+__global__ void stem_repack_kernel(const __nv_bfloat16* __restrict__ w64, __nv_bfloat16* __restrict__ wcol) {
+    const int o = blockIdx.x, t = threadIdx.x;    // 64 threads
+    wcol[o * 64 + t] = __float2bfloat16(0.0f);
+    __syncthreads();
+    if (t < 27) {
+        const int r = t / 9, sx = (t / 3) % 3, c = t % 3;
+        const __nv_bfloat16 v = w64[o * 64 + t];
+        wcol[o * 64 + stem_col_k(sx, r * 3 + c, false)] = v;
+        wcol[o * 64 + stem_col_k(sx, r * 3 + c, true)] = v;
     }
-    w128[o * 128 + k] = v;
 }
 }  // namespace
 
@@ -1167,7 +1174,7 @@ int y3_net_create(y3_ctx* ctx, const y3_layer_desc* layers, int n_layers, int H,
         cudaMemset(n->arena, 0, (size_t)n->arena_bytes);
         for (ConvWeights& w : n->convs) {
             const size_t K = (size_t)w.k * w.k * w.cin;
-            const size_t wbytes = w.direct ? K * w.cout * 4 : (size_t)w.cout_pad * (w.stem_hilo ? (w.stem_col ? 128 : 64) : K) * 2;
+            const size_t wbytes = w.direct ? K * w.cout * 4 : (size_t)w.cout_pad * (w.stem_hilo ? 64 : K) * 2;
             if (cudaMalloc(&w.w, wbytes) != cudaSuccess || cudaMalloc(&w.bias, (size_t)w.cout_pad * 4) != cudaSuccess) {
                 y3_net_destroy(n);
                 return fail(Y3_ERR_CUDA, "cudaMalloc(weights) failed");
@@ -1244,17 +1251,16 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
             for (int o = 0; o < cout; ++o) packed[kk * cout + o] = kernel[kk * cout + o] * scale[o];   // HWIO is already [K][Cout]
         Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
     } else if (w.stem_hilo && w.stem_col) {
-        // column-sharing producer: filter column s occupies K columns [s*24, s*24 + 18): 9 weights (r, c) for bf16(x), the
-        // same 9 for the remainder x - bf16(x)
-        std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * 128, __float2bfloat16(0.0f));
+        // column-sharing producer: K columns in the order its threads store them (stem_col_k)
+        std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * 64, __float2bfloat16(0.0f));
         for (int r = 0; r < 3; ++r)
             for (int sx = 0; sx < 3; ++sx)
                 for (int c = 0; c < 3; ++c) {
                     const size_t kk = (size_t)(r * 3 + sx) * cin_l + c;
                     for (int o = 0; o < cout; ++o) {
                         const __nv_bfloat16 v = __float2bfloat16(kernel[kk * cout + o] * scale[o]);
-                        packed[(size_t)o * 128 + sx * 24 + r * 3 + c] = v;
-                        packed[(size_t)o * 128 + sx * 24 + 9 + r * 3 + c] = v;
+                        packed[(size_t)o * 64 + stem_col_k(sx, r * 3 + c, false)] = v;
+                        packed[(size_t)o * 64 + stem_col_k(sx, r * 3 + c, true)] = v;
                     }
                 }
         Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
@@ -1753,12 +1759,11 @@ int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const v
     void* w_col = nullptr;
     cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
     if (s.stem_col) {
-        Y3_CUDA(cudaMallocAsync(&w_col, 32 * 128 * 2, cst));
-        stem_repack_kernel<<<32, 128, 0, cst>>>(reinterpret_cast<const __nv_bfloat16*>(w_packed),
+        Y3_CUDA(cudaMallocAsync(&w_col, 32 * 64 * 2, cst));
+        stem_repack_kernel<<<32, 64, 0, cst>>>(reinterpret_cast<const __nv_bfloat16*>(w_packed),
                                                  reinterpret_cast<__nv_bfloat16*>(w_col));
     }
-    int rc = s.stem_col ? make_map_2d(ctx->drv, &s.tmB, w_col, 32, 128, 128, 32, 128, true)
-                        : make_map_2d(ctx->drv, &s.tmB, w_packed, 32, 64, 64, 32, 128, true);
+    int rc = make_map_2d(ctx->drv, &s.tmB, s.stem_col ? w_col : w_packed, 32, 64, 64, 32, 128, true);
     if (rc) return rc;
     y3::ConvArgs ca = conv_args(s, d, 3, B);
     ca.bias = bias;
