@@ -19,9 +19,6 @@ namespace y3 {
 // producer warps.  Tiles are dealt round-robin to the epilogue groups (group g owns accumulator stage g) and to the
 // producer groups, so two tiles are gathered / drained concurrently: these layers are latency bound, not byte bound.
 constexpr int kGatherEpiGroups = 2;
-// accumulator stages in TMEM: two per epilogue group (tile j lives in stage j % 4, group j % 2 drains it), so the MMAs
-// of a group's next tile do not wait for the group to release the one it is draining
-constexpr int kGatherAccs = 2 * kGatherEpiGroups;
 
 template <int NPROD>
 constexpr int gather_threads() { return 32 * (4 + 4 * kGatherEpiGroups + 4 * NPROD); }
@@ -31,7 +28,7 @@ struct GatherSmem {
     static constexpr int A_BYTES = kBlockM * SWZ;
     static constexpr int B_BYTES = BLOCK_N * SWZ;
     static constexpr int XPOSE_BYTES = kGatherEpiGroups * 4 * kEpiWarpBytes;
-    static constexpr int BAR_BYTES = (2 * STAGES + 2 * kGatherAccs + 1) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kGatherEpiGroups;
+    static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16 + 8 * kEpiMaxBufs * 4 * kGatherEpiGroups;
     static constexpr int total(int num_k_blocks) {
         return 1024 + STAGES * A_BYTES + num_k_blocks * B_BYTES + XPOSE_BYTES + BAR_BYTES;
     }
@@ -64,10 +61,8 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
     constexpr int NPROD = NPROD_;
     constexpr int BLOCK_K = SWZ / 2;
     constexpr int UMMA_K = 16;
-    constexpr int NACC = kGatherAccs;
-    constexpr uint32_t TMEM_COLS = (NACC * BLOCK_N <= 32) ? 32 : (NACC * BLOCK_N <= 64) ? 64 : (NACC * BLOCK_N <= 128) ? 128
-                                   : (NACC * BLOCK_N <= 256) ? 256 : 512;
-    static_assert(NACC * BLOCK_N <= 512, "accumulators must fit in TMEM");
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
     static_assert(!STEM || SWZ == 128, "stem uses one 64-wide K block");
 
     extern __shared__ uint8_t smem_raw[];
@@ -81,12 +76,12 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + kGatherAccs + a); };
-    const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 2 * kGatherAccs);
-    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 2 * kGatherAccs + 1);
-    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 2 * kGatherAccs + 1) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 5);
+    auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 5) + 16u + 8u * kEpiMaxBufs * w; };   // ring of epilogue warp w
     volatile uint32_t* tmem_ptr_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + tiles_bytes + S::XPOSE_BYTES + 8 * (2 * STAGES + 2 * kGatherAccs + 1));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + tiles_bytes + S::XPOSE_BYTES + 8 * (2 * STAGES + 5));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -100,7 +95,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             mbar_init(full_bar(s), 128);
             mbar_init(empty_bar(s), 1);
         }
-        for (int a = 0; a < NACC; ++a) {
+        for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 128);
         }
@@ -149,8 +144,8 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         uint32_t phase = 0;
         mbar_wait(bfull_bar, 0, 0x700);
         for (int j = 0; j < my_tiles; ++j) {
-            const int acc = j % NACC;
-            mbar_wait(tempty_bar(acc), (uint32_t)(((j / NACC) & 1) ^ 1), 0x200 + acc);
+            const int acc = j & 1;
+            mbar_wait(tempty_bar(acc), (uint32_t)(((j >> 1) & 1) ^ 1), 0x200 + acc);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
             for (int kb = 0; kb < nkb; ++kb) {
@@ -180,18 +175,17 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             const uint32_t stg = smem_base + tiles_bytes + (uint32_t)((warp - 4) * kEpiWarpBytes);
             const EpiTiles et{(int)blockIdx.x + eg * (int)gridDim.x, NEPI * (int)gridDim.x, num_tiles, 1, 1, 0};
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * BLOCK_N);
-            // the group's second accumulator: NEPI stages (columns / barriers) after its first
             if (BLOCK_N >= 64 && p.tma_out == 64)
                 epilogue_role_tma<64, 2>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
-                                         tempty_bar(eg), false, nullptr, 7 + eg, (uint32_t)(NEPI * BLOCK_N), 8u * NEPI);
+                                         tempty_bar(eg), false, nullptr, 7 + eg);
             else
                 epilogue_role_tma<32, 4>(p, &tmO, &tmR, BLOCK_N, et, t_acc, q, lane, stg, res_bar(warp - 4), tfull_bar(eg),
-                                         tempty_bar(eg), false, nullptr, 7 + eg, (uint32_t)(NEPI * BLOCK_N), 8u * NEPI);
+                                         tempty_bar(eg), false, nullptr, 7 + eg);
         } else {
             for (int j = eg; j < my_tiles; j += NEPI) {
-                const int acc = j % NACC;
+                const int acc = j & 1;
                 const int tile = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles);
-                mbar_wait(tfull_bar(acc), (uint32_t)((j / NACC) & 1), 0x400 + acc);
+                mbar_wait(tfull_bar(acc), (uint32_t)((j >> 1) & 1), 0x400 + acc);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
                 epilogue_tile(p, BLOCK_N, tile * kBlockM, 0, t_row, q, lane, xp);

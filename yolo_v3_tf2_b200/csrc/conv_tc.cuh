@@ -305,12 +305,7 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
                                                   int block_n, const EpiTiles et, uint32_t t_acc, int q, int lane,
                                                   uint32_t stg, uint32_t res_bar0, uint32_t tfull_bar,
                                                   uint32_t tempty_addr, bool tempty_remote, unsigned long long* ts,
-                                                  int ts_slot, uint32_t alt_cols = 0, uint32_t alt_bar = 0) {
-    // alt_cols != 0: the group owns TWO accumulators and alternates between them from tile to tile (its second one is
-    // alt_cols TMEM columns / alt_bar barrier bytes further on), so the MMAs of its next tile run while it is still
-    // draining this one.  Used by the 128 x 32 stem tiles, where the accumulator round trip set the pace.
-    const uint32_t alt_mask = alt_cols ? 1u : 0u;
-    const uint32_t alt_shift = alt_cols ? 1u : 0u;
+                                                  int ts_slot) {
     static_assert((CW == 64 || CW == 32) && NBUF >= 2 && NBUF <= kEpiMaxBufs &&
                   NBUF * 32 * CW * (F32 ? 4 : 2) <= kEpiWarpBytes && (!F32 || CW == 32), "ring");
     constexpr uint32_t ROW_BYTES = CW * (F32 ? 4 : 2);
@@ -344,10 +339,8 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
     uint32_t jj = 0;         // tiles of this group seen so far (accumulator phase)
 #pragma unroll 1
     while (pr.valid) {
-        const uint32_t aj = jj & alt_mask;               // which of the group's accumulators this tile lives in
-        const uint32_t t_acc_j = t_acc + aj * alt_cols;
         if (pr.c == 0) {
-            mbar_wait(tfull_bar + aj * alt_bar, (jj >> alt_shift) & 1u, 0x400);
+            mbar_wait(tfull_bar, jj & 1u, 0x400);
             tc_fence_after();
             if (jj == 0 && lane == 0 && q == 0 && ts_slot == 7) ts_mark(ts, 6);   // first accumulator complete
         }
@@ -360,8 +353,8 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
             __syncwarp();
         }
         uint32_t v[CW];
-        tmem_ld_32x32(t_acc_j + (uint32_t)(pr.c * CW), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        if constexpr (CW == 64) tmem_ld_32x32(t_acc_j + (uint32_t)(pr.c * CW + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[CW - 32]));
+        tmem_ld_32x32(t_acc + (uint32_t)(pr.c * CW), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        if constexpr (CW == 64) tmem_ld_32x32(t_acc + (uint32_t)(pr.c * CW + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[CW - 32]));
         // bias of the first 32 columns: issued before the TMEM wait so the (L1-resident after the first tile) loads
         // overlap it; the shared-memory accesses below carry no memory clobber, so the second half's loads hoist too
         const float4* bp = reinterpret_cast<const float4*>(p.bias + pr.ncol);
@@ -374,8 +367,8 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
         if (pr.c == pr.nch - 1) {
             // every TMEM read of this accumulator has completed -> hand it back to the MMA warp now
             tc_fence_before();
-            if (tempty_remote) mbar_arrive_cluster(tempty_addr + aj * alt_bar);
-            else mbar_arrive(tempty_addr + aj * alt_bar);
+            if (tempty_remote) mbar_arrive_cluster(tempty_addr);
+            else mbar_arrive(tempty_addr);
             ++jj;
         }
         if (!drain_only) {
