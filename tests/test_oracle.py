@@ -70,6 +70,42 @@ def test_nms_formulations_agree_random(seed):
             assert np.array_equal(c[0][0], t[0]) and c[1][0] == t[1]
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_nms_oracle_vs_torchvision(seed):
+    """Third opinion on the greedy core of the restatement: torchvision.ops.nms (an implementation written by other
+    people, 'iou > thr', no epsilon, no TF-specific rules) must select the same boxes in the same order wherever the
+    TF-specific rules cannot matter: distinct scores (no tie-break), every box with a positive coordinate, and no
+    pair of boxes whose IoU is within 3e-5 of the threshold ('>=' vs '>', the 1e-8 in the denominator)."""
+    torch = pytest.importorskip("torch")
+    tv = pytest.importorskip("torchvision")
+    from oracle import nms_oracle, c_oracle
+    rng = np.random.default_rng(seed)
+    N = 500
+    b, _ = cluster_boxes(N, 25, seed + 7)
+    b = np.abs(b) + np.float32(1e-3)
+    lo, hi = np.minimum(b[:, :2], b[:, 2:]), np.maximum(b[:, :2], b[:, 2:])
+    hi = np.maximum(hi, lo + np.float32(0.03))                       # sides >= 0.03: the 1e-8 then shifts an IoU by < 2e-5
+    b = np.concatenate([lo, hi], 1).astype(np.float32)
+    s = ((rng.permutation(N) + 0.5) / N).astype(np.float32)          # distinct scores
+    iou_all = tv.ops.box_iou(torch.from_numpy(b), torch.from_numpy(b)).numpy()
+    assert np.abs(nms_oracle.bbox_overlap(b, b) - iou_all).max() < 2e-5   # same IoU up to rounding and the 1e-8
+    checked = 0
+    for thr in (0.3, 0.5, 0.7):
+        for sthr in (0.1, 0.6):
+            keep = s > sthr
+            idx = np.nonzero(keep)[0]
+            if np.any(np.abs(iou_all[np.ix_(idx, idx)] - thr) < 3e-5):
+                continue                                             # a borderline pair: implementations may differ
+            checked += 1
+            ref = idx[tv.ops.nms(torch.from_numpy(b[idx]), torch.from_numpy(s[idx]), thr).numpy()][:100]
+            for sel, nv in (nms_oracle.nms_padded_greedy(b, s, 100, thr, sthr),
+                            nms_oracle.nms_padded_tiled(b, s, 100, thr, sthr),
+                            tuple(x[0] for x in c_oracle.nms(b[None], s[None], 100, thr, sthr))):
+                assert nv == len(ref)
+                assert np.array_equal(sel[:nv], ref)
+    assert checked >= 1
+
+
 def test_nms_semantics_by_hand():
     """Tiny hand-checkable cases for each rule in SURVEY.md row a14."""
     from oracle import nms_oracle
@@ -180,6 +216,19 @@ def test_preprocess_oracle_vs_torch_bilinear():
     out = po.resize_image(rng.random((50, 100, 3), dtype=np.float32), 64, 64)
     assert out.shape == (64, 64, 3) and po.aspect_size(50, 100, 64, 64) == (32, 64)
     assert (out[:16] == 0).all() and (out[48:] == 0).all() and (out[16:48] != 0).any()
+
+
+def test_preprocess_oracle_vs_opencv_bilinear():
+    """Third opinion on the resize restatement: OpenCV's INTER_LINEAR on float32 images uses the same half-pixel-centre,
+    edge-clamped formula as TF2's tf.image.resize(bilinear, antialias=False)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import preprocess_oracle as po
+    rng = np.random.default_rng(1)
+    for (h, w, oh, ow) in [(37, 53, 64, 64), (480, 640, 416, 416), (100, 80, 33, 57), (416, 416, 608, 608)]:
+        img = rng.random((h, w, 3), dtype=np.float32)
+        ours = po.resize_bilinear(img, oh, ow)
+        ref = cv2.resize(img, (ow, oh), interpolation=cv2.INTER_LINEAR)
+        np.testing.assert_allclose(ours, ref, rtol=0, atol=5e-5)
 
 
 def test_next_rows_golden():
