@@ -1753,17 +1753,22 @@ int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const v
     conv_geometry(H, W, 3, stride, 1, s.Ho, s.Wo, s.pad_lo, s.pad_hi);
     y3_layer_desc d{};
     d.ksize = 3; d.stride = stride; d.filters = 32; d.activation = leaky;
-    // stride 1 / pad 1 goes through the column-sharing producer: re-pack the documented [32][64] weights into its
-    // [32][128] layout (stream-ordered scratch buffer)
+    // stride 1 / pad 1 goes through the column-sharing producer: re-pack the documented [32][64] weights into its K
+    // order (stream-ordered scratch buffer, released after the launch on every path)
     s.stem_col = (g_stem_col && stride == 1 && s.pad_lo == 1 && s.Ho == H && s.Wo == W) ? 1 : 0;
-    void* w_col = nullptr;
     cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
+    struct Scratch {
+        void* p = nullptr;
+        cudaStream_t st;
+        ~Scratch() { if (p) cudaFreeAsync(p, st); }
+    } w_col;
+    w_col.st = cst;
     if (s.stem_col) {
-        Y3_CUDA(cudaMallocAsync(&w_col, 32 * 64 * 2, cst));
+        Y3_CUDA(cudaMallocAsync(&w_col.p, 32 * 64 * 2, cst));
         stem_repack_kernel<<<32, 64, 0, cst>>>(reinterpret_cast<const __nv_bfloat16*>(w_packed),
-                                                 reinterpret_cast<__nv_bfloat16*>(w_col));
+                                                 reinterpret_cast<__nv_bfloat16*>(w_col.p));
     }
-    int rc = make_map_2d(ctx->drv, &s.tmB, s.stem_col ? w_col : w_packed, 32, 64, 64, 32, 128, true);
+    int rc = make_map_2d(ctx->drv, &s.tmB, s.stem_col ? w_col.p : w_packed, 32, 64, 64, 32, 128, true);
     if (rc) return rc;
     y3::ConvArgs ca = conv_args(s, d, 3, B);
     ca.bias = bias;
@@ -1777,8 +1782,7 @@ int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const v
         if (rc) return rc;
         ca.tma_out = 32;
     }
-    Y3_CUDA(launch_gather(cfg, s.tmB, s.tmO, s.tmR, ca, ctx->sms, reinterpret_cast<cudaStream_t>(stream)));
-    if (w_col) Y3_CUDA(cudaFreeAsync(w_col, cst));
+    Y3_CUDA(launch_gather(cfg, s.tmB, s.tmO, s.tmR, ca, ctx->sms, cst));
     return Y3_OK;
 }
 
