@@ -179,7 +179,9 @@ int y3_conv2d_flat_bf16(y3_ctx* ctx, const void* x_padded, int B, int H, int W, 
 
 /* The 3-channel stem conv (3x3, 32 filters) on the tensor cores: x fp32 [B,H,W,3]; w_packed bf16 [32][64] with the
  * 27 BN-folded weights of output o at columns 0..26 AND 32..58 (the kernel multiplies bf16(x) and the bf16 remainder
- * x - bf16(x) against the same weights, so the fp32 image keeps its precision).  Unit-test entry. */
+ * x - bf16(x) against the same weights, so the fp32 image keeps its precision).  For stride 1 the library re-orders
+ * the columns internally for its column-sharing producer; the caller's layout is the one above either way.
+ * Unit-test entry. */
 int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const void* w_packed, const float* bias,
                        int stride, int leaky, void* out, int64_t out_stride, void* stream);
 
