@@ -82,6 +82,25 @@ def test_reference_tiny_yamls_match_builtin():
     assert g_ref.outputs == builtin.outputs
 
 
+@pytest.mark.skipif(not has_ref, reason="reference checkout not present")
+def test_reference_thin_heads_yaml_matches_builtin():
+    """config/models/yolov3/model_thin_heads.yaml (multi-output necks, negative entry_index, backbone taps before the
+    shortcut adds -- SURVEY.md 8f-3): loads unchanged, equals the built-in thin-heads wiring, differs from model.yaml in
+    exactly the four re-wired edges, and plans (the two tapped 3x3 convs feed both an Add and a neck, so their Adds
+    cannot be fused into the conv epilogue and run as separate kernels)."""
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import graph, _lib
+    g_ref = graph.load_model_config(os.path.join(REF, "config/models/yolov3/model_thin_heads.yaml"), 80)
+    thin = y3.ParseModel.builtin_yolov3(80, thin_heads=True)
+    std = y3.ParseModel.builtin_yolov3(80).graph
+    assert _strip(g_ref) == _strip(thin.graph) and g_ref.outputs == thin.graph.outputs == std.outputs
+    diff = [i for i, (a, b) in enumerate(zip(_strip(thin.graph), _strip(std))) if a != b]
+    assert diff == [83, 85, 94, 96]
+    p = thin.plan(416, 416, 2)
+    assert [p["layers"][i - 1]["H"] for i in thin.graph.outputs] == [13, 26, 52]
+    assert len(thin.conv_shapes) == 75
+
+
 @pytest.mark.parametrize("nclasses,filters", [(80, 255), (38, 129), (37, 126), (3, 24)])
 def test_head_filters_expression(nclasses, filters):
     import yolo_v3_tf2_b200 as y3

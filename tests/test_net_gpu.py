@@ -85,6 +85,23 @@ def test_maxpool_variants_vs_oracle(cuda):
     _compare(grids, ref)
 
 
+@pytest.mark.parametrize("size,B,C", [(96, 2, 80), (416, 1, 80)])
+def test_thin_heads_forward_vs_oracle(cuda, size, B, C):
+    """The wiring of the reference's model_thin_heads.yaml (multi-output necks, negative entry_index,
+    backbone tapped before two shortcut adds, whose Adds then run as separate kernels) against the oracle of the same
+    graph."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from oracle import net_oracle
+    model = y3.ParseModel.builtin_yolov3(C, thin_heads=True).init_weights("variance", seed=9)
+    x = np.random.default_rng(1).random((B, size, size, 3), dtype=np.float32)
+    grids = model(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    ref = net_oracle.forward(model.graph.layers, model.graph.outputs, model._params, x)
+    assert [tuple(g.shape) for g in grids] == [(B, size // s, size // s, 3, 5 + C) for s in (32, 16, 8)]
+    _compare(grids, ref)
+
+
 def test_forward_batch_invariance_and_rebatch(cuda):
     """Images are independent: a batch of 5 gives the same rows as 5 single-image calls (bit-exact), and growing the
     batch re-plans the arena."""

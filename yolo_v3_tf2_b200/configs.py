@@ -63,8 +63,11 @@ def head_layers(filters, grid_size):
             {"type": "yolo", "grid_size": grid_size, "jitter": 0.3}]
 
 
-def yolov3_config():
-    """Returns (model_config dict in the reference's model.yaml schema, {layers_config_file: layers_config list})."""
+def yolov3_config(thin_heads=False):
+    """Returns (model_config dict in the reference's model.yaml schema, {layers_config_file: layers_config list}).
+    ``thin_heads``: the wiring of config/models/yolov3/model_thin_heads.yaml instead of model.yaml -- same layer files,
+    but the backbone taps layers 36 / 61 (the 3x3 convs BEFORE their shortcut adds), every neck exposes its last two
+    layers and the consumers pick them with negative / positive entry_index values."""
     files = {
         "builtin/yolov3/backbone.yaml": backbone_layers(),
         "builtin/yolov3/neck0.yaml": neck_layers(512, None),
@@ -87,6 +90,16 @@ def yolov3_config():
         {"name": "neck2", "inputs": src(("neck1", 0), ("backbone", 0)), "layers_config_file": "builtin/yolov3/neck2.yaml", "outputs_layers": [-1]},
         {"name": "head2", "inputs": src(("neck2", 0)), "layers_config_file": "builtin/yolov3/head2.yaml", "outputs_layers": [-1]},
     ]
+    if thin_heads:   # config/models/yolov3/model_thin_heads.yaml:5-83
+        subs = [
+            {"name": "backbone", "layers_config_file": "builtin/yolov3/backbone.yaml", "outputs_layers": [36, 61, -1]},
+            {"name": "neck0", "inputs": src(("backbone", 2)), "layers_config_file": "builtin/yolov3/neck0.yaml", "outputs_layers": [-2, -1]},
+            {"name": "head0", "inputs": src(("neck0", -1)), "layers_config_file": "builtin/yolov3/head0.yaml", "outputs_layers": [-1]},
+            {"name": "neck1", "inputs": src(("backbone", 1), ("neck0", -2)), "layers_config_file": "builtin/yolov3/neck1.yaml", "outputs_layers": [-2, -1]},
+            {"name": "head1", "inputs": src(("neck1", 1)), "layers_config_file": "builtin/yolov3/head1.yaml", "outputs_layers": [-1]},
+            {"name": "neck2", "inputs": src(("neck1", 0), ("backbone", 0)), "layers_config_file": "builtin/yolov3/neck2.yaml", "outputs_layers": [-2, -1]},
+            {"name": "head2", "inputs": src(("neck2", 1)), "layers_config_file": "builtin/yolov3/head2.yaml", "outputs_layers": [-1]},
+        ]
     model = {"decay_factor": 0.0005, "output_stage": "head", "grid_sizes": [13, 26, 52], "sub_models_configs": subs}
     return model, files
 

@@ -263,9 +263,10 @@ class ParseModel:
                                         layer_lists=files)
 
     @staticmethod
-    def builtin_yolov3(nclasses):
-        """Darknet-53 YOLOv3 from the built-in description (identical graph to config/models/yolov3/model.yaml)."""
+    def builtin_yolov3(nclasses, thin_heads=False):
+        """Darknet-53 YOLOv3 from the built-in description (identical graph to config/models/yolov3/model.yaml, or to
+        config/models/yolov3/model_thin_heads.yaml with ``thin_heads=True``)."""
         from .. import configs
-        model, files = configs.yolov3_config()
+        model, files = configs.yolov3_config(thin_heads)
         return ParseModel().build_model(None, model["sub_models_configs"], model["output_stage"], nclasses=nclasses,
                                         layer_lists=files)
