@@ -3,6 +3,8 @@
 config 4 = decode + NMS only at batch 512 with the score / IoU threshold sweep, config 5 = custom-class heads at
 batch 128).  CUDA events on the launching stream, warm-up first, inputs larger than L2.  Parity of the same cases is in
 tests/ (test_decode_nms_gpu.py, test_net_gpu.py); this file only measures.  Writes a markdown table to stdout."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import argparse
 import numpy as np
 import torch
@@ -118,7 +120,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     a = ap.parse_args()
-    print("# BASELINE.json configs[2..4] on one B200 (`python tools_bench_configs.py`, CUDA events)")
+    print("# BASELINE.json configs[2..4] on one B200 (`python tools/bench_configs.py`, CUDA events)")
     if a.only in ("", "full"):
         print("\n## Configs 2, 3, 5: whole path (forward + decode + NMS + gather, CUDA-graph replay, device-resident inputs)\n")
         print("| config | images / step | ms / step | images/s | forward only, ms (eager launches) | forward TFLOP/s | mean detections kept |")

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Micro-benchmark of single conv layers through the unit-test entry (GPU only).
-usage: [Y3_DBG=n] python tools_bench_conv.py"""
+usage: [Y3_DBG=n] python tools/bench_conv.py"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import numpy as np, torch
 from yolo_v3_tf2_b200 import _lib
 ctx = _lib.context()

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Measurements for the SURVEY section 8 'next' rows on a B200 (GPU only): GPU pre-processing (f-2), YOLOv3-tiny incl. its
 maxpool kernel (f-3), evaluation counters (f-4).  Prints a markdown table (committed under profiles/)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import json
 import numpy as np
 import torch

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """NMS / decode micro-benchmark on the bench workload (Keras-default init: every box passes the score threshold) and on
 sparse synthetic scores.  GPU only; profiling aid."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import numpy as np, torch
 import yolo_v3_tf2_b200 as y3
 from yolo_v3_tf2_b200 import configs

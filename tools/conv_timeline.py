@@ -2,7 +2,9 @@
 """In-kernel timeline of single conv layers (CTA-pair kernel) from per-CTA %globaltimer stamps (y3_dbg_timestamps).
 Prints, per layer, the time from the earliest CTA entry to each milestone (min / median / max over CTAs), so the fixed
 cost of a launch (prologue, first operand latency, tail, store drain, teardown) can be read off directly.
-usage: python tools_conv_timeline.py        (GPU only; profiling aid)"""
+usage: python tools/conv_timeline.py        (GPU only; profiling aid)"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import numpy as np, torch
 from yolo_v3_tf2_b200 import _lib
 ctx = _lib.context()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs on the GPU box (under gpurun): default bench, then the ncu launch list, the DRAM traffic of one forward pass and
 # one full capture of the top kernels.  Every ncu pass follows a plain run of the same command that exited 0.
-# usage: bash tools_gpu_profile.sh <tag>
+# usage: bash tools/gpu_profile.sh <tag>
 set -u
 TAG=${1:-rX}
 mkdir -p gpurun_out

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Reads an .ncu-rep (captured with --set full --import-source on) and prints, per kernel: headline metrics and the
 stall-sample breakdown of the warp roles, identified by the barrier/TMA/MMA instructions around them."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout

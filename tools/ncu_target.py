@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Tiny target for ncu: two forward passes (+ decode + NMS) of the bench workload; profile the second one.
-usage: python tools_ncu_target.py [batch] [size]"""
+usage: python tools/ncu_target.py [batch] [size]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import sys
 import torch
 import yolo_v3_tf2_b200 as y3

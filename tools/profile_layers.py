@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Per-layer device times and achieved TFLOP/s of one forward pass (profiling aid; GPU only).
-usage: python tools_profile_layers.py [batch] [size]"""
+usage: python tools/profile_layers.py [batch] [size]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import sys
 import numpy as np
 import torch

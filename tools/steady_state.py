@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """How does the step time evolve over a few seconds of continuous load (power capping)?  Prints the mean step time and
-the SM clock per window of 50 steps.  GPU only; profiling aid.  usage: python tools_steady_state.py [steps] [sync_every]"""
+the SM clock per window of 50 steps.  GPU only; profiling aid.  usage: python tools/steady_state.py [steps] [sync_every]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import subprocess, sys, time
 import torch
 import yolo_v3_tf2_b200 as y3

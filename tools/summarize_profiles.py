@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Turns gpurun_out/<tag>_launches.csv (+ optional .ncu-rep files) into the tracked summaries under profiles/.
-usage: python tools_summarize_profiles.py <tag> [<out-name>]"""
+usage: python tools/summarize_profiles.py <tag> [<out-name>]"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import collections
 import csv
 import io

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
 """Does UMMA accept row-shifted descriptors into a TMA-swizzled tile? (GPU only)"""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import numpy as np, torch
 from yolo_v3_tf2_b200 import _lib
 ctx = _lib.context(); lib = _lib.lib()

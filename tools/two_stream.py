@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Experiment: one batch of 64 as a single forward pass vs two half batches on two CUDA streams (their layer kernels
 overlap at the tails).  GPU only; profiling aid."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))   # repo root
 import sys
 import torch
 import yolo_v3_tf2_b200 as y3
