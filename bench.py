@@ -39,17 +39,20 @@ def conv_flops(model, H, W):
     return fl, launches
 
 
-def conv_traffic_bytes(size, batch):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one forward pass, from the newest committed
-    ncu capture (profiles/*_traffic.json, taken at 416^2 batch 64); None for any other workload."""
-    if size != 416 or batch != 64:
-        return None
-    import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), key=os.path.getmtime)
-    if not files:
-        return None
-    d = json.load(open(files[-1]))
-    return d["dram_bytes_read"] + d["dram_bytes_write"]
+# DRAM traffic of the conv launches of one forward pass: ONE named ncu capture, tied to the commit it was taken at
+# (tools/gpu_profile.sh + tools/summarize_profiles.py write it); not "whichever file is newest".
+TRAFFIC_CAPTURE = os.path.join("profiles", "r2_traffic.json")
+
+
+def conv_traffic(size, batch):
+    """(bytes, provenance) from TRAFFIC_CAPTURE when it was taken on this workload, else (None, reason)."""
+    path = os.path.join(ROOT, TRAFFIC_CAPTURE)
+    if not os.path.exists(path):
+        return None, f"{TRAFFIC_CAPTURE} not present"
+    d = json.load(open(path))
+    if d.get("size", 416) != size or d.get("batch", 64) != batch:
+        return None, f"{TRAFFIC_CAPTURE} was captured at {d.get('size', 416)}^2 batch {d.get('batch', 64)}"
+    return d["dram_bytes_read"] + d["dram_bytes_write"], f"{TRAFFIC_CAPTURE} (ncu capture at commit {d.get('commit', '?')})"
 
 
 class ClockSampler:
@@ -142,6 +145,7 @@ def run_reference(args, rank, world):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.size, args.batch), "images_per_gpu": args.batch,
+                       "images_per_step": sample_b,
                        "note": f"reference arm: CPU restatement of the reference (TensorFlow 2.8.1 is not installable here), "
                                f"each step is a bounded sample of {sample_b} images of that workload"},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
@@ -157,8 +161,16 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (weak scaling)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: this many images per step in total, split evenly over the ranks "
+                         "(BASELINE config 3: --size 608 --global-batch 256)")
     ap.add_argument("--size", type=int, default=416)
+    ap.add_argument("--input", default="u8", choices=["u8", "f32"],
+                    help="u8: uint8 images, x/255 inside the stem conv (the serving input, inference.py:157-158); "
+                         "f32: float32 images in [0,1] (the Keras model's own input)")
+    ap.add_argument("--settle-seconds", type=float, default=2.0,
+                    help="untimed steady load after the W warm-up steps so the SM clock has settled (reported as settle_steps)")
     ap.add_argument("--ref-batch", type=int, default=8,
                     help="images per step of the CPU reference arm (8 keeps all host cores busy; a step is ~0.5 s on 16 cores)")
     ap.add_argument("--cpu-baseline-images", type=int, default=96,
@@ -182,6 +194,7 @@ def main():
     import torch.distributed as dist
     import yolo_v3_tf2_b200 as y3
     from yolo_v3_tf2_b200 import configs, distributed as y3dist
+    from yolo_v3_tf2_b200.core.yolo_nms import nms_padded
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
@@ -191,72 +204,46 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B, S = args.batch, args.size
+    S = args.size
+    strong = args.global_batch > 0
+    if strong:
+        lo, hi = y3dist.shard_range(args.global_batch, rank, world)
+        B = hi - lo
+    else:
+        B = args.batch
+    K = args.steps
+    u8 = args.input == "u8"
     model = y3.ParseModel.builtin_yolov3(NCLASSES).init_weights("keras", seed=0)
     anchors = configs.coco_anchors()
     det = y3.Detector(model, anchors, NCLASSES, yolo_max_boxes=100, nms_iou_threshold=0.5, nms_score_threshold=0.1)
     flops_img, launches_fwd = conv_flops(model, S, S)
-
-    # synthetic inputs: per-rank seed = global image index block; a few rotating device buffers + pinned host copies
-    nbuf = 3
-    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    host = [torch.rand((B, S, S, 3), generator=gen, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
-    xs = [h.to(dev) for h in host]
     mx = det.max_boxes
 
-    from yolo_v3_tf2_b200.core.yolo_nms import nms_padded
-    from yolo_v3_tf2_b200.inference import gather_detections_batched
+    # synthetic inputs: per-rank seed; a few rotating device buffers + pinned host copies
+    nbuf = 3
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    if u8:
+        host = [torch.randint(0, 256, (B, S, S, 3), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+    else:
+        host = [torch.rand((B, S, S, 3), generator=gen, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    xs = [h.to(dev) for h in host]
+    in_bytes = host[0].numel() * host[0].element_size()
 
     no_gather = os.environ.get("Y3_BENCH_NO_GATHER") == "1"   # diagnosis only: N > 1 without the NCCL gather
-
-    def step(x):
-        """public-API step: local detections, then (N > 1) the NCCL gather of the fixed-size records"""
-        local = det.detections(x)
-        if world > 1 and not no_gather:
-            y3dist.gather_detections(*local)
-        return local
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing (value) ----------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    # W untimed warm-up steps as asked, and never fewer than 20: a fresh process needs a few hundred milliseconds of load
-    # before the SM clock has settled (short runs measured 10 % low in the first timed loop otherwise)
-    nwarm = max(args.warmup, 3) if args.ncu else max(args.warmup, 20)
-    t_w = time.perf_counter()
-    for i in range(nwarm):
-        step(xs[i % nbuf])
-    sync_all()
-    # ... then about 2 s of steady load: the first CUDA process on a fresh box needs that long before its clocks settle
-    # (the first nwarm steps mostly pay one-time initialisation, so the step time is taken from a second batch of 20)
-    t_w = time.perf_counter()
-    for i in range(0 if args.ncu else 20):
-        step(xs[i % nbuf])
-    sync_all()
-    dt_w = max(time.perf_counter() - t_w, 1e-3)
-    nwarm += 0 if args.ncu else 20
-    extra = 0 if args.ncu else min(2000, int(2.0 / dt_w) * 20)
-    if world > 1:   # every rank must issue the same number of collectives
-        tw = torch.tensor([extra], dtype=torch.int64, device=dev)
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        extra = int(tw.item())
-    for i in range(extra):
-        step(xs[i % nbuf])
-    nwarm += extra
-    sync_all()
-    # The timed steps call the public serving entry point Detector.detections_graphed(): the ~80 launches of a step are
-    # replayed from a CUDA graph, so the number does not depend on how fast this box's host can issue launches (the
-    # eager loop measured anything between 5.3 and 7.9 ms/step on different boxes for a 5.4 ms GPU step).
+    # The timed steps call the public serving entry point Detector.detections_graphed(): the launches of a step are
+    # replayed from a CUDA graph, so the number does not depend on how fast this box's host can issue launches.
     def gstep(x):
         if args.ncu:
-            local = det.detections(x)
+            local = det.detections(x, packed=(world > 1))
             if world > 1 and not no_gather:
-                y3dist.gather_detections(*local)
-            return local
+                y3dist.gather_packed(local[4])
+            return local[:4]
         # static_input: the loop rotates over a fixed set of device input buffers, one graph per buffer reads it in place
         if world > 1 and not no_gather:
             local = det.detections_graphed(x, packed=True, static_input=True)   # records packed inside the graph
@@ -264,12 +251,35 @@ def main():
             return local[:4]
         return det.detections_graphed(x, static_input=True)
 
-    for i in range(3):
+    # ---------------- warm-up: exactly the W steps asked for, then a separately reported settle phase ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    W = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
+    for i in range(W):
         gstep(xs[i % nbuf])
     sync_all()
+    # settle: a fresh process needs ~2 s of steady load before the SM clock / power state stops moving (the first timed
+    # loop measured 10-30 % low otherwise).  Not counted as warm-up steps; reported as settle_steps.
+    settle = 0
+    if not args.ncu and args.settle_seconds > 0:
+        t0 = time.perf_counter()
+        for i in range(10):
+            gstep(xs[i % nbuf])
+        sync_all()
+        dt10 = max(time.perf_counter() - t0, 1e-4)
+        settle = 10 + min(4000, int(args.settle_seconds / dt10 * 10))
+        if world > 1:   # every rank must issue the same number of collectives
+            tw = torch.tensor([settle], dtype=torch.int64, device=dev)
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            settle = int(tw.item())
+        for i in range(settle - 10):
+            gstep(xs[i % nbuf])
+        sync_all()
+
+    # ---------------- device-resident timing (value) ----------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(K):
         gstep(xs[i % nbuf])
     e1.record()
     sync_all()
@@ -278,51 +288,58 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max / 1e3)
+    value = world * B * K / (ms_max / 1e3)
 
-    # roofline of the conv stack: the forward pass alone (75 conv launches, also replayed from a graph), timed with CUDA
-    # events for the same number of steps right after the timed region, same clocks / power state
-    fx = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)
-    fx.copy_(xs[0])
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        fouts = model(fx, padded=True)
-    torch.cuda.current_stream().wait_stream(side)
-    class _Eager:
-        def replay(self):
+    # ---------------- roofline: forward pass / decode / NMS, timed INTERLEAVED with the step ----------------
+    # Every iteration replays the whole step and then, between their own event pairs, the forward pass alone, the
+    # decode alone and the NMS alone (each its own small CUDA graph on this step's data).  All four are measured under the
+    # same clocks and power state, so forward_ms <= step_ms holds by construction and nothing is subtracted.
+    roof = {}
+    if not args.ncu:
+        fx = xs[0].clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fouts = model(fx, padded=True)
+            dense = model(fx)
+            dec_c = y3.yolo_decode(fouts, anchors, NCLASSES, compact=True)
+            dec_f = y3.yolo_decode(dense, anchors, NCLASSES)
+            nms_padded(dec_c[0], dec_c[3], mx, 0.5, 0.1)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g_fwd, g_decc, g_decf, g_nms = (torch.cuda.CUDAGraph() for _ in range(4))
+        with torch.cuda.graph(g_fwd):
             model(fx, padded=True, outs=fouts)
-
-    if args.ncu:
-        fgraph = _Eager()
-    else:
-        fgraph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(fgraph):
-            model(fx, padded=True, outs=fouts)
-    for i in range(3):
-        fgraph.replay()
-    torch.cuda.synchronize()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(args.steps):
-        fx.copy_(xs[i % nbuf], non_blocking=True)     # a different input every pass, as in the timed steps
-        fgraph.replay()
-    f1.record()
-    torch.cuda.synchronize()
-    copy_ms = 0.0
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for i in range(args.steps):
-        fx.copy_(xs[i % nbuf], non_blocking=True)
-    c1.record()
-    torch.cuda.synchronize()
-    copy_ms = c0.elapsed_time(c1)
-    fwd_ms = (f0.elapsed_time(f1) - copy_ms) / args.steps
-    achieved_tflops = flops_img * B / (fwd_ms / 1e3) / 1e12
+        with torch.cuda.graph(g_decc):
+            dec_c = y3.yolo_decode(fouts, anchors, NCLASSES, compact=True)
+        with torch.cuda.graph(g_decf):
+            dec_f = y3.yolo_decode(dense, anchors, NCLASSES)
+        with torch.cuda.graph(g_nms):
+            nms_out = nms_padded(dec_c[0], dec_c[3], mx, 0.5, 0.1)
+        parts = {"step": None, "forward": g_fwd, "decode_fused": g_decc, "decode_full": g_decf, "nms": g_nms}
+        evs = {k: [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+               for k in parts}
+        for i in range(3):
+            for g in (g_fwd, g_decc, g_decf, g_nms):
+                g.replay()
+        torch.cuda.synchronize()
+        for i in range(K):
+            for name, g in parts.items():
+                a, b = evs[name][i]
+                a.record()
+                if g is None:
+                    det.detections_graphed(xs[i % nbuf], packed=(world > 1 and not no_gather), static_input=True)
+                else:
+                    g.replay()
+                b.record()
+        torch.cuda.synchronize()
+        roof = {k: sum(a.elapsed_time(b) for a, b in v) / K for k, v in evs.items()}
+    fwd_ms = roof.get("forward", float("nan"))
+    achieved_tflops = flops_img * B / (fwd_ms / 1e3) / 1e12 if roof else None
 
     # ---------------- end to end through the public API with host buffers (e2e) ----------------
     out_host = [torch.empty((B, mx * 6 + 1), dtype=torch.float32).pin_memory() for _ in range(2)]
-    xin = [torch.empty((B, S, S, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+    xin = [torch.empty_like(xs[0]) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
 
@@ -346,8 +363,7 @@ def main():
             main_stream.wait_event(ready[cur])
             # the public serving call: the whole step replayed from a CUDA graph (one launch), then the NCCL gather
             if args.ncu:
-                ob, oc, os_, nv = det.detections(xin[cur])
-                rec = y3dist.pack_detections(ob, oc, os_, nv)
+                rec = det.detections(xin[cur], packed=True)[4]
             else:
                 rec = det.detections_graphed(xin[cur], packed=True, static_input=True)[4]
             if world > 1 and not no_gather:
@@ -360,7 +376,7 @@ def main():
     sync_all()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
-    e2e_loop(args.steps)
+    e2e_loop(K)
     s1.record()
     sync_all()
     e2e_ms = s0.elapsed_time(s1)
@@ -368,7 +384,7 @@ def main():
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+    e2e_value = world * B * K / (float(t.item()) / 1e3)
 
     if rank == 0:
         peaks = {}
@@ -377,31 +393,62 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        hbm = float(peaks.get("hbm_gbs", 6500.0))
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.5 TB/s"
+        traffic, traffic_src = conv_traffic(S, B)
+        N = 3 * sum((S // s) ** 2 for s in (32, 16, 8))
+        F = 5 + NCLASSES
         line = {
             "metric": f"images/sec ({S}^2, backbone+decode+NMS)", "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": nwarm, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(S, B), "images_per_gpu": B, "l2": "inputs rotate over 3 device buffers; each step streams a ~1 GB "
-                                                  "activation arena (>> 126 MB L2) so no step starts with a warm L2"},
+            "steps": K, "warmup": W, "settle_steps": settle, "ms_per_step": ms_max / K,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_name(S, B), "images_per_gpu": B, "images_per_step": B * world,
+                       "input": ("uint8 [B,S,S,3] images, x/255 (core/load_tfrecords.py:46) inside the stem conv, bit-identical "
+                                 "to feeding float32" if u8 else "float32 [B,S,S,3] in [0,1]"),
+                       "l2": "inputs rotate over 3 device buffers; each step streams a ~1 GB activation arena "
+                             "(>> 126 MB L2) so no step starts with a warm L2"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * S * S * 3 * 4,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": B * (mx * 6 + 1) * 4,
                     "note": "Detector.detections_graphed() (the step replayed from a CUDA graph) on pinned host batches, "
                             "double-buffered H2D on a copy stream, detections copied back to pinned host memory every step"},
-            "gpu_launches": args.steps * (launches_fwd + 3),
-            "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak, "traffic": conv_traffic_bytes(S, B), "peak_source": peak_src,
-                         "kernel": f"tcgen05 implicit-GEMM conv kernels ({launches_fwd} launches/step = the whole forward "
-                                   "pass, timed with CUDA events inside the timed loop; achieved = algorithmic conv FLOPs of "
-                                   "one batch / that time); traffic = DRAM bytes of those launches from the committed ncu "
-                                   "capture (profiles/), algorithmic bytes = 190 MB/img",
-                         "forward_ms": fwd_ms, "flops_per_step": flops_img * B},
+            "gpu_launches": K * (launches_fwd + 3),
         }
+        if roof:
+            line["roofline"] = {
+                "bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved_tflops / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": f"tcgen05 implicit-GEMM conv kernels (the whole forward pass: {launches_fwd} conv layers), "
+                          "replayed from its own CUDA graph between CUDA events right after each timed-style step "
+                          "(interleaved, same clocks); achieved = algorithmic conv FLOPs of one batch / that time; "
+                          "algorithmic bytes = 190 MB/img",
+                "forward_ms": fwd_ms, "step_ms_interleaved": roof["step"], "flops_per_step": flops_img * B}
+            dec_bytes = 2 * N * F * 4 * B                      # read N*F*4, write N*(4+1+C)*4 per image
+            decc_bytes = (N * F * 4 + N * (16 + 4 + 8)) * B    # fused form: boxes + scores + int64 class ids out
+            nms_bytes = (N * 20 + (mx + 1) * 4) * B
+            line["roofline_decode"] = {
+                "bound": "hbm", "achieved": dec_bytes / (roof["decode_full"] / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": dec_bytes / (roof["decode_full"] / 1e3) / 1e9 / hbm, "ms": roof["decode_full"],
+                "algorithmic_bytes": dec_bytes, "peak_source": hbm_src,
+                "kernel": "decode_kernel as the reference's yolo_decode (boxes + confidence + class_probs written)"}
+            line["roofline_decode_fused"] = {
+                "bound": "hbm", "achieved": decc_bytes / (roof["decode_fused"] / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": decc_bytes / (roof["decode_fused"] / 1e3) / 1e9 / hbm, "ms": roof["decode_fused"],
+                "algorithmic_bytes": decc_bytes,
+                "kernel": "decode_kernel as run inside the step (compact: boxes + scores + class ids; probabilities are "
+                          "never written because NMS does not read them)"}
+            line["roofline_nms"] = {
+                "bound": "latency", "achieved": nms_bytes / (roof["nms"] / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": nms_bytes / (roof["nms"] / 1e3) / 1e9 / hbm, "ms": roof["nms"], "algorithmic_bytes": nms_bytes,
+                "images_per_s": B / (roof["nms"] / 1e3),
+                "kernel": "nms_kernel (one CTA per image; sort + IoU bitmask chunks: latency-bound, 212 940 B/img)"}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             nimg = args.cpu_baseline_images
-            xc = torch.cat([host[i % nbuf] for i in range((nimg + B - 1) // B)])[:nimg].numpy()
+            xc = torch.cat([host[i % nbuf] for i in range((nimg + B - 1) // B)])[:nimg]
+            xc = (xc.float() / 255.0).numpy() if u8 else xc.numpy()
             cpu_reference_step(model, anchors, xc[:1], cores)   # warm-up
             t0 = time.perf_counter()
             for i0 in range(0, nimg, 8):                       # 8 images at a time bounds the oracle's memory

@@ -81,6 +81,10 @@ typedef struct {
 const char* y3_last_error(void);
 int y3_version(void);
 
+/* CRC-32C (Castagnoli) of data[0..n), continuing from crc (0 to start): host helper of the TensorFlow checkpoint
+ * reader / writer that stands in for model.load_weights / save_weights (inference.py:102, train.py:93-104). */
+uint32_t y3_crc32c(uint32_t crc, const void* data, int64_t n);
+
 /* device < 0 creates a planning-only context (no CUDA calls; usable on a CPU-only machine for y3_net_plan_*). */
 int y3_ctx_create(int device, y3_ctx** out);
 void y3_ctx_destroy(y3_ctx* ctx);
@@ -117,6 +121,13 @@ int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n
 int y3_net_forward_pitched(y3_net* net, const float* x, int B, float* const* outs, const int* out_pitch, int n_outs,
                            void* stream);
 
+/* Same for a uint8 image x [B,H,W,3] already at the network resolution: computes the network on float32(x) / 255, the
+ * serving input of the reference (inference.py:157-158 resize(...) / 255, core/load_tfrecords.py:46), bit-identical to
+ * y3_net_forward_pitched on that float tensor, with a quarter of the input bytes.  out_pitch may be NULL (dense
+ * outputs as y3_net_forward). */
+int y3_net_forward_u8(y3_net* net, const uint8_t* x, int B, float* const* outs, const int* out_pitch, int n_outs,
+                      void* stream);
+
 /* Profiling aid: same as y3_net_forward with a CUDA event between kernels; after the call ms_host[i] is the device time
  * of kernel i and layer_host[i] the layer index it implements (n_steps = y3_net_num_steps). Synchronises the stream. */
 int y3_net_num_steps(y3_net* net);
@@ -124,7 +135,9 @@ int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs,
                          float* ms_host, int32_t* layer_host, int n_steps);
 
 /* grids[s]: [B,gh[s],gw[s],3,5+C] fp32; anchors_host: 3x3x2 fp32 (scale, anchor, (w,h)) image fractions.
- * bboxes [B,N,4], conf [B,N,1], probs [B,N,C]; scores [B,N] and class_idx [B,N] (int64) optional (both or neither). */
+ * bboxes [B,N,4], conf [B,N,1], probs [B,N,C]; scores [B,N] and class_idx [B,N] (int64) optional (both or neither).
+ * "Compact" decode: conf and probs may both be NULL when scores / class_idx are given -- what yolo_nms (core/yolo_nms.py:
+ * 18-33) needs of the decode output is boxes, scores and class ids only. */
 int y3_decode(y3_ctx* ctx, const float* const* grids, const int* gh, const int* gw, int n_scales,
               const float* anchors_host, int B, int nclasses, float* bboxes, float* conf, float* probs, float* scores,
               int64_t* class_idx, void* stream);
@@ -137,7 +150,11 @@ int y3_decode_pitched(y3_ctx* ctx, const float* const* grids, const int* gh, con
 int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, int N, int nclasses, float* scores,
                     int64_t* class_idx, void* stream);
 
-/* selected [B,max_boxes] int32 zero padded, num_valid [B] int32, status [B] int32 (0 ok, 1 = kept-list overflow) */
+/* tf.image.non_max_suppression_padded(pad_to_max_output_size=True) as called at core/yolo_nms.py:26-33.
+ * selected [B,max_boxes] int32 zero padded, num_valid [B] int32, status [B] int32 (0 ok, 1 = kept-list overflow).
+ * Preconditions (Y3_ERR_UNSUPPORTED otherwise where checkable): max_boxes <= 768; iou_thr > 0 (TF suppresses on
+ * iou >= thr only where iou > 0); boxes are canonical corners (x1 <= x2, y1 <= y2) -- TF's whole-batch coordinate
+ * swap keyed on the first box of the first image is NOT reproduced (yolo_decode always emits canonical boxes). */
 int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, int max_boxes, float iou_thr,
            float score_thr, int32_t* selected, int32_t* num_valid, int32_t* status, void* stream);
 
@@ -161,6 +178,12 @@ int y3_preprocess(y3_ctx* ctx, const void* image_descs_dev, int B, int dst_h, in
 int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_idx, const float* scores,
                          const int32_t* selected, const int32_t* num_valid, int B, int N, int max_boxes,
                          float* out_boxes, int64_t* out_classes, float* out_scores, void* stream);
+
+/* Same, additionally writing the packed float32 records [B, max_boxes*6 + 1] (x1,y1,x2,y2,score,class per slot, then
+ * num_valid) that the multi-GPU detection gather sends (packed may be NULL). */
+int y3_gather_detections_packed(y3_ctx* ctx, const float* bboxes, const int64_t* class_idx, const float* scores,
+                                const int32_t* selected, const int32_t* num_valid, int B, int N, int max_boxes,
+                                float* out_boxes, int64_t* out_classes, float* out_scores, float* packed, void* stream);
 
 /* One fused conv layer on bf16 NHWC views (unit-test entry; the net executor runs the same kernel).
  * x: [B,H,W,Cin] bf16 with pixel stride x_stride elements.  w_packed: [Cout_pad][k][k][Cin] bf16 (Cout_pad = Cout

@@ -221,3 +221,45 @@ def test_yolo_nms_layer_matches_reference_api(cuda):
     assert np.array_equal(bb.cpu().numpy(), ref[0][0][ref[3][0][:n]])
     assert np.array_equal(cc.cpu().numpy(), ref[1][0][ref[3][0][:n]])
     assert np.array_equal(ss.cpu().numpy(), ref[2][0][ref[3][0][:n]])
+
+
+@pytest.mark.parametrize("C", [80, 37])
+def test_compact_decode_and_packed_gather(cuda, C):
+    """The fused pipeline's decode writes only boxes / scores / class ids (conf and probs are not needed by yolo_nms,
+    core/yolo_nms.py:18-33) and its gather also emits the packed records of distributed.pack_detections: both must
+    equal the full-output calls bit for bit."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    from yolo_v3_tf2_b200.core.yolo_nms import nms_padded
+    from yolo_v3_tf2_b200.inference import gather_detections_batched
+    from yolo_v3_tf2_b200.distributed import pack_detections
+    rng = np.random.default_rng(C)
+    B = 3
+    grids = [torch.from_numpy(rng.normal(0, 1.5, (B, g, g, 3, 5 + C)).astype(np.float32)).cuda() for g in (13, 26, 52)]
+    anchors = configs.coco_anchors()
+    full = y3.yolo_decode(grids, anchors, C, with_scores=True)
+    comp = y3.yolo_decode(grids, anchors, C, compact=True)
+    assert comp[1] is None and comp[2] is None
+    for k in (0, 3, 4):
+        assert torch.equal(full[k], comp[k])
+    sel, nv, st = nms_padded(comp[0], comp[3], 100, 0.5, 0.1)
+    ob, oc, os_ = gather_detections_batched(comp[0], comp[4], comp[3], sel, nv)
+    pb, pc, ps, rec = gather_detections_batched(comp[0], comp[4], comp[3], sel, nv, packed=True)
+    assert torch.equal(ob, pb) and torch.equal(oc, pc) and torch.equal(os_, ps)
+    assert torch.equal(rec, pack_detections(ob, oc, os_, nv))
+    assert int(nv.min()) > 0
+
+
+def test_nms_rejects_unsupported_parameters(cuda):
+    """parameters the kernel cannot honour are refused instead of returning truncated results."""
+    import torch
+    from yolo_v3_tf2_b200 import _lib
+    from yolo_v3_tf2_b200.core.yolo_nms import nms_padded
+    b = torch.rand((1, 64, 4), device="cuda")
+    s = torch.rand((1, 64), device="cuda")
+    with pytest.raises(_lib.Y3Unsupported, match="yolo_max_boxes"):
+        nms_padded(b, s, 769, 0.5, 0.1)
+    with pytest.raises(_lib.Y3Unsupported, match="nms_iou_threshold"):
+        nms_padded(b, s, 100, 0.0, 0.1)
+    nms_padded(b, s, 768, 0.5, 0.1)

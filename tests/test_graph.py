@@ -209,8 +209,9 @@ def test_planner_through_c_abi():
 
 
 def test_planner_flat_opt_in():
-    """Y3_FLAT=1 (read when the library loads, hence the subprocess): all 32 3x3 stride-1 convs behind a 1x1 conv run the
-    flat-patch kernel on a zero-haloed input."""
+    """Y3_FLAT=1 (an experiment knob of the profiling library liby3b200_prof.so, read when the library loads, hence
+    the subprocess): all 32 3x3 stride-1 convs behind a 1x1 conv run the flat-patch kernel on a zero-haloed input.
+    The release library ignores the environment."""
     import os
     import subprocess
     import sys
@@ -224,8 +225,12 @@ def test_planner_flat_opt_in():
         "        assert l.ksize == 3 and l.stride == 1 and L[l.src0 - 1]['padded'] == 1\n"
     )
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, Y3_FLAT="1", PYTHONPATH=root)
+    env = dict(os.environ, Y3_FLAT="1", Y3_PROF_LIB="1", PYTHONPATH=root)
     subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=root)
+    release = code.replace("== 32 and sum(1 for l in L if l['padded']) == 32", "== 0 and sum(1 for l in L if l['padded']) == 0")
+    env = dict(os.environ, Y3_FLAT="1", PYTHONPATH=root)
+    env.pop("Y3_PROF_LIB", None)
+    subprocess.run([sys.executable, "-c", release], check=True, env=env, cwd=root)
 
 
 def test_planner_arena_no_live_overlap():

@@ -227,3 +227,73 @@ def test_reference_yaml_and_darknet_weights_roundtrip(cuda, tmp_path):
     a, b, c = m1(x), m2(x), m3(x)
     for k in range(3):
         assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k])
+
+
+@pytest.mark.parametrize("tiny", [False, True])
+def test_uint8_input_equals_float_input(cuda, tiny):
+    """uint8 serving input (reference inference.py:157-158 / core/load_tfrecords.py:46: resize(...) / 255): the stem
+    conv divides by 255 itself through a 256-entry table of (bf16 hi, bf16 lo) pairs; the logits are bit-identical to
+    feeding float32(x) / 255 -- for YOLOv3 (stride-1 tensor-core stem) and YOLOv3-tiny (16-filter stem stored as 32
+    channels, same kernel), dense and pitched outputs, and through the whole detector."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    from oracle import preprocess_oracle
+    model = (y3.ParseModel.builtin_yolov3_tiny(80) if tiny else y3.ParseModel.builtin_yolov3(80)).init_weights("variance", seed=5)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    xu = torch.randint(0, 256, (3, 96, 128, 3), dtype=torch.uint8, generator=g)
+    xu[0, :4] = 0
+    xu[1, -3:] = 255
+    # the float tensor the reference's pipeline would feed: numpy float32 division, as in the pre-processing oracle
+    xf = torch.from_numpy(xu.numpy().astype(np.float32) / np.float32(255))
+    a = model(xu.cuda())
+    b = model(xf.cuda())
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    ap = model(xu.cuda(), padded=True)
+    bp = model(xf.cuda(), padded=True)
+    for u, v in zip(ap, bp):
+        assert torch.equal(u, v)
+    # numpy uint8 goes the same way, and predict() keeps the dtype
+    c = model(xu.numpy())
+    for u, v in zip(a, c):
+        assert torch.equal(u, v)
+    anchors = configs.coco_anchors() if not tiny else configs.coco_anchors()[:2]
+    det = y3.Detector(model, anchors, 80, nms_score_threshold=0.05)
+    du = det.detections(xu.cuda())
+    df = det.detections(xf.cuda())
+    for u, v in zip(du, df):
+        assert torch.equal(u, v)
+    gu = det.detections_graphed(xu.cuda())
+    torch.cuda.synchronize()
+    for u, v in zip(du, gu):
+        assert torch.equal(u, v)
+
+
+def test_net_rebuild_keeps_captured_graphs_valid(cuda):
+    """growing the batch re-plans the net; the old net (arena, weights, tensor maps) must stay alive because a
+    CUDA graph captured on it still replays."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    model = y3.ParseModel.builtin_yolov3(80).init_weights("variance", seed=2)
+    det = y3.Detector(model, configs.coco_anchors(), 80, nms_score_threshold=0.05)
+    x2 = torch.rand((2, 96, 96, 3), device="cuda")
+    want2 = [t.clone() for t in det.detections(x2)]
+    g2 = [t.clone() for t in det.detections_graphed(x2)]
+    x5 = torch.rand((5, 96, 96, 3), device="cuda")
+    want5 = [t.clone() for t in det.detections(x5)]           # batch 5 > 2: the net is rebuilt
+    junk = [torch.full((64 << 20,), 7, dtype=torch.uint8, device="cuda") for _ in range(4)]   # reuse freed memory, if any
+    again2 = det.detections_graphed(x2)                        # replays the graph captured on the first net
+    torch.cuda.synchronize()
+    for a, b, c in zip(want2, g2, again2):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    for a, b in zip(want5, det.detections_graphed(x5)):
+        assert torch.equal(a, b)
+    del junk
+    # new weights reach every net, including the retired one the batch-2 graph replays on
+    model.init_weights("variance", seed=3)
+    fresh = [t.clone() for t in det.detections(x2)]
+    assert not torch.equal(fresh[0], want2[0])
+    for a, b in zip(fresh, det.detections_graphed(x2)):
+        assert torch.equal(a, b)

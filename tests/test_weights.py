@@ -62,10 +62,13 @@ def test_tf_checkpoint_roundtrip_object_based(tmp_path):
     m.save_weights(prefix)
     idx = tc.read_index(prefix + ".index")
     assert idx[""]["num_shards"] == 1 and idx[""]["endianness"] == 0
-    # sub-models backbone(7 convs), neck0(1), head0(2), neck1(1), head1(2): the first variable of head0's bias-only conv
+    # Keras numbers Model.layers by decreasing depth: backbone(7 convs)=0, neck0(1)=1, neck1(1)=2, head0(2)=3, head1(2)=4;
+    # head0's bias-only conv is the third layer with weights of sub-model 3
     assert "layer_with_weights-0/layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE" in idx
     assert "layer_with_weights-0/layer_with_weights-1/moving_variance/.ATTRIBUTES/VARIABLE_VALUE" in idx
-    assert "layer_with_weights-2/layer_with_weights-2/bias/.ATTRIBUTES/VARIABLE_VALUE" in idx
+    assert "layer_with_weights-3/layer_with_weights-2/bias/.ATTRIBUTES/VARIABLE_VALUE" in idx
+    assert idx["layer_with_weights-3/layer_with_weights-2/bias/.ATTRIBUTES/VARIABLE_VALUE"]["shape"] == [255]
+    assert idx["layer_with_weights-2/layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE"]["shape"] == [1, 1, 256, 128]
     e = idx["layer_with_weights-0/layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE"]
     assert e["shape"] == [3, 3, 3, 16] and e["dtype"] == 1 and e["size"] == 3 * 3 * 3 * 16 * 4
     for path in (prefix, prefix + ".index"):
@@ -78,6 +81,67 @@ def test_tf_checkpoint_roundtrip_object_based(tmp_path):
         y3.ParseModel.builtin_yolov3_tiny(3).load_weights(prefix)
     with pytest.raises(FileNotFoundError):
         y3.ParseModel.builtin_yolov3_tiny(80).load_weights(str(tmp_path / "missing.tf"))
+
+
+def test_keras_depth_order_of_sub_models():
+    """``layer_with_weights-<i>`` follows Model.layers, which Keras sorts by decreasing depth -- yolov3:
+    backbone, neck0, neck1, neck2, head0, head1, head2 (NOT the sub_models_configs order); inside a sub-model conv and
+    batch-normalization layers alternate."""
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import graph
+    for thin in (False, True):
+        g = y3.ParseModel.builtin_yolov3(80, thin_heads=thin).graph
+        slots = graph.keras_weight_slots(g)
+        order = {}
+        for ci, (i, jc, jb) in enumerate(slots):
+            order.setdefault(i, g.layers[g.conv_layers[ci]].sub_model)
+        assert [order[i] for i in sorted(order)] == ["backbone", "neck0", "neck1", "neck2", "head0", "head1", "head2"]
+        # the backbone: 52 convs each followed by its BN -> j = 0..103; heads: conv, bn, biased conv
+        assert slots[0] == (0, 0, 1) and slots[51] == (0, 102, 103)
+        assert slots[57] == (4, 0, 1) and slots[58] == (4, 2, None) and slots[74] == (6, 2, None)
+        assert slots[59] == (2, 0, 1)          # neck1's first conv (creation index 59) lives in sub-model 2
+    gt = y3.ParseModel.builtin_yolov3_tiny(80).graph
+    st = graph.keras_weight_slots(gt)
+    assert [s[0] for s in st] == [0] * 7 + [1, 3, 3, 2, 4, 4]
+
+
+def test_tf_checkpoint_handmade_fixture():
+    """tests/golden/tf_bundle_handmade.* was assembled byte by byte by tests/golden/make_tf_bundle_fixture.py, an
+    encoder that shares no code with yolo_v3_tf2_b200.tf_checkpoint (prefix-compressed keys with restart interval 4,
+    snappy-compressed blocks, a 9-block index with shortest-separator keys, a DT_STRING object-graph entry, Keras
+    depth-ordered variable names written out by hand).  The reader must return exactly the generator's arrays."""
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_tf_bundle_fixture as fx
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import tf_checkpoint as tc
+    idx = tc.read_index(fx.PREFIX + ".index")
+    assert len(idx) == 57 and idx[""]["num_shards"] == 1
+    assert idx["_CHECKPOINTABLE_OBJECT_GRAPH"]["dtype"] == 7
+    back = tc.read_checkpoint(fx.PREFIX)
+    assert "_CHECKPOINTABLE_OBJECT_GRAPH" not in back and int(back["save_counter" + fx.SUFFIX]) == 8
+    m = y3.ParseModel().build_model(None, fx.SMALL_MODEL["sub_models_configs"], "head", nclasses=fx.NCLASSES,
+                                    layer_lists=fx.SMALL_LAYERS)
+    m.load_weights(fx.PREFIX).expect_partial()
+    for p, (k, b, g, be, mu, v) in zip(m._params, fx.expected_params()):
+        np.testing.assert_array_equal(p.kernel, k)
+        if b is not None:
+            np.testing.assert_array_equal(p.bias, b)
+        else:
+            for got, want in ((p.gamma, g), (p.beta, be), (p.mean, mu), (p.var, v)):
+                np.testing.assert_array_equal(got, want)
+    # a corrupted tensor payload is caught by the per-tensor crc32c of the BundleEntryProto
+    import shutil, tempfile
+    d = tempfile.mkdtemp()
+    for suf in (".index", ".data-00000-of-00001"):
+        shutil.copy(fx.PREFIX + suf, os.path.join(d, "c" + suf))
+    raw = bytearray(open(os.path.join(d, "c.data-00000-of-00001"), "rb").read())
+    raw[100] ^= 0x40
+    open(os.path.join(d, "c.data-00000-of-00001"), "wb").write(bytes(raw))
+    with pytest.raises(ValueError, match="crc32c"):
+        tc.read_checkpoint(os.path.join(d, "c"))
 
 
 def test_tf_checkpoint_format_details(tmp_path):

@@ -63,8 +63,12 @@ if os.path.exists(tp):
                    f"{d.get('dram__bytes_write.sum', 0) / 1e6:.1f} | {d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 0):.1f} |")
     out.append("")
     import json
-    json.dump({"dram_bytes_read": rd, "dram_bytes_write": wr, "launches": len(per), "kernel_time_ms": tt / 1e6},
-              open(f"profiles/{name}_traffic.json", "w"))
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    rec = {"dram_bytes_read": rd, "dram_bytes_write": wr, "launches": len(per), "kernel_time_ms": tt / 1e6,
+           "size": 416, "batch": 64, "commit": commit, "capture": f"gpurun_out/{tag}_traffic.csv",
+           "command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum ... -k regex:conv_ "
+                      "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ncu"}
+    json.dump(rec, open(f"profiles/{name}_traffic.json", "w"), indent=1)
 
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",

@@ -7,7 +7,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liby3b200.so")
+# liby3b200.so is the release library (no environment knobs, no debug branches).  Measurement tools set Y3_PROF_LIB=1 to
+# load liby3b200_prof.so instead: the same sources compiled with -DY3_PROFILING (Y3_* experiment knobs, per-CTA
+# timestamps, kernel ablations).  Same ABI, same results with the knobs at their defaults.
+LIB_PATH = os.path.join(_HERE, "lib", "liby3b200_prof.so" if os.environ.get("Y3_PROF_LIB") == "1" else "liby3b200.so")
 
 Y3_OK, Y3_ERR_INVALID, Y3_ERR_UNSUPPORTED, Y3_ERR_CUDA, Y3_ERR_STATE = 0, 1, 2, 3, 4
 OP_CONV, OP_SHORTCUT, OP_UPSAMPLE, OP_CONCAT, OP_YOLO, OP_MAXPOOL = range(6)
@@ -41,6 +44,7 @@ _i64 = C.c_int64
 SIGNATURES = {
     "y3_last_error": (C.c_char_p, []),
     "y3_version": (_i, []),
+    "y3_crc32c": (C.c_uint32, [C.c_uint32, _p, _i64]),
     "y3_ctx_create": (_i, [_i, C.POINTER(_p)]),
     "y3_ctx_destroy": (None, [_p]),
     "y3_ctx_sm_count": (_i, [_p]),
@@ -54,6 +58,7 @@ SIGNATURES = {
     "y3_net_load_conv": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _f]),
     "y3_net_forward": (_i, [_p, _p, _i, C.POINTER(_p), _i, _p]),
     "y3_net_forward_pitched": (_i, [_p, _p, _i, C.POINTER(_p), C.POINTER(_i), _i, _p]),
+    "y3_net_forward_u8": (_i, [_p, _p, _i, C.POINTER(_p), C.POINTER(_i), _i, _p]),
     "y3_net_num_steps": (_i, [_p]),
     "y3_net_forward_timed": (_i, [_p, _p, _i, C.POINTER(_p), _i, _p, _p, _p, _i]),
     "y3_decode": (_i, [_p, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
@@ -61,6 +66,7 @@ SIGNATURES = {
     "y3_class_reduce": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "y3_nms": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
     "y3_gather_detections": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "y3_gather_detections_packed": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "y3_preprocess": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "y3_evaluate": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p, _p]),
     "y3_conv_block_n": (_i, [_i, _i]),

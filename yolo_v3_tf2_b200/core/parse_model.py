@@ -23,7 +23,10 @@ class Y3Model:
         self.nclasses = g.nclasses
         self.conv_shapes = g.conv_shapes()
         self._params = None       # list[weights_mod.ConvParams]
-        self._nets = {}           # (H, W) -> dict(handle, max_batch)
+        self._nets = {}           # (device, H, W) -> dict(handle, max_batch)
+        self._retired = []        # nets replaced by a larger-batch plan: kept alive until close(), because CUDA graphs
+                                  # captured on them (Detector.detections_graphed) hold raw pointers into their arena,
+                                  # weights and tensor maps
         self._descs = graph_mod.to_descs(g)
 
     # ---------------- weights ----------------
@@ -34,8 +37,8 @@ class Y3Model:
             if p.kernel.shape != (k, k, cin, cout) or p.has_bn != bn:
                 raise ValueError(f"conv parameters do not match the model: kernel {p.kernel.shape} vs {(k, k, cin, cout)}")
         self._params = list(params)
-        for key in list(self._nets):
-            self._upload(self._nets[key]["handle"])
+        for ent in list(self._nets.values()) + self._retired:
+            self._upload(ent["handle"])
 
     def set_weights(self, arrays):
         """Keras order: per conv layer [kernel, (bias)] followed by its BN layer's [gamma, beta, mean, variance]."""
@@ -77,7 +80,8 @@ class Y3Model:
             z = np.load(path)
             self.set_weights([z[f"arr_{i}"] for i in range(len(z.files))])
         elif tf_checkpoint.is_checkpoint(path):
-            self.set_params(tf_checkpoint.params_from_checkpoint(path, self.conv_shapes))
+            self.set_params(tf_checkpoint.params_from_checkpoint(path, self.conv_shapes,
+                                                                 graph_mod.keras_weight_slots(self.graph)))
         else:
             raise FileNotFoundError(f"{path}: neither a Darknet .weights file, an .npz, nor a TensorFlow checkpoint prefix "
                                     f"({path}.index not found)")
@@ -96,13 +100,7 @@ class Y3Model:
         from .. import tf_checkpoint
         if self._params is None:
             raise _lib.Y3Error("model has no weights yet")
-        g = self.graph
-        counts = []
-        for name in g.sub_model_names:
-            n = sum(1 for li in g.conv_layers if g.layers[li].sub_model == name)
-            if n:
-                counts.append(n)
-        names = tf_checkpoint.keras_variable_names(counts, self.conv_shapes)
+        names = tf_checkpoint.keras_variable_names(graph_mod.keras_weight_slots(self.graph), self.conv_shapes)
         tensors = {}
         for p, nm in zip(self._params, names):
             for key, arr in zip(nm, p.as_list()):
@@ -119,14 +117,14 @@ class Y3Model:
             _lib.check(lib.y3_net_load_conv(handle, i, *args, weights_mod.BN_EPS))
 
     def _net(self, H, W, B, device=None):
-        key = (int(H), int(W))
+        ctx = _lib.context(device)
+        key = (ctx.device, int(H), int(W))
         ent = self._nets.get(key)
         if ent is not None and ent["max_batch"] >= B:
             return ent
         lib = _lib.lib()
-        ctx = _lib.context(device)
         if ent is not None:
-            lib.y3_net_destroy(ent["handle"])
+            self._retired.append(ent)   # never freed while a captured graph may still replay on it
         h = C.c_void_p()
         _lib.check(lib.y3_net_create(ctx.handle, self._descs, len(self._descs), int(H), int(W), int(B),
                                      int(self.nclasses), C.byref(h)))
@@ -157,35 +155,44 @@ class Y3Model:
         return out
 
     def __call__(self, x, training=False, outs=None, padded=False):
-        """x: [B, H, W, 3] float32 NHWC in [0, 1] (torch CUDA tensor; numpy / CPU tensors are copied to the GPU).
+        """x: [B, H, W, 3] NHWC (torch CUDA tensor; numpy / CPU tensors are copied to the GPU), either float32 in [0, 1]
+        as ``inference.py:157-158`` feeds the Keras model, or **uint8**: the network then runs on ``float32(x) / 255``
+        (the reference's ``resize(...) / 255``, core/load_tfrecords.py:46) with the division done inside the stem conv --
+        bit-identical results, a quarter of the input bytes.
         ``padded=True`` (used by ``Detector``): each output is [B, gh, gw, P] with P = 3*(5+C) rounded up to a multiple
         of 4 floats and the logits of a pixel at its start -- the head convs then store through TMA and ``yolo_decode``
         reads the pitched layout directly."""
         if self._params is None:
             raise _lib.Y3Error("model has no weights: call load_weights / set_weights / init_weights first")
         if isinstance(x, np.ndarray):
-            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            x = torch.from_numpy(np.ascontiguousarray(x if x.dtype == np.uint8 else x.astype(np.float32, copy=False)))
         if x.dim() != 4 or x.shape[3] != 3:
             raise ValueError(f"input shape {tuple(x.shape)} is not [B, H, W, 3]")
         if not x.is_cuda:
             x = x.to(torch.device("cuda", _lib.context().device), non_blocking=True)
-        x = x.contiguous().float()
+        u8 = x.dtype == torch.uint8
+        x = x.contiguous() if u8 else x.contiguous().float()
         B, H, W, _ = x.shape
         ent = self._net(H, W, B, x.device.index)
+        lib = _lib.lib()
         if padded:
             if outs is None:
                 outs = [torch.empty((B, gh, gw, (ch + 3) // 4 * 4), dtype=torch.float32, device=x.device)
                         for gh, gw, ch in ent["out_shapes"]]
-            op = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
             pitch = (C.c_int * len(outs))(*[int(o.shape[3]) for o in outs])
-            _lib.check(_lib.lib().y3_net_forward_pitched(ent["handle"], _lib.ptr(x), int(B), op, pitch, len(outs),
-                                                         _lib.stream_ptr()))
-            return outs
-        if outs is None:
-            outs = [torch.empty((B, gh, gw, 3, ch // 3), dtype=torch.float32, device=x.device)
-                    for gh, gw, ch in ent["out_shapes"]]
+        else:
+            if outs is None:
+                outs = [torch.empty((B, gh, gw, 3, ch // 3), dtype=torch.float32, device=x.device)
+                        for gh, gw, ch in ent["out_shapes"]]
+            pitch = None
         op = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
-        _lib.check(_lib.lib().y3_net_forward(ent["handle"], _lib.ptr(x), int(B), op, len(outs), _lib.stream_ptr()))
+        if u8:
+            _lib.check(lib.y3_net_forward_u8(ent["handle"], _lib.ptr(x), int(B), op, pitch, len(outs), _lib.stream_ptr()))
+        elif padded:
+            _lib.check(lib.y3_net_forward_pitched(ent["handle"], _lib.ptr(x), int(B), op, pitch, len(outs),
+                                                  _lib.stream_ptr()))
+        else:
+            _lib.check(lib.y3_net_forward(ent["handle"], _lib.ptr(x), int(B), op, len(outs), _lib.stream_ptr()))
         return outs
 
     def profile_layers(self, x):
@@ -209,7 +216,7 @@ class Y3Model:
         """Keras ``model.predict``: batches of ``batch_size`` (Keras default 32), numpy arrays out."""
         if isinstance(x, torch.Tensor):
             x = x.detach().cpu().numpy()
-        x = np.ascontiguousarray(x, dtype=np.float32)
+        x = np.ascontiguousarray(x) if x.dtype == np.uint8 else np.ascontiguousarray(x, dtype=np.float32)
         chunks = []
         for i in range(0, x.shape[0], batch_size):
             chunks.append([o.cpu().numpy() for o in self(x[i:i + batch_size])])
@@ -223,9 +230,10 @@ class Y3Model:
                      f"k={l.ksize} s={l.stride} filters={l.filters} bn={l.batch_normalize} act={l.activation}")
 
     def close(self):
-        for ent in self._nets.values():
+        for ent in list(self._nets.values()) + self._retired:
             _lib.lib().y3_net_destroy(ent["handle"])
         self._nets = {}
+        self._retired = []
 
     def __del__(self):
         try:

@@ -15,14 +15,16 @@ def _as_device_f32(t, device):
     return t.contiguous().float()
 
 
-def yolo_decode(model_output_grids, anchors_table, nclasses, with_scores=False):
+def yolo_decode(model_output_grids, anchors_table, nclasses, with_scores=False, compact=False):
     """reference core/yolo_decode_layer.py:15-36.
 
     model_output_grids: list of [B, gh, gw, 3, 5+nclasses] float32 (torch CUDA tensors; numpy is copied to the GPU)
     anchors_table:      [n_scales, 3, 2] image-fraction anchors (reference core/utils.py:31-37)
     returns (bboxes [B,N,4], confidence [B,N,1], class_probs [B,N,nclasses]) as CUDA tensors; with
     ``with_scores=True`` additionally (scores [B,N], class_indices [B,N] int64) computed in the same pass
-    (reference core/yolo_nms.py:18-24).
+    (reference core/yolo_nms.py:18-24).  ``compact=True`` (implies with_scores; used by ``Detector``): confidence and
+    class_probs are not written at all -- the return value is (bboxes, None, None, scores, class_indices) -- because
+    yolo_nms only consumes boxes, scores and class ids.
     """
     ctx = _lib.context()
     dev = torch.device("cuda", ctx.device)
@@ -46,8 +48,12 @@ def yolo_decode(model_output_grids, anchors_table, nclasses, with_scores=False):
         raise ValueError(f"anchors_table shape {anchors.shape} != ({ns}, 3, 2)")
     N = sum(int(g.shape[1] * g.shape[2] * 3) for g in grids)
     bboxes = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
-    conf = torch.empty((B, N, 1), dtype=torch.float32, device=dev)
-    probs = torch.empty((B, N, int(nclasses)), dtype=torch.float32, device=dev)
+    conf = probs = None
+    if compact:
+        with_scores = True
+    else:
+        conf = torch.empty((B, N, 1), dtype=torch.float32, device=dev)
+        probs = torch.empty((B, N, int(nclasses)), dtype=torch.float32, device=dev)
     scores = cls = None
     if with_scores:
         scores = torch.empty((B, N), dtype=torch.float32, device=dev)

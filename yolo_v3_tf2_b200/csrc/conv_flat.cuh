@@ -97,8 +97,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(pempty_bar(ps), pphase ^ 1u, 0x100 + ps);
                 if (leader_lane) {
                     const uint32_t lead = mapa_shared(pfull_bar(ps), 0);
-                    if (is_leader) mbar_arrive_expect_tx(pfull_bar(ps), (p.dbg & 4) ? 0u : 2 * patch_tx);
-                    if (!(p.dbg & 4))
+                    if (is_leader) mbar_arrive_expect_tx(pfull_bar(ps), (Y3_DBG_BITS(p) & 4) ? 0u : 2 * patch_tx);
+                    if (!(Y3_DBG_BITS(p) & 4))
                         for (int b = 0; b < p.patch_boxes; ++b)
                             tma2_load_2d(smem_p + ps * patch_bytes + b * box_bytes, &tmA, lead, cb * BLOCK_K,
                                          row0 + b * p.box_rows);
@@ -108,8 +108,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(bempty_bar(bs), bphase ^ 1u, 0x180 + bs);
                     if (leader_lane) {
                         const uint32_t lead = mapa_shared(bfull_bar(bs), 0);
-                        if (is_leader) mbar_arrive_expect_tx(bfull_bar(bs), (p.dbg & 16) ? 0u : 2 * b_bytes);
-                        if (!(p.dbg & 16)) tma2_load_2d(smem_b + bs * b_bytes, &tmB, lead, kcoord, nb);
+                        if (is_leader) mbar_arrive_expect_tx(bfull_bar(bs), (Y3_DBG_BITS(p) & 16) ? 0u : 2 * b_bytes);
+                        if (!(Y3_DBG_BITS(p) & 16)) tma2_load_2d(smem_b + bs * b_bytes, &tmB, lead, kcoord, nb);
                     }
                     kcoord += BLOCK_K;
                     if (++bs == BST) { bs = 0; bphase ^= 1u; }
@@ -143,7 +143,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (leader_lane) {
                                 const uint64_t adesc = pdesc + (uint64_t)(((r * wp + sx) * SWZ) >> 4);
                                 const uint64_t bdesc = bdesc0 + (uint64_t)(bs * (b_bytes >> 4));
-                                if (!(p.dbg & 8)) {
+                                if (!(Y3_DBG_BITS(p) & 8)) {
 #pragma unroll
                                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                                         umma2_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,

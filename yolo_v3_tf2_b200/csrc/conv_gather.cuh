@@ -11,6 +11,8 @@
 // The Cin == 32 path is opt-in (Y3_GATHER_CIN32=1): measured 0.45 ms (one producer group) / 0.38 ms (two) per layer
 // against 0.27 ms for the TMA im2col kernel, so the planner keeps TMA for those layers.
 #pragma once
+#include <type_traits>
+
 #include "conv_tc.cuh"
 
 namespace y3 {
@@ -51,12 +53,19 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 }
 
 // COL (stride-1 stem only): the column-sharing producer described at the producer role below.
-template <int BLOCK_N, int SWZ, int STAGES, bool STEM, int NPROD_ = (STEM ? 2 : 1), bool COL = false>
+// U8 (COL only): the image is uint8 [B,H,W,3] and the network input is x / in_div (reference inference.py:157-158,
+// core/load_tfrecords.py:46: `/ 255`).  A byte has 256 possible values, so the float division, the bf16 rounding and the
+// bf16 remainder are looked up in a 256-entry shared-memory table (hi | lo << 16) built once per CTA with exactly the
+// arithmetic of the float path -- results are bit-identical to feeding float32(x) / in_div, with a quarter of the input
+// bytes and fewer producer instructions (9 LDS + 9 PRMT instead of ~40 conversion instructions per pixel column).
+template <int BLOCK_N, int SWZ, int STAGES, bool STEM, int NPROD_ = (STEM ? 2 : 1), bool COL = false, bool U8 = false>
 __global__ void __launch_bounds__(gather_threads<NPROD_>(), 1)
 conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ CUtensorMap tmR, const ConvArgs p) {
     using S = GatherSmem<BLOCK_N, SWZ, STAGES>;
     static_assert(!COL || (STEM && SWZ == 128), "column producer is a stem variant");
+    static_assert(!U8 || COL, "uint8 input is a variant of the column producer");
+    __shared__ uint32_t u8_lut[U8 ? 256 : 1];
     constexpr int NEPI = kGatherEpiGroups;
     constexpr int NPROD = NPROD_;
     constexpr int BLOCK_K = SWZ / 2;
@@ -110,6 +119,14 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
     if (warp == 2) {
         tmem_alloc(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish();
+    }
+    if constexpr (U8) {
+        if (threadIdx.x < 256) {
+            const float f = __fdiv_rn((float)threadIdx.x, p.in_div);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(f, __bfloat162float(hi)));
+            u8_lut[threadIdx.x] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+        }
     }
     if constexpr (COL) {
         // columns 54..63 of every row are read by the MMAs but never written by the producers: clear the stages once
@@ -209,19 +226,35 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             // columns 48 + 2s, 49 + 2s = lo_7, lo_8; columns 54..63 are zero.  Every (row, s) slot has exactly one
             // writer: the neighbour in the same image row and tile, else the row's own thread (zeros at the image border,
             // or the halo column at a tile edge).
-            const float* src = reinterpret_cast<const float*>(p.src);
+            using In = typename std::conditional<U8, uint8_t, float>::type;      // element of the image
+            using Val = typename std::conditional<U8, uint32_t, float>::type;    // what a thread keeps per value
+            const In* src = reinterpret_cast<const In*>(p.src);
             const int W = p.W;
-            auto loadcol = [&](long long pix, int y, bool valid, float (&v)[9]) {
+            auto loadcol = [&](long long pix, int y, bool valid, Val (&v)[9]) {
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const int yy = y - 1 + r;
                     const bool ok = valid && yy >= 0 && yy < p.H;
-                    const float* px = src + (pix + (long long)(r - 1) * W) * 3;
+                    const In* px = src + (pix + (long long)(r - 1) * W) * 3;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) v[r * 3 + c] = ok ? __ldg(px + c) : 0.0f;
+                    for (int c = 0; c < 3; ++c) v[r * 3 + c] = ok ? (Val)__ldg(px + c) : (Val)0;   // byte 0 -> table entry (0, 0)
                 }
             };
-            auto convert = [&](const float (&v)[9], uint4& p0, uint4& p1, uint32_t& p2) {
+            auto convert = [&](const Val (&vv)[9], uint4& p0, uint4& p1, uint32_t& p2) {
+                if constexpr (U8) {
+                    uint32_t w[9];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) w[i] = u8_lut[vv[i]];
+                    // w = hi | lo << 16: (hi_a, hi_b) = prmt 0x5410, (lo_a, lo_b) = prmt 0x7632, (hi_a, lo_b) = prmt 0x7610
+                    p0 = make_uint4(__byte_perm(w[0], w[1], 0x5410), __byte_perm(w[2], w[3], 0x5410),
+                                    __byte_perm(w[4], w[5], 0x5410), __byte_perm(w[6], w[7], 0x5410));
+                    p1 = make_uint4(__byte_perm(w[8], w[0], 0x7610), __byte_perm(w[1], w[2], 0x7632),
+                                    __byte_perm(w[3], w[4], 0x7632), __byte_perm(w[5], w[6], 0x7632));
+                    p2 = __byte_perm(w[7], w[8], 0x7632);
+                } else {
+                float v[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) v[i] = (float)vv[i];
                 __nv_bfloat162 h[4], l[4];
                 float f[9];
 #pragma unroll
@@ -241,13 +274,14 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                 p1 = make_uint4(*reinterpret_cast<const uint32_t*>(&mid), *reinterpret_cast<uint32_t*>(&l[0]),
                                 *reinterpret_cast<uint32_t*>(&l[1]), *reinterpret_cast<uint32_t*>(&l[2]));
                 p2 = *reinterpret_cast<uint32_t*>(&l[3]);
+                }
             };
             // pixel of this thread in tile j, its column (and the halo column the tile-edge threads need)
             struct Pix { int m, y, x; bool valid, halo; };
             auto locate = [&](int j) {
                 Pix q;
                 q.m = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + row;   // < 2^31 (host-checked)
-                q.valid = (j < my_tiles) && (q.m < p.M) && !(p.dbg & 4);
+                q.valid = (j < my_tiles) && (q.m < p.M) && !(Y3_DBG_BITS(p) & 4);
                 const int n = q.m / hw;
                 const int rem = q.m - n * hw;
                 q.y = rem / W;
@@ -256,7 +290,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                 return q;
             };
             Pix qn = locate(pg);
-            float vn[9], hn[9];
+            Val vn[9], hn[9];
             loadcol(qn.m, qn.y, qn.valid, vn);
             if (qn.halo) loadcol(qn.m + (row == 0 ? -1 : 1), qn.y, qn.valid, hn);
             for (int j = pg; j < my_tiles; j += NPROD) {
@@ -277,7 +311,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                     st_shared_v4(a_s + swz_off<128>(drow, 2 * sx + 1), p1);
                     st_shared_u32(a_s + swz_off<128>(drow, 6) + 4u * (uint32_t)sx, p2);
                 };
-                if (!(p.dbg & 32)) {
+                if (!(Y3_DBG_BITS(p) & 32)) {
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                     put(row, 1, c0, c1, c2);
                     if (row > 0 && q.x > 0) put(row - 1, 2, c0, c1, c2);
@@ -295,7 +329,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
             const float* src = reinterpret_cast<const float*>(p.src);
             auto load27 = [&](int j, float (&v)[27]) {
                 const int m = tile_id(p, blockIdx.x + j * gridDim.x, num_tiles) * kBlockM + row;
-                const bool valid = (j < my_tiles) && (m < p.M) && !(p.dbg & 4);   // Y3_DBG=4: no image loads (profiling)
+                const bool valid = (j < my_tiles) && (m < p.M) && !(Y3_DBG_BITS(p) & 4);   // Y3_DBG=4: no image loads (profiling)
                 const int n = m / hw;
                 const int rem = m - n * hw;
                 const int po = rem / p.Wo;
@@ -343,7 +377,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                 const uint32_t phase = (uint32_t)((j / STAGES) & 1);
                 mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                 const uint32_t a_s = smem_a + stage * S::A_BYTES;
-                if (!(p.dbg & 32)) {                               // Y3_DBG=32: no shared-memory stores (profiling)
+                if (!(Y3_DBG_BITS(p) & 32)) {                               // Y3_DBG=32: no shared-memory stores (profiling)
 #pragma unroll
                     for (int jc = 0; jc < 8; ++jc)
                         st_shared_v4(a_s + swz_off<128>(row, jc), make_uint4(w[4 * jc], w[4 * jc + 1], w[4 * jc + 2], w[4 * jc + 3]));

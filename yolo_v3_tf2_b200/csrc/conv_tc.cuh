@@ -63,6 +63,7 @@ struct ConvArgs {
                            //    layer to layer so that a layer starts on the pixels its predecessor wrote LAST, which are
                            //    still in L2 (each 52x52 tensor is 88 MB of a 126 MB L2)
     int stem_col;          // stem only: column-sharing producer (conv_gather.cuh), weights in its K order
+    float in_div;          // stem only, uint8 image: the network input is (float)byte / in_div (255 in the reference)
     int stages;            // weights-resident kernels only: A-operand pipeline depth (what fits next to the weights)
     int tma_out;           // 0: register-transpose epilogue; 32 / 64: bf16 dense output written with TMA stores in chunks
                            //    of that many columns (epilogue_role_tma); tmO (and tmR when a residual is fused) are
@@ -170,7 +171,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int block_n, in
             for (int j = 0; j < 8; ++j) bias4[j] = __ldg(bp + j);
         }
         tmem_ld_wait();
-        if (p.dbg & 1) continue;
+        if (Y3_DBG_BITS(p) & 1) continue;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float4 f;
@@ -208,7 +209,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& p, int block_n, in
                     for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
                     const uint4 o = *reinterpret_cast<uint4*>(o2);
                     __nv_bfloat16* dst = ob + rm[it].out * p.out_stride + ncol + seg * 8;
-                    if (p.dbg & 2) {
+                    if (Y3_DBG_BITS(p) & 2) {
                         if (o.x == 0x12345678u && o.y == 0x9abcdef0u) ob[0] = __float2bfloat16(0.f);   // keep the math alive
                     } else if (p.upsample) {
                         const long long up_row = 2LL * p.Wo * p.out_stride;
@@ -310,7 +311,7 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
                   NBUF * 32 * CW * (F32 ? 4 : 2) <= kEpiWarpBytes && (!F32 || CW == 32), "ring");
     constexpr uint32_t ROW_BYTES = CW * (F32 ? 4 : 2);
     constexpr uint32_t BUF_BYTES = 32 * ROW_BYTES;
-    const bool drain_only = (p.dbg & 1) != 0;
+    const bool drain_only = (Y3_DBG_BITS(p) & 1) != 0;
     const bool has_res = !F32 && (p.residual != nullptr) && !drain_only;
     const float slope = p.leaky ? 0.1f : 1.0f;   // LeakyReLU(0.1)(x) = max(x, 0.1x); slope 1 makes it the identity
     const uint32_t sw = (ROW_BYTES == 128) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
@@ -421,7 +422,7 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
             if (stamp && g == 1) ts_clock(ts, 20);   // fenced
             __syncwarp();
             if (lane == 0) {
-                if (!(p.dbg & 2)) tma_store_2d(tmO, buf, pr.ncol, pr.row);
+                if (!(Y3_DBG_BITS(p) & 2)) tma_store_2d(tmO, buf, pr.ncol, pr.row);
                 tma_store_commit();
                 if (stamp && g == 1) ts_clock(ts, 21);   // store issued
                 if (has_res && pf.valid) {

@@ -158,8 +158,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                         (uint16_t)sx, (uint16_t)r);
                                 } else {
                                     if (is_leader)
-                                        mbar_arrive_expect_tx(full_bar(stage), (p.dbg & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
-                                    if (!(p.dbg & 4))
+                                        mbar_arrive_expect_tx(full_bar(stage), (Y3_DBG_BITS(p) & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
+                                    if (!(Y3_DBG_BITS(p) & 4))
                                         tma2_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, lead_full, c0, cw, ch, cn,
                                                             (uint16_t)sx, (uint16_t)r);
                                     tma2_load_2d(smem_b + stage * S::B_BYTES, &tmB, lead_full, kcoord, nb);
@@ -180,8 +180,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             tma2_load_2d(smem_a + stage * S::A_BYTES, &tmA, lead_full, kcoord, m0);
                         } else {
                             if (is_leader)
-                                mbar_arrive_expect_tx(full_bar(stage), (p.dbg & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
-                            if (!(p.dbg & 4)) tma2_load_2d(smem_a + stage * S::A_BYTES, &tmA, lead_full, kcoord, m0);
+                                mbar_arrive_expect_tx(full_bar(stage), (Y3_DBG_BITS(p) & 4) ? 2 * S::B_BYTES : 2 * S::STAGE_BYTES);
+                            if (!(Y3_DBG_BITS(p) & 4)) tma2_load_2d(smem_a + stage * S::A_BYTES, &tmA, lead_full, kcoord, m0);
                             tma2_load_2d(smem_b + stage * S::B_BYTES, &tmB, lead_full, kcoord, nb);
                         }
                     }
@@ -218,7 +218,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (leader_lane) {
                         const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
                         const uint64_t bdesc = bdesc0 + (uint64_t)((BRES ? kb : stage) * (S::B_BYTES >> 4));
-                        if (!(p.dbg & 8)) {
+                        if (!(Y3_DBG_BITS(p) & 8)) {
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                                 umma2_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,

@@ -28,8 +28,8 @@ struct DecodeArgs {
     float anchors[18];     // [3 scales][3 anchors][w, h]
     int B, C, N;
     float* bboxes;
-    float* conf;
-    float* probs;
+    float* conf;           // conf and probs may both be null when scores / cls are requested ("compact" decode: the fused
+    float* probs;          // pipeline's NMS only reads boxes and scores, so 225 of the 425 MB per 64 images are not written)
     float* scores;         // optional
     long long* cls;        // optional
     int stage_bytes;       // size of the record staging buffer (the record-index array follows it)
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         box.z = __fadd_rn(cx, hw);
         box.w = __fadd_rn(cy, hh);
         reinterpret_cast<float4*>(a.bboxes)[orec] = box;
-        a.conf[orec] = obj;
+        if (a.conf != nullptr) a.conf[orec] = obj;
         r[4] = obj;   // kept for the fused score in phase (3)
     }
     __syncthreads();
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
             o.y = sigmoidf_acc(r[1]);
             o.z = sigmoidf_acc(r[2]);
             o.w = sigmoidf_acc(r[3]);
-            *reinterpret_cast<float4*>(a.probs + (long long)out_rec[ri] * C + c) = o;
+            if (a.probs != nullptr) *reinterpret_cast<float4*>(a.probs + (long long)out_rec[ri] * C + c) = o;
             r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = o.w;
         }
     } else {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
             const int c = e - ri * C;
             float* r = rec_at(ri) + 5 + c;
             const float pc = sigmoidf_acc(*r);
-            a.probs[(long long)out_rec[ri] * C + c] = pc;
+            if (a.probs != nullptr) a.probs[(long long)out_rec[ri] * C + c] = pc;
             *r = pc;
         }
     }

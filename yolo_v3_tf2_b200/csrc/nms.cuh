@@ -370,7 +370,7 @@ __global__ void gather_detections_kernel(const float* __restrict__ boxes, const 
                                          const float* __restrict__ scores, const int* __restrict__ selected,
                                          const int* __restrict__ num_valid, int B, int N, int max_boxes,
                                          float* __restrict__ out_boxes, long long* __restrict__ out_cls,
-                                         float* __restrict__ out_scores) {
+                                         float* __restrict__ out_scores, float* __restrict__ packed) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * max_boxes) return;
     const int b = t / max_boxes, k = t - b * max_boxes;
@@ -386,6 +386,14 @@ __global__ void gather_detections_kernel(const float* __restrict__ boxes, const 
     reinterpret_cast<float4*>(out_boxes)[t] = bb;
     out_cls[t] = c;
     out_scores[t] = s;
+    if (packed != nullptr) {
+        // the record the multi-GPU gather sends (distributed.pack_detections): per image max_boxes x (x1, y1, x2, y2,
+        // score, class) then num_valid, all float32 (class ids < 2^24 are exact)
+        float* rec = packed + (long long)b * (max_boxes * 6 + 1);
+        float* r = rec + k * 6;
+        r[0] = bb.x; r[1] = bb.y; r[2] = bb.z; r[3] = bb.w; r[4] = s; r[5] = (float)c;
+        if (k == 0) rec[max_boxes * 6] = (float)num_valid[b];
+    }
 }
 
 }  // namespace y3

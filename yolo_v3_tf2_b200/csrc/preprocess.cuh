@@ -90,4 +90,12 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessArgs a)
     o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
 }
 
+// uint8 -> float32 with the reference's `/ 255` (core/load_tfrecords.py:46): only used when the stem conv has no uint8
+// variant of its own (stride-2 or CUDA-core stems)
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
+                                                        long long n, float div) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        out[i] = __fdiv_rn((float)in[i], div);
+}
+
 }  // namespace y3

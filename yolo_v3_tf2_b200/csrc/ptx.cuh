@@ -29,14 +29,25 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Profiling ablations (ConvArgs::dbg bits, per-CTA timestamps) exist only in the profiling build (-DY3_PROFILING):
+// in the release library the knob reads as the constant 0 and every branch on it is compiled out.
+#ifdef Y3_PROFILING
+#define Y3_DBG_BITS(p) ((p).dbg)
+#else
+#define Y3_DBG_BITS(p) 0
+#endif
 // profiling stamp k of this CTA (see ConvArgs::ts); one thread calls it
 constexpr int kTsSlots = 32;
 __device__ __forceinline__ void ts_mark(unsigned long long* ts, int k) {
+#ifdef Y3_PROFILING
     if (ts) ts[kTsSlots * blockIdx.x + k] = global_timer_ns();
+#endif
 }
 // slots 16.. hold SM cycle counts (clock64) for intervals inside one warp
 __device__ __forceinline__ void ts_clock(unsigned long long* ts, int k) {
+#ifdef Y3_PROFILING
     if (ts) ts[kTsSlots * blockIdx.x + k] = (unsigned long long)clock64();
+#endif
 }
 
 __device__ __forceinline__ bool elect_one() {

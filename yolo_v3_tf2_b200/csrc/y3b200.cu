@@ -9,7 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "conv_first.cuh"
@@ -26,6 +29,36 @@
 namespace {
 
 thread_local std::string g_err;
+
+// Experiment knobs (Y3_* environment variables) exist only in the profiling build (-DY3_PROFILING ->
+// liby3b200_prof.so, used by tools/); the release library ignores the environment and always runs the defaults.
+inline int env_int(const char* name, int dflt) {
+#ifdef Y3_PROFILING
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember what was configured per
+// (device, kernel) -- a process may hold contexts on several GPUs -- under a lock (ctypes callers may be threaded).
+std::mutex g_smem_mu;
+std::map<std::pair<int, const void*>, int> g_smem_conf;
+cudaError_t ensure_dyn_smem(const void* kern, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    int& cur = g_smem_conf[{dev, kern}];
+    if (bytes > cur) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        cur = bytes;
+    }
+    return cudaSuccess;
+}
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -121,7 +154,7 @@ int make_map_epi_f32(const Driver& d, CUtensorMap* tm, const void* base, uint64_
 // 64 wide, else 32 columns (four 2 KB buffers).  Measured on the whole net: 64 everywhere 4.98 ms, 32 for the layers
 // with a fused residual (deeper residual prefetch, twice the chunks) 5.06 ms, 32 everywhere 5.26 ms.  Y3_EPI_CW forces one.
 int epi_chunk_cols(int block_n, bool has_residual) {
-    static const int forced = []() { const char* e = getenv("Y3_EPI_CW"); return e ? atoi(e) : 0; }();
+    static const int forced = env_int("Y3_EPI_CW", 0);
     (void)has_residual;
     if (block_n < 64) return 32;
     if (forced == 32 || forced == 64) return forced;
@@ -132,7 +165,7 @@ int epi_chunk_cols(int block_n, bool has_residual) {
 unsigned long long* g_ts_ptr = nullptr;
 
 // TMA-store epilogue (Y3_TMA_EPI=0 falls back to the register-transpose epilogue, for A/B measurements)
-const bool g_use_tma_epi = []() { const char* e = getenv("Y3_TMA_EPI"); return !(e && e[0] == '0'); }();
+const bool g_use_tma_epi = env_int("Y3_TMA_EPI", 1) != 0;
 
 // NHWC bf16 activation seen as (C, W, H, N) for the im2col load of a k x k conv with the reference's padding rule:
 //   stride 1 ('same'):                      pad_lo = pad_hi = (k-1)/2
@@ -160,7 +193,7 @@ int make_map_im2col(const Driver& d, CUtensorMap* tm, const void* base, int N, i
 // conv tile configuration + launch
 // ------------------------------------------------------------------------------------------------
 // programmatic dependent launch between consecutive conv layers (Y3_PDL=0 disables)
-const bool g_use_pdl = []() { const char* e = getenv("Y3_PDL"); return !(e && e[0] == '0'); }();
+const bool g_use_pdl = env_int("Y3_PDL", 1) != 0;
 
 constexpr int fit_stages(int stage_bytes);
 constexpr int st1(int bn, int swz);
@@ -182,13 +215,13 @@ int pick_block_n(int cout) {
 
 bool pick_cfg(int cin, int cout, int ksize, ConvCfg& c) {
     c.gather = 0;
-    static const int cluster_env = []() { const char* e = getenv("Y3_CLUSTER"); return e ? atoi(e) : 3; }();
+    static const int cluster_env = env_int("Y3_CLUSTER", 3);
     c.cluster = (cluster_env == 2) ? 2 : 1;
     if (cin == 3 && ksize == 3 && cout == 32) {   // stem: one 64-wide K block (27 hi + 27 lo), weights resident
         c.block_n = 32; c.swz = 128; c.stages = 8; c.gather = 2;
         return true;
     }
-    static const bool gather32 = []() { const char* e = getenv("Y3_GATHER_CIN32"); return e && e[0] == '1'; }();
+    static const bool gather32 = env_int("Y3_GATHER_CIN32", 0) == 1;
     if (gather32 && cin == 32 && ksize == 3 && cout <= 128) {   // optional software-im2col path for 64-byte rows
         c.block_n = pick_block_n(cout); c.swz = 64; c.stages = 8; c.gather = 1;
         return true;
@@ -206,7 +239,7 @@ bool pick_cfg(int cin, int cout, int ksize, ConvCfg& c) {
 }
 
 // column-sharing stem producer (conv_gather.cuh, COL): Y3_STEM_COL=0 falls back to the one-thread-per-pixel producer
-const bool g_stem_col = []() { const char* e = getenv("Y3_STEM_COL"); return !(e && e[0] == '0'); }();
+const bool g_stem_col = env_int("Y3_STEM_COL", 1) != 0;
 // K column of value i = r*3 + c of filter column sx in a row built by that producer: hi part bf16(x), lo part the
 // bf16 remainder.  [sx*16, sx*16+9) hi_0..8, [sx*16+9, sx*16+16) lo_0..6, 48+2sx / 49+2sx lo_7 / lo_8.
 __host__ __device__ inline int stem_col_k(int sx, int i, bool lo) {
@@ -215,7 +248,7 @@ __host__ __device__ inline int stem_col_k(int sx, int i, bool lo) {
 }
 
 // weights-resident variants of the conv kernels (BRES): Y3_BRES=0 disables them
-const bool g_use_bres = []() { const char* e = getenv("Y3_BRES"); return !(e && e[0] == '0'); }();
+const bool g_use_bres = env_int("Y3_BRES", 1) != 0;
 
 template <int BN, int SWZ, int ST, int CL>
 cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
@@ -242,11 +275,9 @@ cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const CU
             smem = y3::ConvSmem<BN, SWZ, 8>::total_resident(rst, args.num_k_blocks);
         }
     }
-    static int configured[2] = {0, 0};
-    if (smem > configured[rst ? 1 : 0]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dyn_smem(kern, smem);
         if (e != cudaSuccess) return e;
-        configured[rst ? 1 : 0] = smem;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -322,11 +353,9 @@ cudaError_t launch_conv2_t(const CUtensorMap& ta, const CUtensorMap& tb, const C
         args.stages = rst;
         smem = y3::Conv2Smem<BN, 128, 8>::total_resident(rst, args.num_k_blocks);
     }
-    static int configured[2] = {0, 0};
-    if (smem > configured[rst ? 1 : 0]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dyn_smem((const void*)kern, smem);
         if (e != cudaSuccess) return e;
-        configured[rst ? 1 : 0] = smem;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -355,18 +384,16 @@ cudaError_t launch_conv(const ConvCfg& c, const CUtensorMap& ta, const CUtensorM
     return c.cluster == 2 ? launch_conv_cl<2>(c, ta, tb, to, tr, a, sms, st) : launch_conv_cl<1>(c, ta, tb, to, tr, a, sms, st);
 }
 
-template <int BN, int SWZ, int ST, bool STEM, int NPROD = (STEM ? 2 : 1), bool COL = false>
+template <int BN, int SWZ, int ST, bool STEM, int NPROD = (STEM ? 2 : 1), bool COL = false, bool U8 = false>
 cudaError_t launch_gather_t(const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const y3::ConvArgs& args,
                             int sms, cudaStream_t st) {
     using S = y3::GatherSmem<BN, SWZ, ST>;
-    auto kern = y3::conv_gather_kernel<BN, SWZ, ST, STEM, NPROD, COL>;
+    auto kern = y3::conv_gather_kernel<BN, SWZ, ST, STEM, NPROD, COL, U8>;
     const int smem = S::total(args.num_k_blocks);
     if (smem > 232448) return cudaErrorInvalidValue;
-    static int configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    {
+        cudaError_t e = ensure_dyn_smem((const void*)kern, smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const int grid = std::max(1, std::min(args.tiles_m, sms));
     cudaLaunchConfig_t cfg{};
@@ -383,15 +410,19 @@ cudaError_t launch_gather_t(const CUtensorMap& tb, const CUtensorMap& to, const 
 }
 
 cudaError_t launch_gather(const ConvCfg& c, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                          const y3::ConvArgs& a, int sms, cudaStream_t st) {
+                          const y3::ConvArgs& a, int sms, cudaStream_t st, bool u8 = false) {
     if (a.tiles_n != 1) return cudaErrorInvalidValue;
+    if (u8) {
+        if (c.gather == 2 && a.stem_col) return launch_gather_t<32, 128, 8, true, 2, true, true>(tb, to, tr, a, sms, st);
+        return cudaErrorInvalidValue;   // callers convert to float32 first for every other stem
+    }
     if (c.gather == 2 && a.stem_col) return launch_gather_t<32, 128, 8, true, 2, true>(tb, to, tr, a, sms, st);
     if (c.gather == 2) return launch_gather_t<32, 128, 8, true>(tb, to, tr, a, sms, st);
     switch (c.block_n) {
         case 32: return launch_gather_t<32, 64, 8, false>(tb, to, tr, a, sms, st);
         case 64: {
             // experiment knob: producer groups (taps copied concurrently) for the Cin = 32 -> 64 layers
-            static const int nprod = []() { const char* e = getenv("Y3_GATHER_NPROD"); return e ? atoi(e) : 1; }();
+            static const int nprod = env_int("Y3_GATHER_NPROD", 1);
             if (nprod == 2) return launch_gather_t<64, 64, 12, false, 2>(tb, to, tr, a, sms, st);
             if (nprod == 3) return launch_gather_t<64, 64, 12, false, 3>(tb, to, tr, a, sms, st);
             return launch_gather_t<64, 64, 8, false>(tb, to, tr, a, sms, st);
@@ -404,7 +435,7 @@ cudaError_t launch_gather(const ConvCfg& c, const CUtensorMap& tb, const CUtenso
 // The flat-patch 3x3 kernel (conv_flat.cuh) is parity-green but measured slower end to end than the im2col path
 // (forward 6.13 ms vs 5.52 ms at B = 64: the haloed layouts cost the neighbouring 1x1 layers more than the 3x3 layers
 // gain), so it is opt-in: Y3_FLAT=1.
-const bool g_use_flat = []() { const char* e = getenv("Y3_FLAT"); return e && e[0] == '1'; }();
+const bool g_use_flat = env_int("Y3_FLAT", 0) == 1;
 
 // patch / pipeline geometry of the flat-patch kernel for a haloed row pitch of wp pixels
 struct FlatGeom {
@@ -431,12 +462,9 @@ bool flat_geometry(int wp, int swz, int block_n, FlatGeom& g) {
 cudaError_t launch_flat(int swz, const CUtensorMap& ta, const CUtensorMap& tb, const y3::ConvArgs& args, size_t smem,
                         int sms, cudaStream_t st) {
     auto kern = (swz == 128) ? y3::conv_flat_kernel<128> : y3::conv_flat_kernel<64>;
-    static size_t configured[2] = {0, 0};
-    size_t& conf = configured[swz == 128 ? 0 : 1];
-    if (smem > conf) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = ensure_dyn_smem((const void*)kern, (int)smem);
         if (e != cudaSuccess) return e;
-        conf = smem;
     }
     const int work = ((args.tiles_m + 1) / 2) * args.tiles_n;
     const int grid = std::max(1, std::min(work, sms / 2)) * 2;
@@ -555,6 +583,7 @@ struct y3_net {
     int64_t arena_bytes = 0;
     uint8_t* arena = nullptr;
     bool maps_built = false;
+    float* x_scratch = nullptr;        // float32 copy of a uint8 input, only for stems without a uint8 kernel
 };
 
 namespace {
@@ -881,7 +910,7 @@ int plan_net(y3_net& n) {
                 w.cout_pad = d.filters;
             }
             // alternate the tile direction from conv to conv (Y3_REV=0 disables): the next layer starts where this one ended
-            static const bool use_rev = []() { const char* e = getenv("Y3_REV"); return !(e && e[0] == '0'); }();
+            static const bool use_rev = env_int("Y3_REV", 1) != 0;
             s.rev = (use_rev && s.kind == 1 && !s.flat) ? (s.conv_idx & 1) : 0;
             pl.kernel = s.kind;
             pl.fused_add = residual[i];
@@ -1072,7 +1101,7 @@ y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
         a.pst = s.pst; a.bst = s.bst;
         a.num_k_blocks = 9 * a.cblocks;
     }
-    static const int dbg = []() { const char* e = getenv("Y3_DBG"); return e ? atoi(e) : 0; }();
+    static const int dbg = env_int("Y3_DBG", 0);
     a.dbg = dbg;
     a.ts = g_ts_ptr;
     a.rev = s.rev;
@@ -1105,6 +1134,36 @@ __global__ void stem_repack_kernel(const __nv_bfloat16* __restrict__ w64, __nv_b
 }  // namespace
 
 extern "C" {
+
+// CRC-32C (Castagnoli, reflected 0x82F63B78), slicing-by-8: host helper for the TensorFlow checkpoint reader / writer
+// (every tensor of a bundle carries one; a full model is 248 MB, far too much for a pure-Python loop)
+uint32_t y3_crc32c(uint32_t crc, const void* data, int64_t n) {
+    static uint32_t T[8][256];
+    static std::once_flag once;
+    std::call_once(once, []() {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+            T[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; ++i)
+            for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xFF];
+    });
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    crc = ~crc;
+    while (n >= 8) {
+        uint32_t lo, hi;
+        std::memcpy(&lo, p, 4);
+        std::memcpy(&hi, p + 4, 4);
+        lo ^= crc;
+        crc = T[7][lo & 0xFF] ^ T[6][(lo >> 8) & 0xFF] ^ T[5][(lo >> 16) & 0xFF] ^ T[4][lo >> 24] ^
+              T[3][hi & 0xFF] ^ T[2][(hi >> 8) & 0xFF] ^ T[1][(hi >> 16) & 0xFF] ^ T[0][hi >> 24];
+        p += 8;
+        n -= 8;
+    }
+    while (n-- > 0) crc = T[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
+    return ~crc;
+}
 
 const char* y3_last_error(void) { return g_err.c_str(); }
 int y3_version(void) { return 100; }
@@ -1193,6 +1252,7 @@ int y3_net_create(y3_ctx* ctx, const y3_layer_desc* layers, int n_layers, int H,
 void y3_net_destroy(y3_net* net) {
     if (!net) return;
     if (net->arena) cudaFree(net->arena);
+    if (net->x_scratch) cudaFree(net->x_scratch);
     for (ConvWeights& w : net->convs) {
         if (w.w) cudaFree(w.w);
         if (w.bias) cudaFree(w.bias);
@@ -1292,17 +1352,22 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
     return Y3_OK;
 }
 
-static int net_forward_impl(y3_net* net, const float* x, int B, float* const* outs, const int* out_pitch, int n_outs,
-                            void* stream, std::vector<cudaEvent_t>* evs);
+static int net_forward_impl(y3_net* net, const void* x, bool x_u8, int B, float* const* outs, const int* out_pitch,
+                            int n_outs, void* stream, std::vector<cudaEvent_t>* evs);
 
 int y3_net_forward(y3_net* net, const float* x, int B, float* const* outs, int n_outs, void* stream) {
-    return net_forward_impl(net, x, B, outs, nullptr, n_outs, stream, nullptr);
+    return net_forward_impl(net, x, false, B, outs, nullptr, n_outs, stream, nullptr);
+}
+
+int y3_net_forward_u8(y3_net* net, const uint8_t* x, int B, float* const* outs, const int* out_pitch, int n_outs,
+                      void* stream) {
+    return net_forward_impl(net, x, true, B, outs, out_pitch, n_outs, stream, nullptr);
 }
 
 int y3_net_forward_pitched(y3_net* net, const float* x, int B, float* const* outs, const int* out_pitch, int n_outs,
                            void* stream) {
     if (!out_pitch) return fail(Y3_ERR_INVALID, "out_pitch is null");
-    return net_forward_impl(net, x, B, outs, out_pitch, n_outs, stream, nullptr);
+    return net_forward_impl(net, x, false, B, outs, out_pitch, n_outs, stream, nullptr);
 }
 
 int y3_net_num_steps(y3_net* net) { return net ? (int)net->steps.size() : 0; }
@@ -1312,7 +1377,7 @@ int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs,
     if (!net || !ms_host || n_steps != (int)net->steps.size()) return fail(Y3_ERR_INVALID, "bad timing buffers");
     std::vector<cudaEvent_t> evs(net->steps.size() + 1);
     for (auto& e : evs) Y3_CUDA(cudaEventCreate(&e));
-    int rc = net_forward_impl(net, x, B, outs, nullptr, n_outs, stream, &evs);
+    int rc = net_forward_impl(net, x, false, B, outs, nullptr, n_outs, stream, &evs);
     if (rc == Y3_OK) {
         cudaError_t e = cudaEventSynchronize(evs.back());
         if (e != cudaSuccess) rc = fail(Y3_ERR_CUDA, std::string("cudaEventSynchronize: ") + cudaGetErrorString(e));
@@ -1327,10 +1392,10 @@ int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs,
     return rc;
 }
 
-static int net_forward_impl(y3_net* net, const float* x, int B, float* const* outs, const int* out_pitch, int n_outs,
-                            void* stream, std::vector<cudaEvent_t>* evs) {
+static int net_forward_impl(y3_net* net, const void* x_in, bool x_u8, int B, float* const* outs, const int* out_pitch,
+                            int n_outs, void* stream, std::vector<cudaEvent_t>* evs) {
     (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
-    if (!net || !x || !outs) return fail(Y3_ERR_INVALID, "null argument");
+    if (!net || !x_in || !outs) return fail(Y3_ERR_INVALID, "null argument");
     if (net->ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (B <= 0 || B > net->max_batch) return fail(Y3_ERR_INVALID, "batch " + std::to_string(B) + " exceeds max_batch");
     if (n_outs != (int)net->outputs.size()) return fail(Y3_ERR_INVALID, "wrong number of outputs");
@@ -1338,6 +1403,25 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
         if (!w.loaded) return fail(Y3_ERR_STATE, "weights not loaded for every conv");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int sms = net->ctx->sms;
+    // uint8 image: the stride-1 tensor-core stem reads the bytes itself (x / 255 through a lookup table); any other stem
+    // gets a float32 copy (x / 255, same IEEE division) in a scratch buffer first
+    const float* x = reinterpret_cast<const float*>(x_in);
+    bool stem_u8 = false;
+    if (x_u8) {
+        bool direct = true;
+        for (const Step& s : net->steps)
+            if ((s.kind == 1 || s.kind == 2) && s.src == 0) direct = direct && s.kind == 1 && s.cfg.gather == 2 && s.stem_col;
+        if (direct) {
+            stem_u8 = true;
+        } else {
+            if (!net->x_scratch)
+                Y3_CUDA(cudaMalloc(&net->x_scratch, (size_t)net->max_batch * net->H * net->W * 3 * sizeof(float)));
+            const long long n = (long long)B * net->H * net->W * 3;
+            y3::u8_to_f32_kernel<<<grid_for(n, 256, sms), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(x_in), net->x_scratch, n, 255.0f);
+            Y3_CUDA(cudaGetLastError());
+            x = net->x_scratch;
+        }
+    }
     size_t step_no = 0;
     for (const Step& s : net->steps) {
         const y3_layer_desc& d = net->layers[s.layer];
@@ -1384,13 +1468,14 @@ static int net_forward_impl(y3_net* net, const float* x, int B, float* const* ou
             } else if (s.cfg.gather) {
                 ca.H = a.H; ca.W = a.W;
                 if (s.cfg.gather == 2) {
-                    ca.src = x;
+                    ca.src = stem_u8 ? x_in : (const void*)x;
                     ca.src_stride = 3;
+                    ca.in_div = 255.0f;
                 } else {
                     ca.src = tensor_ptr(*net, s.src);
                     ca.src_stride = a.pix_stride;
                 }
-                Y3_CUDA(launch_gather(s.cfg, s.tmB, *tmo, s.tmR, ca, sms, st));
+                Y3_CUDA(launch_gather(s.cfg, s.tmB, *tmo, s.tmR, ca, sms, st, stem_u8 && s.cfg.gather == 2));
             } else {
                 Y3_CUDA(launch_conv(s.cfg, s.tmA, s.tmB, *tmo, s.tmR, ca, sms, st));
             }
@@ -1478,7 +1563,9 @@ static int decode_impl(y3_ctx* ctx, const float* const* grids, const int* gh, co
                        int n_scales, const float* anchors_host, int B, int nclasses, float* bboxes, float* conf,
                        float* probs, float* scores, int64_t* class_idx, void* stream) {
     (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
-    if (!ctx || !grids || !gh || !gw || !anchors_host || !bboxes || !conf || !probs) return fail(Y3_ERR_INVALID, "null argument");
+    if (!ctx || !grids || !gh || !gw || !anchors_host || !bboxes) return fail(Y3_ERR_INVALID, "null argument");
+    if ((conf == nullptr) != (probs == nullptr)) return fail(Y3_ERR_INVALID, "conf and probs go together");
+    if (!conf && !scores) return fail(Y3_ERR_INVALID, "compact decode (no conf / probs) needs scores and class_idx");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (n_scales < 1 || n_scales > 3) return fail(Y3_ERR_UNSUPPORTED, "1..3 scales supported");
     if (B <= 0 || nclasses <= 0) return fail(Y3_ERR_INVALID, "bad B / nclasses");
@@ -1521,11 +1608,7 @@ static int decode_impl(y3_ctx* ctx, const float* const* grids, const int* gh, co
     a.stage_bytes = (((y3::kDecodeRecs / 3 + 1) * (max_pitch + 4) + 3) & ~3) * 4;   // +4: bank-conflict padding of the staging pitch
     const size_t smem = (size_t)a.stage_bytes + 2 * y3::kDecodeRecs * 4;
     if (smem > 200 * 1024) return fail(Y3_ERR_UNSUPPORTED, "nclasses too large for the decode tile");
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        Y3_CUDA(cudaFuncSetAttribute(y3::decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) Y3_CUDA(ensure_dyn_smem((const void*)y3::decode_kernel, (int)smem));
     y3::decode_kernel<<<chunks, y3::kDecodeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     Y3_CUDA(cudaGetLastError());
     return Y3_OK;
@@ -1546,11 +1629,7 @@ int y3_class_reduce(y3_ctx* ctx, const float* probs, const float* conf, int B, i
     const long long ctas = recs > 0 ? (nrec + recs - 1) / recs : 0;
     if (recs >= 4 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0 && ctas <= 0x7fffffffLL) {
         const size_t smem = (size_t)(recs * rec_bytes);
-        static size_t configured = 48 * 1024;
-        if (smem > configured) {
-            Y3_CUDA(cudaFuncSetAttribute(y3::class_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        if (smem > 48 * 1024) Y3_CUDA(ensure_dyn_smem((const void*)y3::class_reduce_kernel, (int)smem));
         y3::class_reduce_kernel<<<(unsigned)ctas, y3::kReduceThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
             probs, conf, nrec, nclasses, recs, scores, reinterpret_cast<long long*>(class_idx));
     } else {
@@ -1569,6 +1648,13 @@ int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, 
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (B <= 0 || N <= 0 || max_boxes <= 0) return fail(Y3_ERR_INVALID, "bad shape");
     if (N > y3::kNmsMaxN) return fail(Y3_ERR_UNSUPPORTED, "N > 32768 boxes per image is not supported");
+    // the kept list holds kNmsKeptCap entries and grows by up to one chunk past max_boxes before the kernel stops
+    if (max_boxes + y3::kNmsChunk > y3::kNmsKeptCap)
+        return fail(Y3_ERR_UNSUPPORTED, "yolo_max_boxes > " + std::to_string(y3::kNmsKeptCap - y3::kNmsChunk) +
+                                            " is not supported (kept-list capacity)");
+    // tf.image.non_max_suppression_padded suppresses on iou >= thr only where iou > 0; the kernel's `iou >= thr` is the
+    // same rule for thr > 0 only
+    if (!(iou_thr > 0.0f)) return fail(Y3_ERR_UNSUPPORTED, "nms_iou_threshold must be > 0");
     if ((reinterpret_cast<uintptr_t>(bboxes) & 15) != 0) return fail(Y3_ERR_INVALID, "bboxes must be 16-byte aligned");
     y3::NmsArgs a{};
     a.boxes = bboxes; a.scores = scores;
@@ -1580,11 +1666,7 @@ int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, 
     a.iou_thr = iou_thr; a.score_thr = score_thr;
     a.selected = selected; a.num_valid = num_valid; a.status = status;
     const size_t smem = (size_t)np * 6 + (size_t)(y3::kNmsKeptCap + y3::kNmsChunk) * 16 + (size_t)y3::kNmsChunk * 8 * 4 + 32;
-    static size_t configured = 0;   // static shared memory of the kernel counts against the 227 KB limit too
-    if (smem > configured) {
-        Y3_CUDA(cudaFuncSetAttribute(y3::nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    Y3_CUDA(ensure_dyn_smem((const void*)y3::nms_kernel, (int)smem));   // static shared memory counts against the limit too
     y3::nms_kernel<<<B, y3::kNmsThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     Y3_CUDA(cudaGetLastError());
     return Y3_OK;
@@ -1593,6 +1675,13 @@ int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, 
 int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_idx, const float* scores,
                          const int32_t* selected, const int32_t* num_valid, int B, int N, int max_boxes,
                          float* out_boxes, int64_t* out_classes, float* out_scores, void* stream) {
+    return y3_gather_detections_packed(ctx, bboxes, class_idx, scores, selected, num_valid, B, N, max_boxes, out_boxes,
+                                       out_classes, out_scores, nullptr, stream);
+}
+
+int y3_gather_detections_packed(y3_ctx* ctx, const float* bboxes, const int64_t* class_idx, const float* scores,
+                                const int32_t* selected, const int32_t* num_valid, int B, int N, int max_boxes,
+                                float* out_boxes, int64_t* out_classes, float* out_scores, float* packed, void* stream) {
     (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
     if (!ctx || !bboxes || !class_idx || !scores || !selected || !num_valid || !out_boxes || !out_classes || !out_scores)
         return fail(Y3_ERR_INVALID, "null argument");
@@ -1600,7 +1689,7 @@ int y3_gather_detections(y3_ctx* ctx, const float* bboxes, const int64_t* class_
     const int total = B * max_boxes;
     y3::gather_detections_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         bboxes, reinterpret_cast<const long long*>(class_idx), scores, selected, num_valid, B, N, max_boxes, out_boxes,
-        reinterpret_cast<long long*>(out_classes), out_scores);
+        reinterpret_cast<long long*>(out_classes), out_scores, packed);
     Y3_CUDA(cudaGetLastError());
     return Y3_OK;
 }

@@ -46,6 +46,11 @@ class Graph:
     conv_layers: List[int] = field(default_factory=list)    # layer indices of convs in creation order
     sub_model_names: List[str] = field(default_factory=list)
     nclasses: int = 0
+    # what the Keras checkpoint order needs (keras_weight_slots): per sub-model its producers in ``inputs.source`` order
+    # ('' = the model Input), its output tensor ids in ``outputs_layers`` order, and the names of the model's outputs
+    sub_model_sources: dict = field(default_factory=dict)
+    sub_model_outputs: dict = field(default_factory=dict)
+    output_sub_models: List[str] = field(default_factory=list)
 
     def add(self, layer: Layer) -> int:
         self.layers.append(layer)
@@ -140,6 +145,7 @@ def build_graph(sub_models_configs, output_stage="head", nclasses=0, search_dirs
     for sm in sub_models_configs:
         name = sm["name"]
         inputs_config = sm.get("inputs")
+        g.sub_model_sources[name] = []
         if inputs_config:
             if "shape" in inputs_config:
                 raise _lib.Y3Unsupported("sub-model inputs.shape (fresh Input) is not used by the yolov3 configs")
@@ -147,12 +153,14 @@ def build_graph(sub_models_configs, output_stage="head", nclasses=0, search_dirs
             for source_entry in inputs_config["source"]:
                 sel = [p for p in produced if p["name"] == source_entry["name"]]
                 src = sel[0]   # IndexError when the producer does not exist, like parse_model.py:227
+                g.sub_model_sources[name].append(src["name"])
                 idx = source_entry.get("entry_index", 0)
                 out = src["outputs"]
                 entries.append(out[idx] if isinstance(out, list) else out)
             inputs_entry = entries[0] if len(entries) == 1 else entries
         else:
             inputs_entry = 0   # the model input (parse_model.py:300)
+            g.sub_model_sources[name].append("")
 
         if layer_lists is not None and sm["layers_config_file"] in layer_lists:
             layers_config = layer_lists[sm["layers_config_file"]]
@@ -201,12 +209,119 @@ def build_graph(sub_models_configs, output_stage="head", nclasses=0, search_dirs
         # Keras unwraps one-element output lists (parse_model.py:304-307)
         produced.append({"name": name, "outputs": outs[0] if len(outs) == 1 else outs})
         g.sub_model_names.append(name)
+        g.sub_model_outputs[name] = list(outs)
 
     for p in produced:
         if output_stage in p["name"]:
             o = p["outputs"]
             g.outputs += o if isinstance(o, list) else [o]
+            g.output_sub_models.append(p["name"])
     return g
+
+
+def _keras_order(nodes, inbound, outputs):
+    """Order of ``Model.layers`` of a Keras functional model (keras/engine/functional.py ``_map_graph_network``):
+    decreasing depth (longest path to an output, in layers), ties broken by the order in which a depth-first walk from
+    the outputs first completes a layer (inbound layers before the layer itself, outputs in their listed order).
+    ``nodes``: hashable ids; ``inbound[n]``: list of ids feeding n (in call-argument order); -> list of ids."""
+    index, order = {}, []
+
+    def visit(n):
+        stack = [(n, iter(inbound.get(n, ())))]
+        seen_local = {n}
+        while stack:
+            cur, it = stack[-1]
+            nxt = next(it, None)
+            if nxt is None:
+                stack.pop()
+                if cur not in index:
+                    index[cur] = len(order)
+                    order.append(cur)
+            elif nxt not in index and nxt not in seen_local:
+                seen_local.add(nxt)
+                stack.append((nxt, iter(inbound.get(nxt, ()))))
+
+    for o in outputs:
+        if o not in index:
+            visit(o)
+    depth = {n: 0 for n in order}
+    for n in reversed(order):            # consumers before producers: order is a topological order
+        for p in inbound.get(n, ()):
+            if p in depth:
+                depth[p] = max(depth[p], depth[n] + 1)
+    return sorted(order, key=lambda n: (-depth[n], index[n])), depth
+
+
+def keras_weight_slots(g: Graph):
+    """Per conv (creation order): (i, j_conv, j_bn or None) such that the reference's Keras model stores the conv's
+    variables under ``layer_with_weights-<i>/layer_with_weights-<j_conv>/{kernel,bias}`` and its batch-normalization
+    under ``layer_with_weights-<i>/layer_with_weights-<j_bn>/...`` (``model.save_weights``, train.py:93-104).
+
+    ``layer_with_weights-<n>`` counts the layers with weights in ``Model.layers`` order, and Keras sorts that list by
+    decreasing depth, not by creation order (the reference's convert.py notes the same: ``model.layers`` is not in conv
+    creation order).  For yolov3 the sub-models come out as backbone, neck0, neck1, neck2, head0, head1, head2; for
+    yolov3-tiny as backbone, neck0, neck1, head0, head1.  The same rule is applied inside every sub-model, one Keras
+    layer per ZeroPadding2D / Conv2D / BatchNormalization / LeakyReLU / Add / UpSampling2D / Concatenate / Reshape /
+    MaxPooling2D the reference creates (core/parse_model.py:13-213)."""
+    names = [n for n in g.sub_model_names]
+    if not g.sub_model_sources:          # legacy monolithic schema: sub-models were consecutive slices of one chain
+        top = names
+    else:
+        inbound = {n: [s if s else "__input__" for s in g.sub_model_sources.get(n, [])] for n in names}
+        top, _ = _keras_order(names + ["__input__"], inbound, g.output_sub_models)
+        top = [n for n in top if n != "__input__"]
+    conv_index = {li: ci for ci, li in enumerate(g.conv_layers)}
+    slots = {}
+    i = 0
+    for name in top:
+        lids = [k for k, l in enumerate(g.layers) if l.sub_model == name]
+        if not any(g.layers[k].op == _lib.OP_CONV for k in lids):
+            continue
+        mine = set(k + 1 for k in lids)       # tensor ids produced inside this sub-model
+        # Keras layers of the sub-model: (layer id, position) with the per-IR-layer chain pad? conv bn? leaky?
+        inbound, weighted = {}, {}
+
+        def src_node(t):
+            return ("L", t - 1, "end") if t in mine else ("in", t)
+
+        for k in lids:
+            l = g.layers[k]
+            if l.op == _lib.OP_CONV:
+                chain = (["pad"] if l.stride > 1 else []) + ["conv"] + (["bn"] if l.batch_normalize else []) + \
+                        (["leaky"] if l.activation == 1 else [])
+                prev = src_node(l.src0)
+                for pos, kind in enumerate(chain):
+                    node = ("L", k, "end") if pos == len(chain) - 1 else ("L", k, kind)
+                    inbound[node] = [prev]
+                    if kind in ("conv", "bn"):
+                        weighted[node] = (k, kind)
+                    prev = node
+            elif l.op == _lib.OP_SHORTCUT:
+                inbound[("L", k, "end")] = [src_node(l.src1), src_node(l.src0)]     # Add()([layers[from], x])
+            elif l.op == _lib.OP_CONCAT:
+                inbound[("L", k, "end")] = [src_node(l.src0), src_node(l.src1)]
+            else:
+                inbound[("L", k, "end")] = [src_node(l.src0)]
+        outs = [src_node(t) for t in g.sub_model_outputs.get(name, [lids[-1] + 1])]
+        order, _ = _keras_order(list(inbound), inbound, outs)
+        j = 0
+        for node in order:
+            if node in weighted:
+                k, kind = weighted[node]
+                slots.setdefault(conv_index[k], {})[kind] = j
+                j += 1
+        i_used = i
+        for ci in (conv_index[k] for k in lids if g.layers[k].op == _lib.OP_CONV):
+            if ci in slots:
+                slots[ci]["i"] = i_used
+        i += 1
+    out = []
+    for ci in range(len(g.conv_layers)):
+        s = slots.get(ci)
+        if s is None or "conv" not in s:
+            raise ValueError(f"conv {ci} is not reachable from its sub-model's outputs: Keras would not create it")
+        out.append((s["i"], s["conv"], s.get("bn")))
+    return out
 
 
 def build_graph_legacy(model_config, nclasses=0) -> Graph:

@@ -26,9 +26,11 @@ class Inference:
         return bboxes, classes, scores
 
 
-def gather_detections_batched(bboxes, class_indices, scores, selected, num_valid):
+def gather_detections_batched(bboxes, class_indices, scores, selected, num_valid, packed=False):
     """Batched, zero-padded device version of ``gather_valid_detections_results``:
-    -> (boxes [B,max,4] f32, classes [B,max] i64, scores [B,max] f32); rows >= num_valid[b] are zero."""
+    -> (boxes [B,max,4] f32, classes [B,max] i64, scores [B,max] f32); rows >= num_valid[b] are zero.
+    ``packed=True`` appends the float32 record tensor [B, max*6 + 1] of ``distributed.pack_detections``, written by the
+    same kernel."""
     ctx = _lib.context()
     B, N = scores.shape
     mx = selected.shape[1]
@@ -36,9 +38,13 @@ def gather_detections_batched(bboxes, class_indices, scores, selected, num_valid
     ob = torch.empty((B, mx, 4), dtype=torch.float32, device=dev)
     oc = torch.empty((B, mx), dtype=torch.int64, device=dev)
     os_ = torch.empty((B, mx), dtype=torch.float32, device=dev)
-    _lib.check(_lib.lib().y3_gather_detections(ctx.handle, _lib.ptr(bboxes), _lib.ptr(class_indices), _lib.ptr(scores),
-                                               _lib.ptr(selected), _lib.ptr(num_valid), B, N, mx, _lib.ptr(ob),
-                                               _lib.ptr(oc), _lib.ptr(os_), _lib.stream_ptr()))
+    rec = torch.empty((B, mx * 6 + 1), dtype=torch.float32, device=dev) if packed else None
+    _lib.check(_lib.lib().y3_gather_detections_packed(ctx.handle, _lib.ptr(bboxes), _lib.ptr(class_indices),
+                                                      _lib.ptr(scores), _lib.ptr(selected), _lib.ptr(num_valid), B, N, mx,
+                                                      _lib.ptr(ob), _lib.ptr(oc), _lib.ptr(os_), _lib.ptr(rec),
+                                                      _lib.stream_ptr()))
+    if packed:
+        return ob, oc, os_, rec
     return ob, oc, os_
 
 
@@ -51,7 +57,7 @@ class Detector:
     (yolo_decode -> YoloNmsLayer).  Results are identical either way."""
 
     def __init__(self, model: Y3Model, anchors_table, nclasses, yolo_max_boxes=100, nms_iou_threshold=0.5,
-                 nms_score_threshold=0.1, fused=True):
+                 nms_score_threshold=0.1, fused=True, check_status=True):
         self.model = model
         self.anchors = np.asarray(anchors_table, dtype=np.float32)
         self.nclasses = int(nclasses)
@@ -59,6 +65,11 @@ class Detector:
         self.iou_thr = float(nms_iou_threshold)
         self.score_thr = float(nms_score_threshold)
         self.fused = fused
+        # NMS reports a per-image status (1 = its kept list overflowed: only possible with a score threshold <= 0, where
+        # suppressed all-zero boxes stay candidates).  Eager calls raise on it (one device->host read); inside a CUDA
+        # graph capture nothing can be read back, so the status tensor is left in ``last_status`` for the caller.
+        self.check_status = check_status
+        self.last_status = None
         self.nms_layer = YoloNmsLayer(yolo_max_boxes, nms_iou_threshold, nms_score_threshold)
 
     @classmethod
@@ -84,9 +95,13 @@ class Detector:
         if self.fused:
             # pitched head outputs (pixel pitch rounded up to 4 floats): TMA-store epilogue in the head convs
             grids = self.model(x, padded=True)
-            bboxes, conf, probs, scores, cls = yolo_decode(grids, self.anchors, self.nclasses, with_scores=True)
+            # compact decode: NMS reads boxes and scores only, so objectness / class probabilities are never written
+            bboxes, _, _, scores, cls = yolo_decode(grids, self.anchors, self.nclasses, compact=True)
             sel, nvalid, status = nms_padded(bboxes, scores, self.max_boxes, self.iou_thr, self.score_thr)
             self.last_status = status
+            if self.check_status and not torch.cuda.is_current_stream_capturing() and int(status.max().item()) != 0:
+                raise _lib.Y3Unsupported("NMS kept-list overflow: more than 1024 surviving boxes without a positive "
+                                         "coordinate (selected indices / num_valid are truncated)")
             return bboxes, cls, scores, sel, nvalid
         grids = self.model(x)
         decoded = yolo_decode(grids, self.anchors, self.nclasses)
@@ -95,11 +110,12 @@ class Detector:
     __call__ = detect
     predict = detect
 
-    def detections(self, x):
-        """detect + batched gather: (boxes [B,max,4], classes [B,max], scores [B,max], num_valid [B])."""
+    def detections(self, x, packed=False):
+        """detect + batched gather: (boxes [B,max,4], classes [B,max], scores [B,max], num_valid [B]); ``packed=True``
+        appends the float32 record tensor [B, max*6 + 1] the multi-GPU gather sends (same kernel)."""
         bboxes, cls, scores, sel, nvalid = self.detect(x)
-        ob, oc, os_ = gather_detections_batched(bboxes, cls, scores, sel, nvalid)
-        return ob, oc, os_, nvalid
+        out = gather_detections_batched(bboxes, cls, scores, sel, nvalid, packed=packed)
+        return out[:3] + (nvalid,) + out[3:]
 
     def detections_graphed(self, x, packed=False, static_input=False):
         """``detections`` replayed from a CUDA graph: the ~80 launches of a step (75 convs with their programmatic
@@ -110,13 +126,14 @@ class Detector:
         sends.  ``static_input=True``: the caller promises to reuse this very tensor (same memory) for later batches --
         a serving loop that rotates a few device input buffers -- so the graph reads it in place and the copy into a
         static input (133 MB per 64-image batch) is skipped; one graph is kept per such buffer."""
-        if static_input and not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
-            raise ValueError("static_input needs a contiguous float32 CUDA tensor")
-        key = (tuple(x.shape), x.device.index, bool(packed), x.data_ptr() if static_input else None)
+        if static_input and not (x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.is_contiguous()):
+            raise ValueError("static_input needs a contiguous float32 or uint8 CUDA tensor")
+        key = (tuple(x.shape), x.device.index, bool(packed), x.dtype, x.data_ptr() if static_input else None)
         graphs = self.__dict__.setdefault("_graphs", {})
         ent = graphs.get(key)
         if ent is None:
-            static_x = x if static_input else torch.empty_like(x, dtype=torch.float32).contiguous()
+            static_x = x if static_input else torch.empty_like(
+                x, dtype=torch.uint8 if x.dtype == torch.uint8 else torch.float32).contiguous()
             if not static_input:
                 static_x.copy_(x)
             side = torch.cuda.Stream(device=x.device)
@@ -127,10 +144,7 @@ class Detector:
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                outs = self.detections(static_x)
-                if packed:
-                    from .distributed import pack_detections
-                    outs = tuple(outs) + (pack_detections(*outs),)
+                outs = self.detections(static_x, packed=packed)
             ent = graphs[key] = (g, static_x, outs)
         g, static_x, outs = ent
         if not static_input:

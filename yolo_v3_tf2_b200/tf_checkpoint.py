@@ -19,9 +19,11 @@ tensorflow/core/protobuf/tensor_bundle.proto, tensorflow/core/lib/io/table_forma
   .data-SSSSS-of-NNNNN = raw little-endian tensor bytes at [offset, offset + size)
 
 Keras object-based variable names: ``layer_with_weights-<i>/layer_with_weights-<j>/<var>/.ATTRIBUTES/VARIABLE_VALUE``
-where i enumerates the sub-models with weights in ``model.layers`` order (backbone, neck0, head0, neck1, head1, neck2,
-head2 = the reference's sub_models_configs order) and j the layers with weights inside the sub-model in creation order
-(conv2d, batch_normalization, conv2d_1, ...); <var> is kernel / bias / gamma / beta / moving_mean / moving_variance.
+where i enumerates the sub-models with weights in ``model.layers`` order and j the layers with weights inside the
+sub-model, also in ``layers`` order; <var> is kernel / bias / gamma / beta / moving_mean / moving_variance.  Keras sorts
+``Model.layers`` by decreasing depth (longest path to an output), NOT by creation order, so the sub-models of yolov3 are
+numbered backbone, neck0, neck1, neck2, head0, head1, head2 (yolov3-tiny: backbone, neck0, neck1, head0, head1); the
+mapping conv -> (i, j) is computed from the graph by ``graph.keras_weight_slots`` and passed in as ``slots``.
 Name-based (TF1-style) keys ``conv2d_<n>/kernel``, ``batch_normalization_<n>/gamma`` are accepted as well.
 
 NOT validated against a file written by TensorFlow (none can be produced here and the reference ships only 0-byte
@@ -40,6 +42,7 @@ _DT = {1: np.float32, 2: np.float64, 3: np.int32, 4: np.uint8, 5: np.int16, 6: n
        19: np.float16}
 _DT_INV = {np.dtype(v): k for k, v in _DT.items()}
 _SUFFIX = "/.ATTRIBUTES/VARIABLE_VALUE"
+_CRC_VERIFY_MAX = 1 << 16
 
 
 # ---------------------------------------------------------------- varints / protobuf wire format
@@ -117,6 +120,19 @@ def _parse_entry(buf):
 
 # ---------------------------------------------------------------- crc32c (Castagnoli), only used on small buffers
 _CRC_TABLE = None
+
+
+def _tensor_crc(arr):
+    """masked crc32c of a tensor's bytes as stored in BundleEntryProto.crc32c; None if it cannot be computed cheaply"""
+    a = np.ascontiguousarray(arr)
+    try:
+        from . import _lib
+        import ctypes as C
+        return _mask_crc(int(_lib.lib().y3_crc32c(0, a.ctypes.data_as(C.c_void_p), a.nbytes)))
+    except Exception:
+        if a.nbytes <= _CRC_VERIFY_MAX:
+            return _mask_crc(_crc32c(a.tobytes()))
+        return None
 
 
 def _crc32c(data, crc=0):
@@ -268,6 +284,12 @@ def read_checkpoint(prefix, names=None):
             a = np.fromfile(f, dtype=_DT[e["dtype"]], count=int(np.prod(e["shape"], dtype=np.int64)) if e["shape"] else 1)
             if a.nbytes != e["size"]:
                 raise ValueError(f"{name}: truncated tensor data")
+            # per-tensor checksum (BundleEntryProto.crc32c, masked), computed by the shared library's y3_crc32c (pure
+            # Python only for small tensors when the library is not built); table blocks are always verified
+            if e["crc32c"] is not None:
+                got = _tensor_crc(a)
+                if got is not None and got != e["crc32c"]:
+                    raise ValueError(f"{name}: tensor data crc32c mismatch")
             out[name] = a.reshape(e["shape"])
     finally:
         for f in files.values():
@@ -292,8 +314,30 @@ def is_checkpoint(path):
 _VARS = ("kernel", "bias", "gamma", "beta", "moving_mean", "moving_variance")
 
 
+def _object_slots(tensors):
+    """{(i, j, ...): {var: array}} for the object-based keys ``layer_with_weights-<i>/layer_with_weights-<j>/<var>``."""
+    obj = {}
+    for name, arr in tensors.items():
+        if not name.endswith(_SUFFIX):
+            continue
+        parts = name[:-len(_SUFFIX)].split("/")
+        if parts[-1] not in _VARS or len(parts) < 2:
+            continue
+        path = []
+        for comp in parts[:-1]:
+            m = re.fullmatch(r"layer_with_weights-(\d+)", comp)
+            if not m:
+                path = None
+                break
+            path.append(int(m.group(1)))
+        if path:
+            obj.setdefault(tuple(path), {})[parts[-1]] = arr
+    return obj
+
+
 def _layer_slots(tensors):
-    """Ordered list of {var: array} per layer with weights, from object-based or name-based keys."""
+    """Ordered list of {var: array} per layer with weights, from object-based or name-based keys (creation order is
+    assumed for object-based keys: only right when the caller has no graph to derive the Keras order from)."""
     obj = {}
     for name, arr in tensors.items():
         if not name.endswith(_SUFFIX):
@@ -335,9 +379,35 @@ def _layer_slots(tensors):
     return out
 
 
-def params_from_checkpoint(prefix, conv_shapes):
-    """ConvParams list in conv creation order from a Keras checkpoint of the reference's model."""
-    slots = _layer_slots(read_checkpoint(prefix))
+def params_from_checkpoint(prefix, conv_shapes, slots=None):
+    """ConvParams list in conv creation order from a Keras checkpoint of the reference's model.  ``slots`` =
+    ``graph.keras_weight_slots(g)``: per conv (i, j_conv, j_bn) of its ``layer_with_weights-<i>/layer_with_weights-<j>``
+    keys (Keras depth order); without it the keys are taken in sorted order (name-based checkpoints)."""
+    tensors = read_checkpoint(prefix)
+    obj = _object_slots(tensors) if slots is not None else {}
+    if obj:
+        out = []
+        for ci, ((k, cin, cout, bn), (i, jc, jb)) in enumerate(zip(conv_shapes, slots)):
+            conv = obj.get((i, jc))
+            if conv is None or "kernel" not in conv:
+                raise ValueError(f"checkpoint has no kernel for conv {ci} (layer_with_weights-{i}/layer_with_weights-{jc})")
+            kern = np.asarray(conv["kernel"], np.float32)
+            if kern.shape != (k, k, cin, cout):
+                raise ValueError(f"conv {ci}: checkpoint kernel shape {kern.shape}, model expects {(k, k, cin, cout)}")
+            if bn:
+                b = obj.get((i, jb))
+                if b is None or "gamma" not in b:
+                    raise ValueError(f"checkpoint has no batch-normalization variables for conv {ci}")
+                vecs = [np.asarray(b[v], np.float32) for v in ("gamma", "beta", "moving_mean", "moving_variance")]
+                if any(v.shape != (cout,) for v in vecs):
+                    raise ValueError(f"conv {ci}: batch-normalization vectors have the wrong shape")
+                out.append(ConvParams(kern, gamma=vecs[0], beta=vecs[1], mean=vecs[2], var=vecs[3]))
+            else:
+                if "bias" not in conv:
+                    raise ValueError(f"conv {ci}: checkpoint has no bias")
+                out.append(ConvParams(kern, bias=np.asarray(conv["bias"], np.float32)))
+        return out
+    slots = _layer_slots(tensors)
     out, si = [], 0
     for ci, (k, cin, cout, bn) in enumerate(conv_shapes):
         if si >= len(slots) or "kernel" not in slots[si]:
@@ -405,8 +475,11 @@ def write_checkpoint(prefix, tensors, block_entries=64):
             raw = a.tobytes()
             df.write(raw)
             shape = b"".join(_pb_bytes_field(2, _pb_varint_field(1, int(d))) for d in a.shape)
+            crc = _tensor_crc(a)
+            if crc is None:
+                raise RuntimeError("writing a checkpoint needs liby3b200.so (y3_crc32c): TensorFlow verifies every tensor's crc32c")
             ent = (_pb_varint_field(1, _DT_INV[a.dtype]) + _pb_bytes_field(2, shape) + _pb_varint_field(4, off) +
-                   _pb_varint_field(5, len(raw)) + _put_varint((6 << 3) | 5) + struct.pack("<I", 0))
+                   _pb_varint_field(5, len(raw)) + _put_varint((6 << 3) | 5) + struct.pack("<I", crc))
             entries.append((name.encode(), ent))
     header = _pb_varint_field(1, 1) + _pb_varint_field(2, 0) + _pb_bytes_field(3, _pb_varint_field(1, 1))
     items = [(b"", header)] + entries
@@ -429,22 +502,16 @@ def write_checkpoint(prefix, tensors, block_entries=64):
         f.write(footer)
 
 
-def keras_variable_names(sub_model_conv_counts, conv_shapes):
-    """Object-based names of the reference model's variables: sub-model i (in sub_models_configs order) holds
-    ``sub_model_conv_counts[i]`` convs; inside it conv and batch-normalization layers alternate in creation order."""
-    names, ci = [], 0
-    for i, n in enumerate(sub_model_conv_counts):
-        j = 0
-        for _ in range(n):
-            _, _, _, bn = conv_shapes[ci]
-            base = f"layer_with_weights-{i}/layer_with_weights-{j}"
-            j += 1
-            if bn:
-                bbase = f"layer_with_weights-{i}/layer_with_weights-{j}"
-                j += 1
-                names.append([base + "/kernel" + _SUFFIX] + [bbase + "/" + v + _SUFFIX
-                                                              for v in ("gamma", "beta", "moving_mean", "moving_variance")])
-            else:
-                names.append([base + "/kernel" + _SUFFIX, base + "/bias" + _SUFFIX])
-            ci += 1
+def keras_variable_names(slots, conv_shapes):
+    """Object-based names of the reference model's variables, per conv in creation order: [kernel, bias] or
+    [kernel, gamma, beta, moving_mean, moving_variance].  ``slots`` = ``graph.keras_weight_slots(g)``."""
+    names = []
+    for (i, jc, jb), (_, _, _, bn) in zip(slots, conv_shapes):
+        base = f"layer_with_weights-{i}/layer_with_weights-{jc}"
+        if bn:
+            bbase = f"layer_with_weights-{i}/layer_with_weights-{jb}"
+            names.append([base + "/kernel" + _SUFFIX] + [bbase + "/" + v + _SUFFIX
+                                                          for v in ("gamma", "beta", "moving_mean", "moving_variance")])
+        else:
+            names.append([base + "/kernel" + _SUFFIX, base + "/bias" + _SUFFIX])
     return names
