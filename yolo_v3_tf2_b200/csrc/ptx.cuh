@@ -114,6 +114,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// inter-CTA flags in global memory (conv_chain.cuh): release / acquire at GPU scope, and the fence that orders
+// generic-proxy accesses (the flag) against async-proxy accesses (TMA loads / stores of the data the flag guards)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// all state spaces (global + shared): writes made through one proxy become visible to accesses made through the other
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Spin until *flag >= need (monotonic counter), with the same watchdog as mbar_wait.  The successful read is an acquire.
+__device__ __forceinline__ void flag_wait_ge(const uint32_t* flag, uint32_t need, uint32_t code) {
+    if (ld_acquire_gpu(flag) >= need) return;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(flag) < need) {
+        if (clock64() - t0 > 8000000000LL) {
+            atomicExch(&g_watchdog_flag, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
