@@ -99,6 +99,27 @@ void y3_net_destroy(y3_net* net);
 int y3_net_num_convs(y3_net* net);
 int y3_net_num_outputs(y3_net* net);
 int y3_net_get_plan(y3_net* net, y3_layer_plan* plans_host, int n_layers);
+
+/* Layer chaining (csrc/conv_tc.cuh, ChainArgs): how each launch ("step", y3_net_num_steps of them) of a forward pass
+ * of B images synchronises with its producers and in which order it walks its output tiles.  A chained step waits tile
+ * by tile for the 128-row blocks of its input instead of for its whole predecessor (griddepcontrol.wait).  Planning
+ * only; works on a context without a device. */
+typedef struct y3_chain_step {
+    int32_t layer;           /* layer index of the step */
+    int32_t posts;           /* 1: its epilogue posts per-tile completion flags */
+    int32_t chained;         /* 1: waits on those flags (dep_step, res_step) */
+    int32_t dep_step;        /* step that produces its input, -1 */
+    int32_t res_step;        /* step that produces its fused residual, -1 */
+    int32_t tiles;           /* output tiles of the launch */
+    int32_t ctas;            /* CTAs (or CTA pairs) walking them */
+    int32_t tiles_n;         /* N tiles per M group */
+    int32_t rows_per_group;  /* output rows per M group: 128, or 256 for CTA pairs */
+    int32_t rev, rot;        /* sequence position q is tile (q + rot) mod tiles, counted from the end when rev */
+    int32_t run_first;       /* persistent run (csrc/conv_chain.cuh): first step of the launch this step belongs to, -1 */
+    int32_t run_len;         /* steps in that launch */
+    int32_t vshift;          /* CTA pair c walks the tile sequence of pair (c + vshift) mod ctas */
+} y3_chain_step;
+int y3_net_chain_plan(y3_net* net, int B, y3_chain_step* steps_host, int n_steps);
 int64_t y3_net_arena_bytes(y3_net* net);
 /* output k: grid height/width and channel count 3*(5+C) */
 int y3_net_output_shape(y3_net* net, int k, int* gh, int* gw, int* ch);
@@ -223,6 +244,12 @@ int y3_dbg_umma_shift(y3_ctx* ctx, const void* x, int rows, const void* w, int s
  * first operands landed, last MMA issued, first accumulator complete, epilogue hand-off / stores complete per group,
  * exit).  Pass NULL to switch it off. */
 int y3_dbg_timestamps(void* dev_u64_buffer);
+/* The same for every launch of y3_net_forward*: launch k writes at uint64 offset k * 32 * 160 of the buffer
+ * (y3_net_num_steps x 32 x 160 uint64).  Profiling build only (the release kernels carry no stamps). */
+int y3_dbg_timestamps_net(void* dev_u64_buffer);
+/* Measurement aid: 0 makes later y3_net_forward* calls launch every layer separately again (the persistent multi-layer
+ * launches of csrc/conv_chain.cuh are the default), 1 restores the default.  Results are bit-identical either way. */
+int y3_dbg_set_chain_runs(int on);
 
 /* last device-side watchdog code (0 = none) */
 int y3_watchdog_code(y3_ctx* ctx);

@@ -10,7 +10,10 @@ lib = _lib.lib()
 B = 64
 cases = [("1x1 256->128 @52", 52, 256, 128, 1, 1, False), ("3x3 128->256 @52", 52, 128, 256, 3, 1, False),
          ("3x3 128->256 @52 +res", 52, 128, 256, 3, 1, True), ("1x1 512->256 @26", 26, 512, 256, 1, 1, False),
-         ("3x3 64->128 @104 +res", 104, 64, 128, 3, 1, True), ("1x1 128->64 @104", 104, 128, 64, 1, 1, False)]
+         ("3x3 64->128 @104 +res", 104, 64, 128, 3, 1, True), ("1x1 128->64 @104", 104, 128, 64, 1, 1, False),
+         ("3x3 256->512 @26 +res", 26, 256, 512, 3, 1, True), ("3x3 512->1024 @13 +res", 13, 512, 1024, 3, 1, True)]
+if _os.environ.get("Y3_BC_CASES"):
+    cases = [c for i, c in enumerate(cases) if str(i) in _os.environ["Y3_BC_CASES"].split(",")]
 for name, g, cin, cout, k, stride, res in cases:
     x = torch.randn((B, g, g, cin), device="cuda").to(torch.bfloat16)
     bn = lib.y3_conv_block_n(cin, cout)

@@ -27,6 +27,12 @@ class LayerPlan(C.Structure):
                  "block_n", "swizzle", "stages", "flat", "padded")] + [("arena_offset", C.c_int64)]
 
 
+class ChainStep(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("layer", "posts", "chained", "dep_step", "res_step", "tiles", "ctas", "tiles_n", "rows_per_group",
+                 "rev", "rot", "run_first", "run_len", "vshift")]
+
+
 class Y3Error(RuntimeError):
     """CUDA / state failure reported by the library."""
 
@@ -60,6 +66,7 @@ SIGNATURES = {
     "y3_net_forward_pitched": (_i, [_p, _p, _i, C.POINTER(_p), C.POINTER(_i), _i, _p]),
     "y3_net_forward_u8": (_i, [_p, _p, _i, C.POINTER(_p), C.POINTER(_i), _i, _p]),
     "y3_net_num_steps": (_i, [_p]),
+    "y3_net_chain_plan": (_i, [_p, _i, C.POINTER(ChainStep), _i]),
     "y3_net_forward_timed": (_i, [_p, _p, _i, C.POINTER(_p), _i, _p, _p, _p, _i]),
     "y3_decode": (_i, [_p, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "y3_decode_pitched": (_i, [_p, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
@@ -76,6 +83,8 @@ SIGNATURES = {
     "y3_dbg_umma_shift": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p]),
     "y3_dbg_tma_tile": (_i, [_p, _p, _i, _i, _i, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "y3_dbg_timestamps": (_i, [_p]),
+    "y3_dbg_timestamps_net": (_i, [_p]),
+    "y3_dbg_set_chain_runs": (_i, [_i]),
     "y3_watchdog_code": (_i, [_p]),
 }
 

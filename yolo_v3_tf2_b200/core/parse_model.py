@@ -150,6 +150,11 @@ class Y3Model:
         _lib.check(lib.y3_net_get_plan(h, plans, len(self._descs)))
         out = {"arena_bytes": lib.y3_net_arena_bytes(h), "num_convs": lib.y3_net_num_convs(h),
                "layers": [{f: getattr(p, f) for f, _ in _lib.LayerPlan._fields_} for p in plans]}
+        # launch-level view: how every kernel of a max_batch forward pass waits for its producers (layer chaining)
+        nsteps = lib.y3_net_num_steps(h)
+        chain = (_lib.ChainStep * nsteps)()
+        _lib.check(lib.y3_net_chain_plan(h, int(max_batch), chain, nsteps))
+        out["steps"] = [{f: getattr(c, f) for f, _ in _lib.ChainStep._fields_} for c in chain]
         lib.y3_net_destroy(h)
         ctx.close()
         return out

@@ -208,6 +208,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
                 epilogue_tile(p, BLOCK_N, tile * kBlockM, 0, t_row, q, lane, xp);
                 tc_fence_before();
                 mbar_arrive(tempty_bar(acc));
+                epilogue_tile_post(p, tile * kBlockM + q * 32, lane);
             }
         }
     } else if (warp >= 4 + 4 * NEPI) {

@@ -25,6 +25,37 @@
 
 namespace y3 {
 
+// Cross-layer tile flags ("layer chaining").  A conv layer normally starts its main loop with
+// griddepcontrol.wait, i.e. after its predecessor has finished completely: per launch that costs the predecessor's tail
+// (last tile's epilogue, store drain, teardown), this layer's ramp (first operands from a cold pipeline) and the idle
+// SMs of the predecessor's last, partial round of tiles.  With the flags a layer instead waits, tile by tile, for
+// exactly the 128-row M tiles of its input that the tile reads:
+//   producer  every epilogue warp, once the bulk stores of its 32 rows x BLOCK_N block have completed, adds 1 to
+//             post_flags[row / 128] and to post_done (red.release.gpu)
+//   consumer  the TMA producer warp polls dep_flags[t] >= dep_need for the M tiles t its next A tile reads (3x3: the
+//             rows above and below included); the epilogue warps do the same for the residual rows; once
+//             dep_done == dep_total the whole input is known to be complete and the polls stop
+//   gate      before a CTA executes griddepcontrol.launch_dependents it waits until the layer TWO launches back has
+//             completed (gate_done == gate_total).  Layer K+1 can therefore only be resident once layer K-2 is
+//             finished: at most three layers are in flight, which is what the arena planner's live ranges assume
+//             (a buffer is not reused until two launches after its last reader).
+// All pointers are null when the feature is off (single-layer entry points, layers fed by a concat or a non-conv
+// kernel): the kernel then uses griddepcontrol.wait as before.  Counters are zeroed at the start of every forward pass.
+struct ChainArgs {
+    uint32_t* post_flags;        // [CL * ceil(tiles_m / CL) + 1] arrivals per 128-row M tile of THIS layer's output
+    uint32_t* post_done;         // arrivals over all tiles
+    const uint32_t* dep_flags;   // producer of the A operand
+    const uint32_t* dep_done;
+    uint32_t dep_need, dep_total;
+    int dep_h, dep_w;            // spatial size of the A operand (rows / columns per image)
+    const uint32_t* res_flags;   // producer of the residual (same pixel indexing as this layer's output)
+    const uint32_t* res_done;
+    uint32_t res_need, res_total;
+    const uint32_t* gate_done;   // the layer two launches back
+    uint32_t gate_total;
+    uint32_t mode;               // profiling build only (Y3_CHAIN_MODE): 1 = post with red.release instead of red.relaxed
+};
+
 struct ConvArgs {
     int M;                 // B*Ho*Wo
     int Ho, Wo;            // output spatial size
@@ -59,6 +90,10 @@ struct ConvArgs {
     const void* src;       // bf16 NHWC view, or the fp32 [B,H,W,3] image for the stem
     long long src_stride;  // elements between consecutive input pixels
     int H, W;              // input spatial size
+    int rot;               // tile sequence rotation: position seq of the sequence is tile (seq + rot) mod num_tiles (before
+                           //    rev is applied); the planner picks it so that a chained layer starts on tiles whose input
+                           //    its predecessor completed a round ago instead of on the ones still in flight
+    ChainArgs ch;          // cross-layer tile flags, all null = off
     int rev;               // 1: walk the output tiles from the last to the first.  The planner alternates the direction from
                            //    layer to layer so that a layer starts on the pixels its predecessor wrote LAST, which are
                            //    still in L2 (each 52x52 tensor is 88 MB of a 126 MB L2)
@@ -73,12 +108,81 @@ struct ConvArgs {
                            // 4 producer skips the A loads, 8 no MMAs are issued (results are garbage)
 };
 
-// position in a CTA's tile sequence -> tile id (see ConvArgs::rev)
-__device__ __forceinline__ int tile_id(const ConvArgs& p, int seq, int num_tiles) { return p.rev ? num_tiles - 1 - seq : seq; }
-
 constexpr int kConvEpiGroups = 2;   // epilogue warp groups; group g drains accumulator stage g (tiles j % 2 == g)
 constexpr int kConvThreads = 32 * (4 + 4 * kConvEpiGroups);
 constexpr int kBlockM = 128;
+
+// position in a CTA's tile sequence -> tile id (see ConvArgs::rev)
+__device__ __forceinline__ int tile_id(const ConvArgs& p, int seq, int num_tiles) {
+    seq += p.rot;
+    if (seq >= num_tiles) seq -= num_tiles;
+    return p.rev ? num_tiles - 1 - seq : seq;
+}
+
+// ---- layer chaining (ChainArgs) ----
+// The gate is executed by one thread of the CTA during the prologue, ahead of the CTA-wide barrier that precedes
+// griddepcontrol.launch_dependents (issued by every thread: one thread's trigger does not release the successor).
+__device__ __forceinline__ bool chain_enabled(const ConvArgs& p) { return p.ch.dep_flags != nullptr; }
+__device__ __forceinline__ void chain_gate(const ConvArgs& p) {
+    if (p.ch.gate_done != nullptr) flag_wait_ge(p.ch.gate_done, p.ch.gate_total, 0x900);
+}
+// Whole warp: wait until every input pixel read by the A tile of output rows [m0, m0 + 128) has been written.  Returns
+// true once the whole producer layer is known to be complete (the caller then stops calling).
+__device__ __forceinline__ bool chain_wait_a(const ConvArgs& p, int m0, int lane) {
+    const ChainArgs& c = p.ch;
+    uint32_t d = 0;
+    if (lane == 0) d = ld_acquire_gpu(c.dep_done);
+    d = __shfl_sync(0xffffffffu, d, 0);
+    if (d >= c.dep_total) {
+        fence_proxy_async_all();
+        return true;
+    }
+    if (m0 >= p.M) return false;   // phantom tile of an odd pair: reads nothing that matters
+    const int m1 = min(m0 + kBlockM, p.M) - 1;
+    int lo = m0, hi = m1;
+    if (p.a_im2col) {
+        const int hw = p.Ho * p.Wo;
+        const int n0 = m0 / hw, y0 = (m0 - n0 * hw) / p.Wo;
+        const int n1 = m1 / hw, y1 = (m1 - n1 * hw) / p.Wo;
+        const int yi0 = max(0, y0 * p.stride + p.lower);
+        const int yi1 = min(c.dep_h - 1, y1 * p.stride + p.lower + p.ksize - 1);
+        lo = (n0 * c.dep_h + yi0) * c.dep_w;
+        hi = (n1 * c.dep_h + yi1) * c.dep_w + c.dep_w - 1;
+    }
+    for (int t = (lo >> 7) + lane; t <= (hi >> 7); t += 32) flag_wait_ge(c.dep_flags + t, c.dep_need, 0x910);
+    __syncwarp();
+    fence_proxy_async_all();   // the acquires above (generic proxy) order the TMA loads that follow (async proxy)
+    return false;
+}
+// One lane, after the global writes of output rows [row, row + 32) of one tile have completed and are visible to it.
+// The layer-wide counter is posted once per warp, when it is done (chain_post_done): nobody needs it earlier.
+// The increment itself is relaxed: the caller has already waited for the COMPLETION of the bulk stores it announces
+// (cp.async.bulk.wait_group, not .read -- the data is in L2 before the reduction is even issued), or has fenced its
+// ordinary stores (epilogue_tile_post).  A red.release here compiles to MEMBAR.ALL.GPU + RED and cost 0.3 ms per
+// forward pass (measured, ChainArgs::mode bit 0 of the profiling build selects it for comparison).
+__device__ __forceinline__ void chain_post(const ConvArgs& p, int row) {
+#ifdef Y3_PROFILING
+    if (p.ch.mode & 1u) {
+        red_release_gpu_add(p.ch.post_flags + (row >> 7), 1u);
+        return;
+    }
+#endif
+    red_relaxed_gpu_add(p.ch.post_flags + (row >> 7), 1u);
+}
+__device__ __forceinline__ void chain_post_done(const ConvArgs& p, uint32_t tiles) {
+    if (tiles) red_relaxed_gpu_add(p.ch.post_done, tiles);
+}
+// Whole warp, after epilogue_tile (ordinary st.global by every lane): make all lanes' stores visible, then post once.
+__device__ __forceinline__ void epilogue_tile_post(const ConvArgs& p, int row, int lane) {
+    if (p.ch.post_flags == nullptr) return;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        chain_post(p, row);
+        chain_post_done(p, 1u);
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------------------------------
 // Epilogue of one 128 x BLOCK_N accumulator tile, executed by one of the four epilogue warps (TMEM lane quarter q).
@@ -322,7 +426,21 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
     pr.load(p, et, block_n, q);
     pf = pr;
     uint32_t g = 0, gp = 0;  // their running chunk numbers; chunk n lives in ring slot n % NBUF
+    bool res_all = p.ch.res_flags == nullptr;   // chained layer: the residual's producer may still be running
+    // posting (chained layers): a cursor that trails `pr` by kPostLag bulk-store groups.  A tile is posted once that
+    // many newer groups have been committed, so the wait for its stores' completion never actually stalls.
+    constexpr int kPostLag = 4;
+    const bool posting = p.ch.post_flags != nullptr;
+    EpiCursor<CW> pp = pr;
+    uint32_t pp_gend = pp.valid ? (uint32_t)pp.nch : 0u;   // groups committed once pp's tile has been issued completely
+    uint32_t posted = 0;
     auto issue_res = [&]() {   // lane 0 only
+        if (!res_all && pf.c == 0 && pf.row < p.M) {
+            // first chunk of a tile: its 32 residual rows must have been written (later chunks are the same rows)
+            if (ld_acquire_gpu(p.ch.res_done) >= p.ch.res_total) res_all = true;
+            else flag_wait_ge(p.ch.res_flags + (pf.row >> 7), p.ch.res_need, 0x920);
+            fence_proxy_async_all();
+        }
         const uint32_t b = gp % NBUF;
         mbar_arrive_expect_tx(res_bar0 + 8u * b, BUF_BYTES);
         tma_load_2d(stg + b * BUF_BYTES, tmR, res_bar0 + 8u * b, pf.ncol, pf.row);
@@ -425,6 +543,11 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
                 if (!(Y3_DBG_BITS(p) & 2)) tma_store_2d(tmO, buf, pr.ncol, pr.row);
                 tma_store_commit();
                 if (stamp && g == 1) ts_clock(ts, 21);   // store issued
+                if (posting && pp.valid && g + 1 >= pp_gend + kPostLag) {
+                    tma_store_wait<kPostLag>();   // everything but the kPostLag newest groups has completed
+                    chain_post(p, pp.row);
+                    ++posted;
+                }
                 if (has_res && pf.valid) {
                     // all stores but the one just issued have read their buffers: the slot of chunk g - 1 is free,
                     // and it is the slot of chunk gp = g + NBUF - 1
@@ -437,6 +560,11 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
                 pf.next(p, et, block_n, q);
                 ++gp;
             }
+            if (posting && pp.valid && g + 1 >= pp_gend + kPostLag) {   // lane 0 has just posted pp's tile
+                pp.tile += et.step;
+                pp.load(p, et, block_n, q);
+                if (pp.valid) pp_gend += (uint32_t)pp.nch;
+            }
         }
         pr.next(p, et, block_n, q);
         ++g;
@@ -444,6 +572,15 @@ __device__ __forceinline__ void epilogue_role_tma(const ConvArgs& p, const CUten
     if (lane == 0) {
         if (q == 0) ts_mark(ts, ts_slot);         // last chunk handed to the TMA
         tma_store_wait<0>();                      // every bulk store has completed (not just been read) before exit
+        if (posting) {
+            while (pp.valid) {
+                chain_post(p, pp.row);
+                ++posted;
+                pp.tile += et.step;
+                pp.load(p, et, block_n, q);
+            }
+            chain_post_done(p, posted);
+        }
         if (q == 0) ts_mark(ts, ts_slot + 2);
     }
 }
@@ -532,9 +669,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_alloc(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish();
     }
-    if (warp == 3 && lane == 0 && p.tma_out) {
-        tma_prefetch_desc(&tmO);
-        if (p.residual) tma_prefetch_desc(&tmR);
+    if (warp == 3 && lane == 0) {
+        if (p.tma_out) {
+            tma_prefetch_desc(&tmO);
+            if (p.residual) tma_prefetch_desc(&tmR);
+        }
+        chain_gate(p);   // chained layers: the layer two launches back is complete before any thread lets the successor start
     }
     tc_fence_before();
     __syncthreads();
@@ -552,8 +692,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
     // from here on we touch activations it wrote (and buffers it may still be reading), so wait for it to finish.
-    pdl_launch_dependents();
-    pdl_wait();
+    // chained layers (ChainArgs) wait tile by tile in the producer / epilogue warps instead
+    const bool chained = chain_enabled(p);
+    pdl_launch_dependents();   // chained: the gate (chain_gate) was passed before the barrier above
+    if (!chained) pdl_wait();
 
     // The two single-thread roles run their loops with the WHOLE warp (uniform control flow, so the compiler keeps
     // addresses / descriptors / barrier phases in uniform registers) and predicate only the issuing instructions on
@@ -565,6 +707,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
+        bool dep_all = false;   // chained: the whole input has been seen complete
         const int hw = p.Ho * p.Wo;
         auto load_b = [&](int st, int kcoord, int n0) {
             if (CLUSTER == 1) {
@@ -582,6 +725,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m0 = tm * kBlockM;
             const int n0 = tn * BLOCK_N;
             int kcoord = 0;   // K coordinate of the weight tile
+            if (chained && !dep_all) dep_all = chain_wait_a(p, m0, lane);
             if (p.a_im2col) {
                 const int cn = m0 / hw;
                 const int rem = m0 - cn * hw;
@@ -691,6 +835,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // all TMEM reads of this accumulator are complete (wait::ld) -> hand it back to the MMA warp
                 tc_fence_before();
                 mbar_arrive(tempty_bar(acc));
+                epilogue_tile_post(p, tm * kBlockM + q * 32, lane);
             }
         }
     }

@@ -99,9 +99,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_alloc2(tmem_ptr_smem, TMEM_COLS);
         tmem_relinquish2();
     }
-    if (warp == 3 && lane == 0 && p.tma_out) {
-        tma_prefetch_desc(&tmO);
-        if (p.residual) tma_prefetch_desc(&tmR);
+    if (warp == 3 && lane == 0) {
+        if (p.tma_out) {
+            tma_prefetch_desc(&tmO);
+            if (p.residual) tma_prefetch_desc(&tmR);
+        }
+        chain_gate(p);   // chained layers: the layer two launches back is complete before any thread lets the successor start
     }
     tc_fence_before();
     __syncthreads();
@@ -122,8 +125,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0) ts_mark(p.ts, 1);   // prologue done
     // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
     // from here on we touch activations it wrote (and buffers it may still be reading), so wait for it to finish.
-    pdl_launch_dependents();
-    pdl_wait();
+    // chained layers (ChainArgs) wait tile by tile in the producer / epilogue warps instead
+    const bool chained = chain_enabled(p);
+    pdl_launch_dependents();   // chained: the gate (chain_gate) was passed before the barrier above
+    if (!chained) pdl_wait();
     if (threadIdx.x == 0) ts_mark(p.ts, 2);   // predecessor grid complete
 
     if (warp == 0) {
@@ -131,6 +136,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool leader_lane = elect_one();
         int stage = 0;
         uint32_t phase = 0;
+        bool dep_all = false;   // chained: the whole input has been seen complete
         const int hw = p.Ho * p.Wo;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             const int tid_ = tile_id(p, tile, num_tiles);
@@ -139,6 +145,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int m0 = tm * kBlockM;
             const int nb = tn * BLOCK_N + cta_rank * (BLOCK_N / 2);   // this CTA's half of the weight rows
             int kcoord = 0;
+            if (chained && !dep_all) dep_all = chain_wait_a(p, m0, lane);
             if (p.a_im2col) {
                 const int cn = m0 / hw;
                 const int rem = m0 - cn * hw;
@@ -267,6 +274,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc_fence_before();
                 if (is_leader) mbar_arrive(tempty_bar(acc));
                 else mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+                epilogue_tile_post(p, tm * kBlockM + q * 32, lane);
             }
         }
     }

@@ -114,7 +114,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// inter-CTA flags in global memory (conv_chain.cuh): release / acquire at GPU scope, and the fence that orders
+// inter-CTA flags in global memory (ChainArgs in conv_tc.cuh): release / acquire at GPU scope, and the fence that orders
 // generic-proxy accesses (the flag) against async-proxy accesses (TMA loads / stores of the data the flag guards)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -130,6 +130,9 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // all state spaces (global + shared): writes made through one proxy become visible to accesses made through the other
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -139,6 +142,7 @@ __device__ __forceinline__ void flag_wait_ge(const uint32_t* flag, uint32_t need
     if (ld_acquire_gpu(flag) >= need) return;
     const long long t0 = clock64();
     while (ld_acquire_gpu(flag) < need) {
+        __nanosleep(32);
         if (clock64() - t0 > 8000000000LL) {
             atomicExch(&g_watchdog_flag, code);
             __threadfence_system();
@@ -243,6 +247,14 @@ __device__ __forceinline__ void tma_store_wait() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ uint32_t ld_shared_acquire_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_release_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }

@@ -20,6 +20,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "conv_flat.cuh"
+#include "conv_chain.cuh"
 #include "decode.cuh"
 #include "nms.cuh"
 #include "preprocess.cuh"
@@ -163,6 +164,9 @@ int epi_chunk_cols(int block_n, bool has_residual) {
 
 // profiling: device buffer for the per-CTA timestamps of the CTA-pair conv kernel (y3_dbg_timestamps)
 unsigned long long* g_ts_ptr = nullptr;
+// the same for a whole forward pass: launch (step) k of y3_net_forward writes its stamps at offset k * 32 * 160
+unsigned long long* g_ts_net_ptr = nullptr;
+constexpr int kTsNetStride = 32 * 160;
 
 // TMA-store epilogue (Y3_TMA_EPI=0 falls back to the register-transpose epilogue, for A/B measurements)
 const bool g_use_tma_epi = env_int("Y3_TMA_EPI", 1) != 0;
@@ -249,6 +253,25 @@ __host__ __device__ inline int stem_col_k(int sx, int i, bool lo) {
 
 // weights-resident variants of the conv kernels (BRES): Y3_BRES=0 disables them
 const bool g_use_bres = env_int("Y3_BRES", 1) != 0;
+// cross-layer tile flags (ChainArgs in conv_tc.cuh): Y3_CHAIN=0 makes every layer wait for its whole predecessor again;
+// Y3_CHAIN_ROT=0 keeps the flags but not the rotated tile order
+// Y3_CHAIN: 0 every layer is its own launch and waits for its whole predecessor (griddepcontrol.wait);
+//           1 (default) runs of consecutive CTA-pair layers execute as ONE persistent launch (conv_chain.cuh);
+//           2 experiment: separate launches chained through the flags; 3 experiment: flags posted, nobody waits
+const int g_chain_kind = env_int("Y3_CHAIN", 1);
+const bool g_use_chain = g_chain_kind != 0;
+const bool g_chain_runs = g_chain_kind == 1;
+const bool g_chain_post_only = g_chain_kind == 3;
+const int g_chain_mode = env_int("Y3_CHAIN_MODE", 0);             // ChainArgs::mode
+bool g_chain_runs_rt = true;   // y3_dbg_set_chain_runs: A/B measurements of the persistent runs inside one process
+const bool g_chain_vshift = env_int("Y3_CHAIN_VSHIFT", 1) != 0;   // rotate the extra-tile owners from layer to layer
+// a chained layer starts this many full rounds before its producer's partial last round (flags of the very last full
+// round are posted only about when the early CTAs arrive)
+const int g_chain_slack = env_int("Y3_CHAIN_SLACK", 1);
+// layers whose CTAs walk more rounds of tiles than this do not post (and their consumers are not chained): per-tile
+// posting costs more there than the ramp / tail / partial round it would hide
+const int g_chain_max_rounds = env_int("Y3_CHAIN_MAXR", 64);
+const bool g_use_chain_rot = env_int("Y3_CHAIN_ROT", 1) != 0;
 
 template <int BN, int SWZ, int ST, int CL>
 cudaError_t launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
@@ -564,7 +587,26 @@ struct Step {
     int stem_col = 0;      // stem through the column-sharing producer (stride 1, pad 1)
     int tma_out = 0;       // epilogue writes through tmO (and reads the residual through tmR)
     int rev = 0;           // walk the output tiles backwards (alternates from conv to conv, see ConvArgs::rev)
+    long long sync_off = -1;   // tc conv: word offset of this step's [done (32 words) | per-M-tile flags] in y3_net::sync
     CUtensorMap tmA, tmB, tmO, tmR;
+};
+
+// ---- layer chaining (ChainArgs in conv_tc.cuh): what one tensor-core conv step looks like at this batch size ----
+struct ChainStep {
+    bool posts = false;          // its epilogue warps post per-M-tile flags + the done counter
+    uint32_t need = 0, total = 0;
+    uint32_t* done = nullptr;
+    uint32_t* flags = nullptr;
+    // tile sequence of the launch: T tiles walked by G CTAs (or clusters); tile -> (M group = tile / tiles_n, N tile);
+    // one M group is rg output rows; sequence position seq is tile (seq + rot) mod T, mirrored when rev
+    int T = 0, G = 1, tiles_n = 1, rg = y3::kBlockM;
+    int rev = 0, rot = 0;
+    long long M = 0;
+    // consumer side: waits tile by tile on step ps (A operand) and rs (residual, -1: none) instead of griddepcontrol.wait
+    bool chained = false;
+    int ps = -1, rs = -1;
+    // persistent runs (conv_chain.cuh): steps [run_first, run_first + run_len) are one launch on run_pairs CTA pairs
+    int run_first = -1, run_len = 0, run_pairs = 0, vshift = 0;
 };
 
 }  // namespace
@@ -584,6 +626,19 @@ struct y3_net {
     uint8_t* arena = nullptr;
     bool maps_built = false;
     float* x_scratch = nullptr;        // float32 copy of a uint8 input, only for stems without a uint8 kernel
+    // layer chaining (ChainArgs): counters of every tensor-core conv step, zeroed at the start of each forward pass
+    bool chain = false;                // planned for it (arena live ranges extended by two launches)
+    uint32_t* sync = nullptr;
+    long long sync_words = 0;
+    std::vector<int> tensor_step;      // tensor id -> index of the ONE step that writes it (-1: none / several)
+    // persistent runs (conv_chain.cuh): device arrays of ChainLayer, built once per batch size
+    struct RunSet {
+        std::vector<ChainStep> chain;
+        y3::ChainLayer* dev = nullptr;     // all runs' layers, step order
+        y3::ChainLayer* host = nullptr;    // pinned staging copy (kept: a captured graph re-reads it on every replay)
+        std::vector<int> dev_index;        // step -> index into dev (-1: not in a run)
+    };
+    std::map<int, RunSet> runsets;
 };
 
 namespace {
@@ -828,6 +883,9 @@ int plan_net(y3_net& n) {
     }
 
     // ---- steps ----
+    n.chain = g_use_chain && g_use_pdl && !g_use_flat;
+    n.tensor_step.assign(L + 1, -1);
+    n.sync_words = 0;
     int conv_counter = 0;
     n.convs.assign(n.conv_layer.size(), ConvWeights{});
     auto touch = [&](int tensor, int step) {
@@ -867,7 +925,10 @@ int plan_net(y3_net& n) {
                 const long long clusters = std::max(1, n.ctx->sms / 2);
                 const long long r256 = (pairs * ((s.cout_p + 255) / 256) + clusters - 1) / clusters;
                 const long long r128 = (pairs * ((s.cout_p + 127) / 128) + clusters - 1) / clusters;
-                if ((double)r128 * 0.5 * 1.10 < (double)r256 * 0.97) {
+                // ... which only matters when every layer is a launch of its own: inside a persistent run the partial
+                // rounds even out over the layers and the wider tile wins (4.96 -> 4.79 ms forward, Y3_BN_QUANT)
+                static const bool quant = env_int("Y3_BN_QUANT", g_chain_runs ? 0 : 1) != 0;
+                if (quant && (double)r128 * 0.5 * 1.10 < (double)r256 * 0.97) {
                     s.cfg.block_n = 128;
                     s.cfg.stages = st2(128);
                 }
@@ -912,11 +973,22 @@ int plan_net(y3_net& n) {
             // alternate the tile direction from conv to conv (Y3_REV=0 disables): the next layer starts where this one ended
             static const bool use_rev = env_int("Y3_REV", 1) != 0;
             s.rev = (use_rev && s.kind == 1 && !s.flat) ? (s.conv_idx & 1) : 0;
+            // TMA-store epilogue: bf16 output, dense pixel indexing, no fused upsample
+            s.tma_out = 0;
+            if (s.kind == 1 && g_use_tma_epi && !n.tensors[writes[i]].fp32_output && !s.fused_up && !s.flat && !s.in_padded &&
+                !s.out_padded)
+                s.tma_out = epi_chunk_cols(s.cfg.block_n, s.src2 >= 0);
             pl.kernel = s.kind;
             pl.fused_add = residual[i];
             pl.fused_upsample = fused_up[i];
             const int step_id = (int)n.steps.size();
             touch(s.src, step_id); touch(s.src2, step_id); touch(s.dst, step_id);
+            if (s.kind == 1) {
+                n.tensor_step[s.dst] = step_id;
+                const long long tiles_m = ((long long)n.max_batch * s.Ho * s.Wo + y3::kBlockM - 1) / y3::kBlockM;
+                s.sync_off = n.sync_words;
+                n.sync_words += 32 + ((tiles_m + 2 + 31) / 32) * 32;
+            }
             n.steps.push_back(s);
         } else if (d.op == Y3_OP_MAXPOOL) {
             Step s;
@@ -980,9 +1052,12 @@ int plan_net(y3_net& n) {
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return n.buffers[x].first < n.buffers[y].first; });
     int64_t top = 0;
+    // chained layers: up to three consecutive launches are in flight at once (ChainArgs gate), so a buffer may only
+    // be reused by a tensor first written more than two launches after its last reader
+    const int live_ext = n.chain ? 2 : 0;
     for (int bi : order) {
         BufferInfo& b = n.buffers[bi];
-        live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last < b.first; }), live.end());
+        live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last + live_ext < b.first; }), live.end());
         std::sort(live.begin(), live.end(), [](const Live& x, const Live& y) { return x.off < y.off; });
         const int64_t need = (b.bytes + 1023) & ~1023LL;
         int64_t off = 0;
@@ -1045,10 +1120,7 @@ int build_maps(y3_net& n) {
         const TensorInfo& o = n.tensors[s.dst];
         std::memset(&s.tmO, 0, sizeof(s.tmO));
         std::memset(&s.tmR, 0, sizeof(s.tmR));
-        s.tma_out = 0;
-        if (g_use_tma_epi && !o.fp32_output && !s.fused_up && !s.flat && !s.in_padded && !s.out_padded)
-            s.tma_out = epi_chunk_cols(s.cfg.block_n, s.src2 >= 0);
-        if (s.tma_out) {
+        if (s.tma_out) {   // decided by the planner
             const int cw = s.tma_out;
             const uint64_t rows = (uint64_t)n.max_batch * s.Ho * s.Wo;
             rc = make_map_epi(n.ctx->drv, &s.tmO, tensor_ptr(n, s.dst), rows, s.cout_p, o.pix_stride, cw);
@@ -1231,6 +1303,14 @@ int y3_net_create(y3_ctx* ctx, const y3_layer_desc* layers, int n_layers, int H,
             return fail(Y3_ERR_CUDA, std::string("cudaMalloc(arena): ") + cudaGetErrorString(e));
         }
         cudaMemset(n->arena, 0, (size_t)n->arena_bytes);
+        if (n->chain && n->sync_words > 0) {
+            e = cudaMalloc(&n->sync, (size_t)n->sync_words * sizeof(uint32_t));
+            if (e != cudaSuccess) {
+                y3_net_destroy(n);
+                return fail(Y3_ERR_CUDA, std::string("cudaMalloc(sync): ") + cudaGetErrorString(e));
+            }
+            cudaMemset(n->sync, 0, (size_t)n->sync_words * sizeof(uint32_t));
+        }
         for (ConvWeights& w : n->convs) {
             const size_t K = (size_t)w.k * w.k * w.cin;
             const size_t wbytes = w.direct ? K * w.cout * 4 : (size_t)w.cout_pad * (w.stem_hilo ? 64 : K) * 2;
@@ -1253,6 +1333,11 @@ void y3_net_destroy(y3_net* net) {
     if (!net) return;
     if (net->arena) cudaFree(net->arena);
     if (net->x_scratch) cudaFree(net->x_scratch);
+    if (net->sync) cudaFree(net->sync);
+    for (auto& kv : net->runsets) {
+        if (kv.second.dev) cudaFree(kv.second.dev);
+        if (kv.second.host) cudaFreeHost(kv.second.host);
+    }
     for (ConvWeights& w : net->convs) {
         if (w.w) cudaFree(w.w);
         if (w.bias) cudaFree(w.bias);
@@ -1392,6 +1477,316 @@ int y3_net_forward_timed(y3_net* net, const float* x, int B, float* const* outs,
     return rc;
 }
 
+namespace {
+int chain_order_tile(const ChainStep& c, int seq) {
+    seq += c.rot;
+    if (seq >= c.T) seq -= c.T;
+    return c.rev ? c.T - 1 - seq : seq;
+}
+
+// input pixel range [lo, hi] read by output rows [r0, r1] (the device-side rule of chain_wait_a)
+void chain_in_range(const y3::ConvArgs& a, int dep_h, int dep_w, long long r0, long long r1, long long& lo, long long& hi) {
+    lo = r0; hi = r1;
+    if (!a.a_im2col) return;
+    const long long hw = (long long)a.Ho * a.Wo;
+    const long long n0 = r0 / hw, y0 = (r0 - n0 * hw) / a.Wo;
+    const long long n1 = r1 / hw, y1 = (r1 - n1 * hw) / a.Wo;
+    const long long yi0 = std::max<long long>(0, y0 * a.stride + a.lower);
+    const long long yi1 = std::min<long long>(dep_h - 1, y1 * a.stride + a.lower + a.ksize - 1);
+    lo = (n0 * dep_h + yi0) * dep_w;
+    hi = (n1 * dep_h + yi1) * dep_w + dep_w - 1;
+}
+
+// Rotation of a chained layer's tile sequence.  The producer P runs its T tiles in rounds of G; the CTAs without a tile
+// in the last, partial round exit one tile early and the consumer's first CTAs start on those SMs.  If the consumer
+// began with the tiles P writes LAST (plain direction reversal, ConvArgs::rev) those CTAs would only wait; so it begins
+// with the tile fed by the last tile of P's last FULL round, walks back through P's earlier tiles (most recently
+// written first: still in L2) and finishes with the ones fed by P's last round.
+int chain_pick_rot(const ChainStep& P, const ChainStep& C, const y3::ConvArgs& a, int dep_h, int dep_w) {
+    if (P.T <= P.G || C.T <= 1) return 0;
+    const int R = (P.T - 1) / P.G;                 // index of P's last round
+    if (P.T - R * P.G == P.G) return 0;            // it is a full round: nobody exits early
+    const int mg0 = chain_order_tile(P, std::max(0, (R - g_chain_slack) * P.G - 1)) / P.tiles_n;
+    const long long groups = (C.T + C.tiles_n - 1) / C.tiles_n;
+    auto range = [&](long long g, long long& lo, long long& hi) {
+        const long long r0 = g * C.rg, r1 = std::min<long long>((g + 1) * C.rg, C.M) - 1;
+        chain_in_range(a, dep_h, dep_w, std::min(r0, C.M - 1), std::max(r1, std::min(r0, C.M - 1)), lo, hi);
+    };
+    long long lo, hi;
+    if (C.rev) {
+        // P ascending: rows below hi_in are complete; the consumer walks down from the last group that fits below it
+        const long long hi_in = std::min<long long>((long long)(mg0 + 1) * P.rg, P.M) - 1;
+        long long g = std::min<long long>(groups - 1, (long long)((double)(hi_in + 1) / (double)P.M * (double)groups) + 1);
+        for (; g >= 0; --g) {
+            range(g, lo, hi);
+            if (hi <= hi_in) break;
+        }
+        if (g < 0) return 0;
+        const long long start = g * C.tiles_n + C.tiles_n - 1;
+        return (int)(C.T - 1 - start);
+    }
+    // P descending: rows from lo_in up are complete; the consumer walks up from the first group that fits above it
+    const long long lo_in = (long long)mg0 * P.rg;
+    long long g = std::max<long long>(0, (long long)((double)lo_in / (double)P.M * (double)groups) - 1);
+    for (; g < groups; ++g) {
+        range(g, lo, hi);
+        if (lo >= lo_in) break;
+    }
+    if (g >= groups) return 0;
+    return (int)(g * C.tiles_n);
+}
+
+// Which steps post, which are chained to which, and every step's tile order, for a forward pass of B images.
+void plan_chain(const y3_net& net, int B, const int* out_pitch, std::vector<ChainStep>& chain) {
+    const int sms = net.ctx->sms;
+    const int n = (int)net.steps.size();
+    chain.assign(n, ChainStep{});
+    std::vector<y3::ConvArgs> cas(n);
+    std::vector<int> tma(n, 0);
+    // ---- tiling of every tensor-core conv step ----
+    for (int si = 0; si < n; ++si) {
+        const Step& s = net.steps[si];
+        if (s.kind != 1) continue;
+        const TensorInfo& a = net.tensors[s.src];
+        const TensorInfo& o = net.tensors[s.dst];
+        cas[si] = conv_args(s, net.layers[s.layer], a.Cp, B);
+        tma[si] = s.tma_out;   // as net_forward_impl decides it
+        if (o.fp32_output && out_pitch && out_pitch[o.out_index] != o.C) tma[si] = 32;
+        ChainStep& cs = chain[si];
+        const int cl = s.cfg.gather ? 1 : (s.cfg.cluster >= 2 ? 2 : 1);
+        const int groups = (cas[si].tiles_m + cl - 1) / cl;
+        cs.tiles_n = cas[si].tiles_n;
+        cs.T = groups * cas[si].tiles_n;
+        cs.G = std::max(1, std::min(cs.T, sms / cl));
+        cs.rg = y3::kBlockM * cl;
+        cs.M = cas[si].M;
+        cs.need = 4u * (uint32_t)cas[si].tiles_n;
+        cs.total = 4u * (uint32_t)(cl * groups * cas[si].tiles_n);
+        cs.rev = s.rev;
+    }
+    auto plain = [&](int si) {   // a step the flags can describe at all
+        const Step& s = net.steps[si];
+        return s.kind == 1 && !s.flat && !s.in_padded && !s.out_padded && s.sync_off >= 0 && cas[si].dbg == 0;
+    };
+    if (g_chain_runs) {
+        // ---- persistent runs: consecutive CTA-pair layers with the bf16 64-column TMA-store epilogue ----
+        auto eligible = [&](int si) {
+            const Step& s = net.steps[si];
+            return plain(si) && s.cfg.gather == 0 && s.cfg.cluster == 3 && s.cfg.swz == 128 && tma[si] == 64 &&
+                   !net.tensors[s.dst].fp32_output && !s.fused_up;
+        };
+        int si = 0;
+        while (si < n) {
+            if (!eligible(si)) { ++si; continue; }
+            int end = si + 1;
+            for (; end < n && eligible(end); ++end) {
+                // an input written by several steps (concat) or by a step the flags do not cover can only be the input
+                // of a run's FIRST layer: everything before the launch is complete when it starts
+                const Step& s = net.steps[end];
+                const int ps = s.src > 0 ? net.tensor_step[s.src] : -1;
+                const int rs = s.src2 >= 0 ? net.tensor_step[s.src2] : -1;
+                if (s.src <= 0 || ps < 0 || (s.src2 >= 0 && rs < 0)) break;   // (producers at or after si are run members)
+            }
+            const int len = end - si;
+            if (len >= 2) {
+                int pairs = 1;
+                for (int k = si; k < end; ++k) pairs = std::max(pairs, chain[k].G);
+                long long extra = 0;
+                for (int k = si; k < end; ++k) {
+                    ChainStep& cs = chain[k];
+                    const Step& s = net.steps[k];
+                    cs.posts = true;
+                    cs.run_first = si;
+                    cs.run_len = len;
+                    cs.run_pairs = pairs;
+                    cs.G = pairs;
+                    cs.vshift = g_chain_vshift ? (int)((pairs - extra % pairs) % pairs) : 0;
+                    extra += cs.T % pairs;
+                    const int ps = s.src > 0 ? net.tensor_step[s.src] : -1;
+                    const int rs = s.src2 >= 0 ? net.tensor_step[s.src2] : -1;
+                    cs.chained = true;   // member of a run; ps / rs stay -1 when the producer is older than the run
+                    if (ps >= si) cs.ps = ps;
+                    if (rs >= si) cs.rs = rs;
+                    if (cs.ps == k - 1 && g_use_chain_rot) {
+                        cs.rev = 1 - chain[cs.ps].rev;
+                        cs.rot = chain_pick_rot(chain[cs.ps], cs, cas[k], net.tensors[s.src].H, net.tensors[s.src].W);
+                    }
+                }
+            }
+            si = end;
+        }
+        return;
+    }
+    // ---- experiment: every layer its own launch, chained through the flags ----
+    for (int si = 0; si < n; ++si) {
+        if (!plain(si)) continue;
+        const Step& s = net.steps[si];
+        const TensorInfo& a = net.tensors[s.src];
+        ChainStep& cs = chain[si];
+        cs.posts = (cs.T + cs.G - 1) / cs.G <= g_chain_max_rounds;
+        if (!cs.posts) continue;
+        // consumer side: every producer of this layer's inputs and the layer two launches back must post
+        const int ps = s.src > 0 ? net.tensor_step[s.src] : -1;
+        const int rs = s.src2 >= 0 ? net.tensor_step[s.src2] : -1;
+        cs.chained = s.cfg.gather == 0 && ps >= 0 && chain[ps].posts &&
+                     (s.src2 < 0 || (rs >= 0 && chain[rs].posts && tma[si] != 0)) && si >= 1 &&
+                     net.steps[si - 1].kind == 1 && (si < 2 || chain[si - 2].posts);
+        if (g_chain_post_only) cs.chained = false;
+        if (!cs.chained) continue;
+        cs.ps = ps;
+        cs.rs = rs;
+        if (ps == si - 1 && g_use_chain_rot) {
+            cs.rev = 1 - chain[ps].rev;
+            cs.rot = chain_pick_rot(chain[ps], cs, cas[si], a.H, a.W);
+        }
+    }
+}
+}  // namespace
+
+int y3_net_chain_plan(y3_net* net, int B, y3_chain_step* steps_host, int n_steps) {
+    if (!net || !steps_host || n_steps != (int)net->steps.size()) return fail(Y3_ERR_INVALID, "bad chain plan query");
+    if (B <= 0 || B > net->max_batch) return fail(Y3_ERR_INVALID, "batch " + std::to_string(B) + " exceeds max_batch");
+    std::vector<ChainStep> chain(net->steps.size());
+    if (net->chain) plan_chain(*net, B, nullptr, chain);
+    for (int i = 0; i < n_steps; ++i) {
+        const ChainStep& c = chain[i];
+        y3_chain_step& o = steps_host[i];
+        o.layer = net->steps[i].layer;
+        o.posts = c.posts ? 1 : 0;
+        o.chained = c.chained ? 1 : 0;
+        o.dep_step = c.ps;
+        o.res_step = c.rs;
+        o.tiles = c.T;
+        o.ctas = c.G;
+        o.tiles_n = c.tiles_n;
+        o.rows_per_group = c.rg;
+        o.rev = c.rev;
+        o.rot = c.rot;
+        o.run_first = c.run_first;
+        o.run_len = c.run_len;
+        o.vshift = c.vshift;
+    }
+    return Y3_OK;
+}
+
+namespace {
+// ChainArgs of step si (flags of its own tiles, of its producers and of the gate layer) + its tile order
+void wire_chain(const y3_net& net, const std::vector<ChainStep>& chain, int si, y3::ConvArgs& ca) {
+    const ChainStep& cs = chain[si];
+    if (!cs.posts) return;
+    const TensorInfo& a = net.tensors[net.steps[si].src];
+    auto done_of = [&](int k) { return net.sync + net.steps[k].sync_off; };
+    ca.ch.mode = (uint32_t)g_chain_mode;
+    ca.ch.post_done = done_of(si);
+    ca.ch.post_flags = done_of(si) + 32;
+    if (cs.chained) {
+        if (cs.ps >= 0) {
+            const ChainStep& P = chain[cs.ps];
+            ca.ch.dep_done = done_of(cs.ps);
+            ca.ch.dep_flags = done_of(cs.ps) + 32;
+            ca.ch.dep_need = P.need;
+            ca.ch.dep_total = P.total;
+            ca.ch.dep_h = a.H;
+            ca.ch.dep_w = a.W;
+        }
+        if (cs.rs >= 0) {
+            ca.ch.res_done = done_of(cs.rs);
+            ca.ch.res_flags = done_of(cs.rs) + 32;
+            ca.ch.res_need = chain[cs.rs].need;
+            ca.ch.res_total = chain[cs.rs].total;
+        }
+        const int gate = si - 2;
+        if (gate >= 0 && chain[gate].posts && (cs.run_len == 0 || gate >= cs.run_first)) {
+            ca.ch.gate_done = done_of(gate);
+            ca.ch.gate_total = chain[gate].total;
+        }
+    }
+    ca.rev = cs.rev;
+    ca.rot = cs.rot;
+}
+
+// The persistent runs of a forward pass of B images (conv_chain.cuh): planned and uploaded once per batch size.  Returns
+// null when there are none, or when the set would have to be built during a stream capture (allocations are not allowed
+// there: the caller then launches layer by layer; Detector warms up outside the capture, so this does not happen).
+y3_net::RunSet* get_runset(y3_net* net, int B, cudaStream_t st) {
+    if (!net->chain || !net->sync || !g_chain_runs || !g_chain_runs_rt) return nullptr;
+    const int key = B + (g_ts_net_ptr ? (1 << 24) : 0);   // stamped launches (profiling) carry the stamp buffer in their layers
+    auto it = net->runsets.find(key);
+    if (it != net->runsets.end()) return it->second.dev ? &it->second : nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
+    y3_net::RunSet& rs = net->runsets[key];
+    plan_chain(*net, B, nullptr, rs.chain);
+    const int n = (int)net->steps.size();
+    rs.dev_index.assign(n, -1);
+    int cnt = 0;
+    for (int si = 0; si < n; ++si)
+        if (rs.chain[si].run_len > 0) rs.dev_index[si] = cnt++;
+    if (cnt == 0) return nullptr;
+    const size_t bytes = (size_t)cnt * sizeof(y3::ChainLayer);
+    if (cudaMallocHost(&rs.host, bytes) != cudaSuccess || cudaMalloc(&rs.dev, bytes) != cudaSuccess) {
+        if (rs.host) cudaFreeHost(rs.host);
+        rs.host = nullptr;
+        rs.dev = nullptr;
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    std::memset(rs.host, 0, bytes);
+    for (int si = 0; si < n; ++si) {
+        if (rs.dev_index[si] < 0) continue;
+        const Step& s = net->steps[si];
+        const TensorInfo& a = net->tensors[s.src];
+        const TensorInfo& o = net->tensors[s.dst];
+        y3::ChainLayer& L = rs.host[rs.dev_index[si]];
+        L.tmA = s.tmA; L.tmB = s.tmB; L.tmO = s.tmO; L.tmR = s.tmR;
+        L.block_n = s.cfg.block_n;
+        L.vshift = rs.chain[si].vshift;
+        y3::ConvArgs ca = conv_args(s, net->layers[s.layer], a.Cp, B);
+        ca.ts = g_ts_net_ptr ? g_ts_net_ptr + (size_t)si * kTsNetStride : nullptr;
+        ca.bias = net->convs[s.conv_idx].bias;
+        if (s.src2 >= 0) {
+            ca.residual = tensor_ptr(*net, s.src2);
+            ca.res_stride = net->tensors[s.src2].pix_stride;
+        }
+        ca.tma_out = s.tma_out;
+        ca.out = tensor_ptr(*net, s.dst);
+        ca.out_stride = o.pix_stride;
+        wire_chain(*net, rs.chain, si, ca);
+        L.p = ca;
+    }
+    if (cudaMemcpyAsync(rs.dev, rs.host, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(rs.dev);
+        rs.dev = nullptr;
+        return nullptr;
+    }
+    return &rs;
+}
+
+cudaError_t launch_chain(const y3::ChainLayer* layers, int count, int pairs, cudaStream_t st) {
+    const void* kern = (const void*)y3::conv_chain_kernel;
+    {
+        cudaError_t e = ensure_dyn_smem(kern, y3::ChainSmem::TOTAL);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(y3::kConvThreads);
+    cfg.dynamicSmemBytes = y3::ChainSmem::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, y3::conv_chain_kernel, layers, count);
+}
+}  // namespace
+
 static int net_forward_impl(y3_net* net, const void* x_in, bool x_u8, int B, float* const* outs, const int* out_pitch,
                             int n_outs, void* stream, std::vector<cudaEvent_t>* evs) {
     (void)cudaGetLastError();   // drop stale non-sticky errors of earlier calls
@@ -1422,11 +1817,32 @@ static int net_forward_impl(y3_net* net, const void* x_in, bool x_u8, int B, flo
             x = net->x_scratch;
         }
     }
+    // layer chaining: persistent runs (default; not under per-layer timing or timestamps), or the flags experiment
+    bool chain_on = net->chain && net->sync != nullptr;
+    std::vector<ChainStep> chain_local;
+    const std::vector<ChainStep>* chainp = nullptr;
+    y3_net::RunSet* runs = nullptr;
+    if (chain_on && g_chain_runs) {
+        runs = evs ? nullptr : get_runset(net, B, st);
+        chain_on = runs != nullptr;
+        if (runs) chainp = &runs->chain;
+    } else if (chain_on) {
+        plan_chain(*net, B, out_pitch, chain_local);
+        chainp = &chain_local;
+    }
+    if (chain_on) Y3_CUDA(cudaMemsetAsync(net->sync, 0, (size_t)net->sync_words * sizeof(uint32_t), st));
     size_t step_no = 0;
     for (const Step& s : net->steps) {
         const y3_layer_desc& d = net->layers[s.layer];
         if (evs) Y3_CUDA(cudaEventRecord((*evs)[step_no], st));
+        const int si = (int)step_no;
         ++step_no;
+        if (runs && runs->dev_index[si] >= 0) {
+            // member of a persistent run: the whole run is one launch, issued at its first step
+            const ChainStep& cs = runs->chain[si];
+            if (si == cs.run_first) Y3_CUDA(launch_chain(runs->dev + runs->dev_index[si], cs.run_len, cs.run_pairs, st));
+            continue;
+        }
         if (s.kind == 1) {
             const TensorInfo& a = net->tensors[s.src];
             const TensorInfo& o = net->tensors[s.dst];
@@ -1437,6 +1853,7 @@ static int net_forward_impl(y3_net* net, const void* x_in, bool x_u8, int B, flo
                 ca.residual = tensor_ptr(*net, s.src2);
                 ca.res_stride = net->tensors[s.src2].pix_stride;
             }
+            if (g_ts_net_ptr) ca.ts = g_ts_net_ptr + (size_t)si * kTsNetStride;
             CUtensorMap tmo_local;
             const CUtensorMap* tmo = &s.tmO;
             ca.tma_out = s.tma_out;
@@ -1461,6 +1878,7 @@ static int net_forward_impl(y3_net* net, const void* x_in, bool x_u8, int B, flo
                 ca.out = tensor_ptr(*net, s.dst);
                 ca.out_stride = o.pix_stride;
             }
+            if (chain_on && !runs) wire_chain(*net, *chainp, si, ca);
             if (s.flat) {
                 FlatGeom g;
                 flat_geometry(a.W + 1, s.cfg.swz, s.cfg.block_n, g);
@@ -1877,6 +2295,16 @@ int y3_conv2d_stem_f32(y3_ctx* ctx, const float* x, int B, int H, int W, const v
 
 int y3_dbg_timestamps(void* dev_u64_buffer) {
     g_ts_ptr = reinterpret_cast<unsigned long long*>(dev_u64_buffer);
+    return Y3_OK;
+}
+
+int y3_dbg_set_chain_runs(int on) {
+    g_chain_runs_rt = on != 0;
+    return Y3_OK;
+}
+
+int y3_dbg_timestamps_net(void* dev_u64_buffer) {
+    g_ts_net_ptr = reinterpret_cast<unsigned long long*>(dev_u64_buffer);
     return Y3_OK;
 }
 
