@@ -121,6 +121,12 @@ typedef struct y3_chain_step {
 } y3_chain_step;
 int y3_net_chain_plan(y3_net* net, int B, y3_chain_step* steps_host, int n_steps);
 int64_t y3_net_arena_bytes(y3_net* net);
+/* Debugging / parity aid: copy the activation tensor that layer `layer` materialised during the LAST forward pass of B
+ * images to host memory as dense bf16 [B,H,W,C] (H, W, C as in y3_layer_plan; stored padding channels are dropped).
+ * Arena buffers are recycled, so the tensor is only intact if no later layer of the pass reused its buffer (true for
+ * every tensor that is still read by one of the last three launches).  Synchronises the device.  What the reference
+ * offers through Keras sub-model outputs (core/parse_model.py:279-314). */
+int y3_net_read_layer(y3_net* net, int layer, int B, void* host_bf16);
 /* output k: grid height/width and channel count 3*(5+C) */
 int y3_net_output_shape(y3_net* net, int k, int* gh, int* gw, int* ch);
 

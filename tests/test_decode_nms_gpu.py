@@ -251,6 +251,60 @@ def test_compact_decode_and_packed_gather(cuda, C):
     assert int(nv.min()) > 0
 
 
+@pytest.mark.parametrize("C", [80, 37, 3])
+def test_compact_decode_class_ties_and_saturation(cuda, C):
+    """The compact decode finds the class from the raw logits and takes one sigmoid; it must still return exactly the
+    first arg-max of the float32 probabilities (core/yolo_nms.py:18-24 applies tf.argmax to sigmoid outputs): saturated
+    logits (sigmoid == 1.0f for several classes), exact and near ties, all-zero probabilities (logits < -104), denormal
+    probabilities, NaN logits, +-inf."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from yolo_v3_tf2_b200 import configs
+    rng = np.random.default_rng(100 + C)
+    B = 2
+    grids = []
+    for g in (13, 26, 52):
+        t = rng.normal(0, 1.5, (B, g, g, 3, 5 + C)).astype(np.float32)
+        cls = t[..., 5:].reshape(-1, C)
+        n = cls.shape[0]
+        kind = rng.integers(0, 12, n)
+        for k in range(n):
+            row = cls[k]
+            a, b = rng.choice(C, 2, replace=False) if C > 1 else (0, 0)
+            if kind[k] == 0:      # several saturated classes: sigmoid == 1.0f for all of them
+                row[rng.choice(C, min(C, 3), replace=False)] = rng.uniform(17.5, 60.0, min(C, 3))
+            elif kind[k] == 1:    # exact tie of the two largest logits
+                row[a] = row[b] = np.float32(row.max() + 1.0)
+            elif kind[k] == 2:    # near tie: 1 ulp apart, at moderate and at large logits
+                base = np.float32(rng.choice([0.3, 2.0, 5.5, 7.0, 9.0, 12.0, 15.0]))
+                row[a] = base
+                row[b] = np.nextafter(base, np.float32(100.0))
+            elif kind[k] == 3:    # everything underflows to probability 0 (class 0 must win)
+                row[:] = rng.uniform(-200.0, -105.0, C)
+            elif kind[k] == 4:    # denormal probabilities
+                row[:] = rng.uniform(-103.0, -88.0, C)
+            elif kind[k] == 5:    # the flat part of the sigmoid: logits within a few 1e-3 of each other around 6..16
+                row[:] = np.float32(rng.uniform(5.0, 16.0)) + rng.uniform(-4e-3, 4e-3, C).astype(np.float32)
+            elif kind[k] == 6:
+                row[a] = np.float32("inf")
+            elif kind[k] == 7:
+                row[:] = np.float32("-inf")
+            elif kind[k] == 8 and k % 7 == 0:
+                row[a] = np.float32("nan")
+        grids.append(torch.from_numpy(t).cuda())
+    anchors = configs.coco_anchors()
+    full = y3.yolo_decode(grids, anchors, C, with_scores=True)
+    comp = y3.yolo_decode(grids, anchors, C, compact=True)
+    probs = full[2].cpu().numpy()
+    # the non-compact kernel's own scores / classes are the class reduce of the probabilities it wrote ...
+    finite = ~np.isnan(probs).any(axis=2)
+    assert np.array_equal(full[4].cpu().numpy()[finite], probs.argmax(axis=2)[finite])
+    # ... and the compact path agrees with it bit for bit (NaN scores compare equal as bit patterns)
+    assert torch.equal(full[0], comp[0])
+    assert np.array_equal(full[4].cpu().numpy(), comp[4].cpu().numpy())
+    assert np.array_equal(full[3].cpu().numpy().view(np.uint32), comp[3].cpu().numpy().view(np.uint32))
+
+
 def test_nms_rejects_unsupported_parameters(cuda):
     """parameters the kernel cannot honour are refused instead of returning truncated results."""
     import torch

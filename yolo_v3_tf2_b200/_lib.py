@@ -60,6 +60,7 @@ SIGNATURES = {
     "y3_net_num_outputs": (_i, [_p]),
     "y3_net_get_plan": (_i, [_p, C.POINTER(LayerPlan), _i]),
     "y3_net_arena_bytes": (_i64, [_p]),
+    "y3_net_read_layer": (_i, [_p, _i, _i, _p]),
     "y3_net_output_shape": (_i, [_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "y3_net_load_conv": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _f]),
     "y3_net_forward": (_i, [_p, _p, _i, C.POINTER(_p), _i, _p]),

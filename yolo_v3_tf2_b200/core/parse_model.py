@@ -200,6 +200,20 @@ class Y3Model:
             _lib.check(lib.y3_net_forward(ent["handle"], _lib.ptr(x), int(B), op, len(outs), _lib.stream_ptr()))
         return outs
 
+    def read_layer(self, layer, x_shape, device=None):
+        """Activation tensor that graph layer ``layer`` materialised during the last forward pass on an input of shape
+        ``x_shape`` = (B, H, W, 3): float32 numpy [B, h, w, C] (bf16 values).  Parity aid -- the reference exposes
+        intermediate tensors as Keras sub-model outputs (core/parse_model.py:279-314)."""
+        B, H, W, _ = x_shape
+        ent = self._net(H, W, B, device)
+        plans = (_lib.LayerPlan * len(self._descs))()
+        lib = _lib.lib()
+        _lib.check(lib.y3_net_get_plan(ent["handle"], plans, len(self._descs)))
+        pl = plans[layer]
+        raw = np.empty((B, pl.H, pl.W, pl.C), np.uint16)
+        _lib.check(lib.y3_net_read_layer(ent["handle"], int(layer), int(B), raw.ctypes.data_as(C.c_void_p)))
+        return (raw.astype(np.uint32) << 16).view(np.float32)
+
     def profile_layers(self, x):
         """Per-kernel device times of one forward pass: list of (layer index, ms).  Profiling aid, not part of the
         reference surface."""

@@ -1,0 +1,370 @@
+// The 3-channel stem conv (reference config/models/yolov3/backbone.yaml first conv, core/parse_model.py:13-56: 3x3,
+// stride 1, 'same', BN, LeakyReLU) as a band-resident Toeplitz GEMM.
+//
+// Why another stem kernel: the software-im2col stem (conv_gather.cuh) builds a 128-byte A row per output pixel and is
+// bound by the instructions its producers issue (DESIGN.md finding 15: 0.30 ms against an HBM floor of 0.11 ms).  Here
+// the A operand is never built at all:
+//   * a CTA keeps a band of R + 2 image rows in shared memory as a FLAT array of bf16 RGBX pixels (8 bytes each, pixel -1
+//     and the pixels past the row end are zero), one copy for hi = bf16(x) and one for lo = bf16(x - hi) (the fp32 /
+//     uint8 image loses no precision, as in the old stem);
+//   * GEMM row m is the output pixel PAIR (2m, 2m+1); its K = 16 slice for filter row r is the 4 input pixels
+//     2m-1 .. 2m+2 (x 4 channels) of image row y + r - 1, i.e. the 32 bytes at byte 16 m of that row.  Consecutive GEMM
+//     rows therefore start 16 bytes apart and OVERLAP -- which a no-swizzle K-major UMMA descriptor expresses directly:
+//     rows of a core matrix are 16 bytes apart by definition, the second 16-byte K chunk sits LBO = 16 bytes after the
+//     first, the next 8-row group SBO = 128 bytes further.  A filter row is a row-pitch offset of the start address.
+//   * N = 64 = (pixel of the pair j, output channel co); the weights are the banded matrix
+//     B_r[(j, co)][(q, c)] = w[r][s = q - j][c][co] (zero for s outside 0..2 and for the padding channel c = 3).
+//   so one 128 x 64 x 16 MMA per (filter row, hi / lo) -- six per tile -- computes 256 output pixels x 32 channels, and
+//   the producers only convert each input pixel once per band: ~13 instructions per output pixel instead of ~100.
+//   The accumulator row of a pair IS its 128 output bytes (2 pixels x 32 channels, NHWC), so the epilogue is the usual
+//   TMEM -> +bias -> LeakyReLU -> bf16 -> swizzled staging -> TMA store, through a 3-D map (128 B, pairs, rows) that clips
+//   the junk pairs at the end of each row (the flat row pitch P is a multiple of 32 pairs so that no 32-pair store
+//   chunk straddles two image rows).
+// Arithmetic is identical to the old stem (same hi / lo split, same bf16 weights, fp32 accumulation; the summation
+// order inside the tensor core differs).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace y3 {
+
+struct StemArgs {
+    const void* src;     // uint8 or float32 [B, H, W, 3]
+    int B, H, W;
+    int R;               // output rows per band (4 or 8); H % R == 0
+    int P;               // flat row pitch in pixel pairs: multiple of 32, >= W / 2 + 2
+    const void* wq;      // packed weights: [3 filter rows][2 K chunks][64 (j, co)][8] bf16 = 6144 bytes
+    const float* bias;   // [32] fp32
+    int leaky;
+    float in_div;        // uint8 input: x = byte / in_div
+    int dbg;
+};
+
+constexpr int kStemThreads = 512;        // warps: 0 weights, 1 MMA, 2 TMEM, 3 idle, 4-11 epilogue, 12-15 producers
+constexpr int kStemAccStages = 8;        // 8 x 64 fp32 columns = all 512 TMEM columns
+constexpr int kStemWBytes = 6144;
+
+// one plane (hi or lo) of a band: (R + 2) rows of P 16-byte chunks + slack for the last row's K chunk 1; a multiple of
+// 1024 bytes so that the epilogue's swizzled staging buffers behind the planes stay 1024-byte aligned
+__host__ __device__ inline int stem_plane_bytes(int R, int P) { return ((R + 2) * P * 16 + 256 + 1023) & ~1023; }
+__host__ __device__ inline int stem_smem_bytes(int R, int P) {
+    return 1024 + 2 * 2 * stem_plane_bytes(R, P) + kStemWBytes + 8 * kEpiWarpBytes + 1024 /*lut*/ + 512 /*barriers*/;
+}
+
+// no-swizzle K-major operand: 8-row core matrices of 128 contiguous bytes; lbo = distance of the second 16-byte K chunk,
+// sbo = distance of the next 8-row group
+__device__ __forceinline__ uint64_t make_smem_desc_plain(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+// U8: uint8 image, x = byte / in_div through a 256-entry (hi | lo << 16) table (bit-identical to the float path).
+// QS: column slots per producer thread, ceil((W / 4 + 1) / 32).
+template <bool U8, int QS>
+__global__ void __launch_bounds__(kStemThreads, 1)
+conv_stem_band_kernel(const __grid_constant__ CUtensorMap tmO, const StemArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int R = p.R, P = p.P;
+    const uint32_t PB = (uint32_t)stem_plane_bytes(R, P);
+    constexpr uint32_t NPL = 1;
+    const uint32_t buf_bytes = 2u * NPL * PB;                    // [hi (x NPL) | lo (x NPL)]
+    const uint32_t smem_in = smem_base;
+    const uint32_t smem_w = smem_in + 2u * buf_bytes;
+    const uint32_t smem_stg = smem_w + kStemWBytes;
+    const uint32_t smem_lut = smem_stg + 8u * kEpiWarpBytes;
+    const uint32_t bar_base = smem_lut + 1024u;
+    auto in_full = [&](int b) { return bar_base + 8u * b; };
+    auto in_empty = [&](int b) { return bar_base + 8u * (2 + b); };
+    auto tfull = [&](int s) { return bar_base + 8u * (4 + s); };
+    auto tempty = [&](int s) { return bar_base + 8u * (4 + kStemAccStages + s); };
+    const uint32_t wfull = bar_base + 8u * (4 + 2 * kStemAccStages);
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (5 + 2 * kStemAccStages);
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+    const uint32_t* lut = reinterpret_cast<const uint32_t*>(smem_gen + (smem_lut - smem_base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int bands_per_img = p.H / R;
+    const int num_bands = p.B * bands_per_img;
+    const int T = R * P / 128;                                    // M tiles (128 pixel pairs) per band
+    const int half_w = p.W >> 1;
+
+    if (warp == 1 && lane == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(in_full(b), 128); mbar_init(in_empty(b), 1); }
+        for (int s = 0; s < kStemAccStages; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 128); }
+        mbar_init(wfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 3 && lane == 0) tma_prefetch_desc(&tmO);
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    if constexpr (U8) {
+        if (threadIdx.x < 256) {
+            const float f = __fdiv_rn((float)threadIdx.x, p.in_div);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(f, __bfloat162float(hi)));
+            reinterpret_cast<uint32_t*>(smem_gen + (smem_lut - smem_base))[threadIdx.x] =
+                (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+        }
+    }
+    // the pad pixels (pixel -1, pixels >= W, the slack past the last row) are never written by the producers
+    for (uint32_t o = threadIdx.x * 16u; o < 2u * buf_bytes; o += kStemThreads * 16u)
+        st_shared_v4(smem_in + o, make_uint4(0u, 0u, 0u, 0u));
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wfull, kStemWBytes);
+            bulk_load_1d(smem_w, p.wq, kStemWBytes, wfull);
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+        const uint32_t lbo_a = 16u;   // the second K chunk of a row IS the first chunk of the next row
+        mbar_wait(wfull, 0, 0x700);
+        int j = 0, k = 0;
+        for (int band = blockIdx.x; band < num_bands; band += gridDim.x, ++k) {
+            const int b = k & 1;
+            mbar_wait(in_full(b), (uint32_t)((k >> 1) & 1), 0x300 + b);
+            fence_proxy_async_smem();
+            tc_fence_after();
+            const uint32_t in_b = smem_in + (uint32_t)b * buf_bytes;
+            for (int t = 0; t < T; ++t, ++j) {
+                const int s = j & (kStemAccStages - 1);
+                mbar_wait(tempty(s), (uint32_t)(((j / kStemAccStages) & 1) ^ 1), 0x200 + s);
+                tc_fence_after();
+                if (leader && !(p.dbg & 8)) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(s * 64);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const uint64_t bdesc = make_smem_desc_plain(smem_w + (uint32_t)r * 2048u, 1024u, 128u);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t a_addr = in_b + (uint32_t)h * NPL * PB + (uint32_t)(r * P + t * 128) * 16u;
+                            umma_bf16(d_tmem, make_smem_desc_plain(a_addr, lbo_a, 128u), bdesc, idesc, (uint32_t)((r | h) != 0));
+                        }
+                    }
+                }
+                if (leader) umma_commit(tfull(s));
+            }
+            if (leader) umma_commit(in_empty(b));
+        }
+        __syncwarp();
+    } else if (warp >= 4 && warp < 12) {
+        // ===================== epilogue: two groups of four warps, tiles alternate between the groups =====================
+        const int eg = (warp - 4) >> 2;
+        const int q = warp & 3;
+        const uint32_t stg = smem_stg + (uint32_t)(warp - 4) * kEpiWarpBytes;
+        const float slope = p.leaky ? 0.1f : 1.0f;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        uint32_t g = 0;     // chunks stored so far by this warp (ring of two 4 KB buffers)
+        int j = 0, k = 0;
+        for (int band = blockIdx.x; band < num_bands; band += gridDim.x, ++k) {
+            const int n = band / bands_per_img;
+            const int y0 = (band - n * bands_per_img) * R;
+            for (int t = 0; t < T; ++t, ++j) {
+                if ((j & 1) != eg) continue;
+                const int s = j & (kStemAccStages - 1);
+                mbar_wait(tfull(s), (uint32_t)((j / kStemAccStages) & 1), 0x400 + s);
+                tc_fence_after();
+                const int f0 = t * 128 + q * 32;              // first flat pair of this warp's 32 lanes
+                const int i_out = f0 / P;
+                const int m0 = f0 - i_out * P;
+                if (m0 >= half_w) {                            // junk pairs past the end of the image row
+                    tc_fence_before();
+                    mbar_arrive(tempty(s));
+                    continue;
+                }
+                const uint32_t buf = stg + (g & 1u) * 4096u;
+                if (lane == 0) tma_store_wait_read<1>();      // the store that last used this buffer has read it
+                __syncwarp();
+                uint32_t v[64];
+                const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 64);
+                tmem_ld_32x32(t_acc, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld_32x32(t_acc + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                const float4* bp = reinterpret_cast<const float4*>(p.bias);
+                float4 bz[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bz[i] = __ldg(bp + i);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(tempty(s));
+                if (!(p.dbg & 1)) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {              // 16-byte piece c: pixel c / 4 of the pair, channels 8 (c % 4) ..
+                        const float4 b0 = bz[2 * (c & 3)], b1 = bz[2 * (c & 3) + 1];
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        const float2 s2 = make_float2(slope, slope);
+                        __nv_bfloat162 o2[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 y = __fadd2_rn(make_float2(__uint_as_float(v[8 * c + 2 * e]), __uint_as_float(v[8 * c + 2 * e + 1])),
+                                                        make_float2(bb[2 * e], bb[2 * e + 1]));
+                            const float2 z = __fmul2_rn(y, s2);
+                            o2[e] = __floats2bfloat162_rn(fmaxf(y.x, z.x), fmaxf(y.y, z.y));
+                        }
+                        st_shared_v4_relaxed(buf + row_off + ((((uint32_t)c) ^ sw) << 4), *reinterpret_cast<uint4*>(o2));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (!(p.dbg & 2)) tma_store_3d(&tmO, buf, 0, m0, n * p.H + y0 + i_out);
+                        tma_store_commit();
+                    }
+                    ++g;
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait<0>();
+    } else if (warp >= 12) {
+        // ===================== producers: image rows -> flat bf16 RGBX hi / lo planes =====================
+        // Task (row slot rs, column slot qs) of a thread: row i = pw + 4 rs of the band, pixels 4q-1 .. 4q+2 with
+        // q = lane + 32 qs, i.e. the two 16-byte chunks 2q, 2q+1 of that row.  The global loads of a whole band (uint8:
+        // 4 words per task) are issued into registers BEFORE the thread waits for the band's buffer to be released, so
+        // their latency hides behind that wait; the first version loaded task by task and the producers' exposed
+        // load latency (8 round trips per band) made the kernel no faster than the software-im2col stem.
+        const int pw = warp - 12;
+        const int nq = p.W / 4 + 1;
+        constexpr int RS = 3;            // R + 2 <= 10 rows over 4 producer warps
+        auto store_task = [&](uint32_t row_s, int qq, const uint32_t (&px)[4][3]) {
+            if (p.dbg & 32) return;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {   // chunk 2q + ch = pixels (4q - 1 + 2 ch, 4q + 2 ch)
+                const uint32_t (&a)[3] = px[2 * ch];
+                const uint32_t (&c)[3] = px[2 * ch + 1];
+                const uint4 hi4 = make_uint4(__byte_perm(a[0], a[1], 0x5410), a[2] & 0xFFFFu,
+                                             __byte_perm(c[0], c[1], 0x5410), c[2] & 0xFFFFu);
+                const uint4 lo4 = make_uint4(__byte_perm(a[0], a[1], 0x7632), a[2] >> 16,
+                                             __byte_perm(c[0], c[1], 0x7632), c[2] >> 16);
+                const uint32_t off = (uint32_t)(2 * qq + ch) * 16u;
+                st_shared_v4(row_s + off, hi4);
+                st_shared_v4(row_s + PB + off, lo4);
+            }
+        };
+        if constexpr (U8) {
+            uint32_t raw[RS][QS][4];
+            auto load_band = [&](int band) {
+                const bool band_ok = band < num_bands;
+                const int n = band / bands_per_img;
+                const int y0 = (band - n * bands_per_img) * R;
+#pragma unroll
+                for (int rs = 0; rs < RS; ++rs) {
+                    const int i = pw + 4 * rs;
+                    const int y = y0 - 1 + i;
+                    const bool row_ok = band_ok && i < R + 2 && y >= 0 && y < p.H && !(p.dbg & 4);
+                    const uint8_t* rowp = reinterpret_cast<const uint8_t*>(p.src) + ((size_t)n * p.H + (row_ok ? y : 0)) * p.W * 3;
+#pragma unroll
+                    for (int qs = 0; qs < QS; ++qs) {
+                        const int qq = lane + 32 * qs;
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp + 12 * qq);
+                        const bool in = row_ok && qq < nq - 1;
+                        raw[rs][qs][0] = (row_ok && qq > 0 && qq < nq) ? __ldg(wp - 1) : 0u;
+                        raw[rs][qs][1] = in ? __ldg(wp) : 0u;
+                        raw[rs][qs][2] = in ? __ldg(wp + 1) : 0u;
+                        raw[rs][qs][3] = in ? __ldg(wp + 2) : 0u;
+                    }
+                }
+            };
+            load_band((int)blockIdx.x);
+            int k = 0;
+            for (int band = blockIdx.x; band < num_bands; band += gridDim.x, ++k) {
+                const int b = k & 1;
+                mbar_wait(in_empty(b), (uint32_t)(((k >> 1) & 1) ^ 1), 0x100 + b);
+                const uint32_t in_b = smem_in + (uint32_t)b * buf_bytes;
+#pragma unroll
+                for (int rs = 0; rs < RS; ++rs) {
+                    const int i = pw + 4 * rs;
+                    if (i >= R + 2) continue;
+                    const uint32_t row_s = in_b + (uint32_t)(i * P) * 16u;
+#pragma unroll
+                    for (int qs = 0; qs < QS; ++qs) {
+                        const int qq = lane + 32 * qs;
+                        if (qq >= nq) continue;
+                        const uint32_t w0 = raw[rs][qs][0], w1 = raw[rs][qs][1], w2 = raw[rs][qs][2], w3 = raw[rs][qs][3];
+                        uint32_t px[4][3];   // [pixel 4q-1 .. 4q+2][channel] as (hi | lo << 16)
+                        px[0][0] = lut[(w0 >> 8) & 255u]; px[0][1] = lut[(w0 >> 16) & 255u]; px[0][2] = lut[w0 >> 24];
+                        px[1][0] = lut[w1 & 255u]; px[1][1] = lut[(w1 >> 8) & 255u]; px[1][2] = lut[(w1 >> 16) & 255u];
+                        px[2][0] = lut[w1 >> 24]; px[2][1] = lut[w2 & 255u]; px[2][2] = lut[(w2 >> 8) & 255u];
+                        px[3][0] = lut[(w2 >> 16) & 255u]; px[3][1] = lut[w2 >> 24]; px[3][2] = lut[w3 & 255u];
+                        store_task(row_s, qq, px);
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(in_full(b));
+                load_band(band + (int)gridDim.x);     // in flight while this thread waits for the next buffer
+            }
+        } else {
+            int k = 0;
+            for (int band = blockIdx.x; band < num_bands; band += gridDim.x, ++k) {
+                const int b = k & 1;
+                const int n = band / bands_per_img;
+                const int y0 = (band - n * bands_per_img) * R;
+                mbar_wait(in_empty(b), (uint32_t)(((k >> 1) & 1) ^ 1), 0x100 + b);
+                const uint32_t in_b = smem_in + (uint32_t)b * buf_bytes;
+                for (int i = pw; i < R + 2; i += 4) {
+                    const int y = y0 - 1 + i;
+                    const bool row_ok = y >= 0 && y < p.H && !(p.dbg & 4);
+                    const uint32_t row_s = in_b + (uint32_t)(i * P) * 16u;
+                    const float* rowp = reinterpret_cast<const float*>(p.src) + ((size_t)n * p.H + (row_ok ? y : 0)) * p.W * 3;
+                    float raw[QS][12];   // all loads of the row slot first, then the conversions
+#pragma unroll
+                    for (int qs = 0; qs < QS; ++qs) {
+                        const int qq = lane + 32 * qs;
+#pragma unroll
+                        for (int e = 0; e < 12; ++e) {
+                            const int fi = 12 * qq - 3 + e;               // float index inside the row
+                            raw[qs][e] = (row_ok && fi >= 0 && fi < 3 * p.W) ? __ldg(rowp + fi) : 0.0f;
+                        }
+                    }
+#pragma unroll
+                    for (int qs = 0; qs < QS; ++qs) {
+                        const int qq = lane + 32 * qs;
+                        if (qq >= nq) continue;
+                        uint32_t px[4][3];
+#pragma unroll
+                        for (int e = 0; e < 12; ++e) {
+                            const float f = raw[qs][e];
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+                            const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(f, __bfloat162float(hi)));
+                            px[e / 3][e % 3] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+                        }
+                        store_task(row_s, qq, px);
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(in_full(b));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace y3

@@ -63,6 +63,15 @@ struct ConvArgs {
     int lower;             // im2col lower corner (= -pad_before) for w and h
     int a_im2col;          // 0: 2-D tiled A map (1x1), 1: im2col A map
     int ksize;             // 1 or 3
+    // Pixel-pair view of a Cin = 32 input (conv_tc_kernel only; equal to ksize / stride / lower otherwise).  Two
+    // horizontally adjacent pixels are ONE 64-channel "pixel" of 128 bytes, so a 3x3 conv becomes 3 rows x 2 pair columns
+    // = 6 TMA rows of 128 B per output instead of 9 rows of 64 B (these layers are bound by the TMA unit's row rate).
+    //   stride 2: output x reads pairs x-1 (odd half) and x            -> taps (r, S), S in {0,1}, w traversal stride 1
+    //   stride 1: the GEMM row is an output PAIR and the N tile the parity j of the pixel inside it (tiles_n = 2, the
+    //             output row = 2 x Cout channels): output 2X+j reads pairs X-1+j, X+j -> the tap offset is S + j
+    //   (a_shift_n = 1).  Weights: K index (r, S, i, c) holds w[r][s = 2S + i + j - 1][c], zero when s is outside 0..2.
+    int ksize_w, stride_w, lower_w;
+    int a_shift_n;         // added to the im2col w offset per N tile index
     int kblocks_per_tap;   // Cin / BLOCK_K
     int num_k_blocks;      // ksize*ksize*kblocks_per_tap
     int tiles_m, tiles_n;
@@ -731,16 +740,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rem = m0 - cn * hw;
                 const int po = rem / p.Wo;
                 const int qo = rem - po * p.Wo;
-                const int cw = qo * p.stride + p.lower;
+                const int cw = qo * p.stride_w + p.lower_w;
                 const int ch = po * p.stride + p.lower;
+                const int off_w0 = tn * p.a_shift_n;
                 for (int r = 0; r < p.ksize; ++r) {
-                    for (int sx = 0; sx < p.ksize; ++sx) {
+                    for (int sx = 0; sx < p.ksize_w; ++sx) {
                         for (int c0 = 0; c0 < p.kblocks_per_tap * BLOCK_K; c0 += BLOCK_K) {
                             mbar_wait(empty_bar(stage), phase ^ 1u, 0x100 + stage);
                             if (leader) {
                                 mbar_arrive_expect_tx(full_bar(stage), BRES ? S::A_BYTES : S::STAGE_BYTES);
                                 tma_load_im2col_4d(smem_a + stage * S::A_BYTES, &tmA, full_bar(stage), c0, cw, ch, cn,
-                                                   (uint16_t)sx, (uint16_t)r);
+                                                   (uint16_t)(sx + off_w0), (uint16_t)r);
                                 if constexpr (!BRES) load_b(stage, kcoord, n0);
                             }
                             kcoord += BLOCK_K;

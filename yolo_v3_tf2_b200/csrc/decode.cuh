@@ -125,8 +125,62 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     }
     __syncthreads();
 
-    // ---- (2) class probabilities ----
     const int C = a.C;
+    if (a.probs == nullptr && a.scores != nullptr) {
+        // ---- compact decode (the fused pipeline: NMS reads only boxes and scores): what is needed per record is
+        // max_c sigmoid(t_c) and the FIRST class that attains it, not the C probabilities.  sigmoid is increasing, so only
+        // classes whose logit is close to the largest one, m, can attain the float32 maximum: with
+        // thr = min(m, 6) - 4e-3 every class below thr has an exact sigmoid smaller than sigmoid(min(m, 6)) by >= 1e-5
+        // relative, 50 x the rounding error of sigmoidf_acc.  Four threads per record find m, then evaluate the sigmoid of
+        // the candidates t_c >= thr only (one per record for a trained network; all of them for the near-constant
+        // logits of a random-init head) and reduce (probability, lowest class).  Records with m < -80 (zero / denormal
+        // probabilities tie far below m) or a NaN treat every class as a candidate.  The result is bit-identical to the
+        // class reduce of the probabilities this kernel writes in its non-compact mode.
+        const int t = (int)threadIdx.x >> 2, part = (int)threadIdx.x & 3;
+        static_assert(kDecodeThreads == 4 * kDecodeRecs, "four threads per record");
+        const bool live = t < nrec;
+        const float* r = rec_at(live ? t : 0);
+        float m = -INFINITY;
+        bool nan = false;
+        if (live)
+            for (int c = part; c < C; c += 4) {
+                const float v = r[5 + c];
+                nan |= (v != v);
+                m = fmaxf(m, v);
+            }
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        const bool any_nan = ((__ballot_sync(0xffffffffu, nan) >> ((threadIdx.x & 31u) & ~3u)) & 0xFu) != 0u;
+        const float thr = (any_nan || !(m >= -80.0f)) ? -INFINITY : fminf(m, 6.0f) - 4e-3f;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        if (live)
+            for (int c = part; c < C; c += 4) {
+                const float v = r[5 + c];
+                if (v >= thr) {
+                    const float pc = sigmoidf_acc(v);
+                    if (pc > best) { best = pc; bi = c; }      // classes ascend: the first maximum of this thread is kept
+                }
+            }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (live && part == 0) {
+            // the sequential scan this replaces starts from class 0 and replaces it only by a strictly larger value: a NaN
+            // in class 0 is never replaced, a NaN anywhere else never wins
+            const float p0 = r[5];
+            if (p0 != p0 || bi == 0x7fffffff) { best = sigmoidf_acc(p0); bi = 0; }
+            const long long orec = out_rec[t];
+            a.scores[orec] = __fmul_rn(r[4], best);
+            a.cls[orec] = (long long)bi;
+        }
+        return;
+    }
+
+    // ---- (2) class probabilities ----
     if ((C & 3) == 0) {
         const int c4 = C >> 2;
         const int n4 = nrec * c4;

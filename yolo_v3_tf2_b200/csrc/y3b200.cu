@@ -21,6 +21,7 @@
 #include "conv_tc2.cuh"
 #include "conv_flat.cuh"
 #include "conv_chain.cuh"
+#include "conv_stem.cuh"
 #include "decode.cuh"
 #include "nms.cuh"
 #include "preprocess.cuh"
@@ -193,6 +194,27 @@ int make_map_im2col(const Driver& d, CUtensorMap* tm, const void* base, int N, i
     return Y3_OK;
 }
 
+// Pixel-pair view (ConvArgs::ksize_w): a dense NHWC bf16 tensor with 32 channels seen as (C = 64, W / 2, H, N) -- two
+// adjacent pixels are one 128-byte "pixel" -- for a 3 (rows) x 2 (pair columns) filter footprint.  The w traversal
+// stride is 1 pair (stride 2: one output per pair; stride 1: one output PAIR per pair), the w bounding box is
+// [-1, W/2 - 1) so that tap offsets 0..2 reach pairs -1 .. W/2 (both zero filled); h is as in make_map_im2col.
+int make_map_im2col_pairs(const Driver& d, CUtensorMap* tm, const void* base, int N, int H, int W, int stride,
+                          int pad_lo, int pad_hi) {
+    const int Wp = W / 2;
+    cuuint64_t dims[4] = {64, (cuuint64_t)Wp, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {128, 128ull * (uint64_t)Wp, 128ull * (uint64_t)Wp * (uint64_t)H};
+    int lower[2] = {-1, -pad_lo};
+    int upper[2] = {-1, pad_hi - 2};
+    cuuint32_t estr[4] = {1, 1, (cuuint32_t)stride, 1};
+    CUresult r = d.im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                          upper, 64, (cuuint32_t)y3::kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeIm2col (pixel pairs) failed: " + std::to_string((int)r));
+    const uint64_t bytes = 128ull * (uint64_t)Wp * (uint64_t)H * (uint64_t)N;
+    if (d.version <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+    return Y3_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // conv tile configuration + launch
 // ------------------------------------------------------------------------------------------------
@@ -251,6 +273,9 @@ __host__ __device__ inline int stem_col_k(int sx, int i, bool lo) {
     return i < 7 ? sx * 16 + 9 + i : 48 + 2 * sx + (i - 7);
 }
 
+// pixel-pair view of the Cin = 32 3x3 layers (ConvArgs::ksize_w): Y3_PAIRW=0 keeps the 64-byte-row im2col path,
+// 1 = only the stride-2 layers, 2 = only the stride-1 layers, 3 (default) = both
+const int g_pairw = env_int("Y3_PAIRW", 3);
 // weights-resident variants of the conv kernels (BRES): Y3_BRES=0 disables them
 const bool g_use_bres = env_int("Y3_BRES", 1) != 0;
 // cross-layer tile flags (ChainArgs in conv_tc.cuh): Y3_CHAIN=0 makes every layer wait for its whole predecessor again;
@@ -455,6 +480,65 @@ cudaError_t launch_gather(const ConvCfg& c, const CUtensorMap& tb, const CUtenso
     return cudaErrorInvalidValue;
 }
 
+// Band-resident Toeplitz stem (conv_stem.cuh): Y3_STEM_BAND=0 keeps the software-im2col stem
+const bool g_stem_band = env_int("Y3_STEM_BAND", 1) != 0;
+// band height R (output rows) and flat row pitch P (pixel pairs) for an image width W; false if no band fits
+bool stem_band_geometry(int H, int W, int& R, int& P) {
+    if (W % 4 != 0 || W < 8 || W / 4 + 1 > 160) return false;   // at most 5 column slots per producer thread
+    P = (W / 2 + 2 + 31) / 32 * 32;
+    for (int r : {8, 4}) {
+        if (H % r == 0 && y3::stem_smem_bytes(r, P) <= 232448) { R = r; return true; }
+    }
+    return false;
+}
+// output [B, H, W, 32] bf16 (dense) as (128 bytes = one pixel pair, W / 2 pairs, B * H rows); box = 32 pairs of one row
+int make_map_stem_out(const Driver& d, CUtensorMap* tm, const void* base, int B, int H, int W) {
+    cuuint64_t dims[3] = {64, (cuuint64_t)(W / 2), (cuuint64_t)B * (cuuint64_t)H};
+    cuuint64_t strides[2] = {128, 128ull * (uint64_t)(W / 2)};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = d.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeTiled (stem output) failed: " + std::to_string((int)r));
+    return Y3_OK;
+}
+template <bool U8, int QS>
+cudaError_t launch_stem_band_q(const CUtensorMap& to, const y3::StemArgs& a, int sms, cudaStream_t st);
+template <bool U8>
+cudaError_t launch_stem_band_t(const CUtensorMap& to, const y3::StemArgs& a, int sms, cudaStream_t st) {
+    const int qs = (a.W / 4 + 1 + 31) / 32;
+    switch (qs) {
+        case 1: return launch_stem_band_q<U8, 1>(to, a, sms, st);
+        case 2: return launch_stem_band_q<U8, 2>(to, a, sms, st);
+        case 3: return launch_stem_band_q<U8, 3>(to, a, sms, st);
+        case 4: return launch_stem_band_q<U8, 4>(to, a, sms, st);
+        case 5: return launch_stem_band_q<U8, 5>(to, a, sms, st);
+    }
+    return cudaErrorInvalidValue;
+}
+template <bool U8, int QS>
+cudaError_t launch_stem_band_q(const CUtensorMap& to, const y3::StemArgs& a, int sms, cudaStream_t st) {
+    auto kern = y3::conv_stem_band_kernel<U8, QS>;
+    const int smem = y3::stem_smem_bytes(a.R, a.P);
+    {
+        cudaError_t e = ensure_dyn_smem((const void*)kern, smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int bands = a.B * (a.H / a.R);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)std::max(1, std::min(bands, sms)));
+    cfg.blockDim = dim3(y3::kStemThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, to, a);
+}
+
 // The flat-patch 3x3 kernel (conv_flat.cuh) is parity-green but measured slower end to end than the im2col path
 // (forward 6.13 ms vs 5.52 ms at B = 64: the haloed layouts cost the neighbouring 1x1 layers more than the 3x3 layers
 // gain), so it is opt-in: Y3_FLAT=1.
@@ -565,6 +649,10 @@ struct ConvWeights {
     bool stem_hilo = false;   // tensor-core stem: [cout_pad][64] = 27 weights, 5 zeros, the same 27 weights, 5 zeros
     bool stem_col = false;    // ... or, for the column-sharing producer (stride 1): [cout_pad][64] in the K order
                               // of conv_gather.cuh (stem_col_k below)
+    bool stem_band = false;   // band-resident Toeplitz stem (conv_stem.cuh): [3][2][64][8] bf16
+    int pairw = 0;            // pixel-pair view (ConvArgs::ksize_w): [cout_pad][6 * 64], K = (r, S, i, c); 1: stride 2,
+                              // 2: stride 1 (rows j * cout_p + co, j = output pixel parity)
+    int pair_cout_p = 0;      // stride 1: stored output channels per pixel
     void* w = nullptr;     // bf16 [cout_pad][k*k*cin]  or fp32 [k*k*cin][cout] for the direct kernel
     float* bias = nullptr; // fp32 [cout_pad]
     bool loaded = false;
@@ -585,6 +673,9 @@ struct Step {
     int out_padded = 0;    // output stored haloed-flat
     int patch_boxes = 0, box_rows = 0, pst = 0, bst = 0;
     int stem_col = 0;      // stem through the column-sharing producer (stride 1, pad 1)
+    int stem_band = 0;     // stem through conv_stem_band_kernel; band rows / pair pitch below
+    int band_r = 0, band_p = 0;
+    int pairw = 0;         // Cin = 32 3x3 conv on the pixel-pair view of its input (1: stride 2, 2: stride 1)
     int tma_out = 0;       // epilogue writes through tmO (and reads the residual through tmR)
     int rev = 0;           // walk the output tiles backwards (alternates from conv to conv, see ConvArgs::rev)
     long long sync_off = -1;   // tc conv: word offset of this step's [done (32 words) | per-M-tile flags] in y3_net::sync
@@ -933,6 +1024,28 @@ int plan_net(y3_net& n) {
                     s.cfg.stages = st2(128);
                 }
             }
+            if (tc_ok && s.cfg.gather == 0 && !flat_conv[i] && d.ksize == 3 && a.Cp == 32 && d.src0 != 0 &&
+                (g_pairw & (d.stride == 2 ? 1 : 2)) && a.W % 2 == 0 && a.pix_stride == 32 && a.chan_off == 0 && !a.padded &&
+                s.cout_p <= 64 && !fused_up[i] && !n.tensors[writes[i]].fp32_output && s.pad_lo == 1) {
+                // Cin = 32 3x3 conv on the pixel-pair view of its (dense) input: 6 TMA rows of 128 B per output, not 9 of 64 B
+                const TensorInfo& o = n.tensors[writes[i]];
+                bool ok = d.stride == 2 ? s.pad_hi == 0 : s.pad_hi == 1;
+                if (d.stride == 1) {
+                    // the output (and the residual) are addressed as [pixel pairs][2 * channels]: dense tensors only
+                    ok = ok && s.Wo == a.W && o.pix_stride == s.cout_p && o.chan_off == 0 && !o.padded;
+                    if (residual[i] >= 0) {
+                        const TensorInfo& rt = n.tensors[residual[i]];
+                        ok = ok && rt.pix_stride == s.cout_p && rt.chan_off == 0 && !rt.padded;
+                    }
+                }
+                if (ok) {
+                    s.pairw = d.stride == 2 ? 1 : 2;
+                    s.cfg.swz = 128;
+                    s.cfg.block_n = pick_block_n(s.cout_p);   // == cout_p (32 or 64)
+                    s.cfg.cluster = 1;
+                    s.cfg.stages = st1(s.cfg.block_n, 128);
+                }
+            }
             if (tc_ok && flat_conv[i]) {
                 s.flat = 1;
                 s.cfg.gather = 0;
@@ -953,9 +1066,18 @@ int plan_net(y3_net& n) {
             if (tc_ok) {
                 s.kind = 1;
                 w.cout_pad = ((s.cout_p + s.cfg.block_n - 1) / s.cfg.block_n) * s.cfg.block_n;
+                if (s.pairw == 2) w.cout_pad *= 2;   // one N tile per output-pixel parity
+                w.pairw = s.pairw;
+                w.pair_cout_p = s.cout_p;
                 w.stem_hilo = (s.cfg.gather == 2);
                 s.stem_col = (s.cfg.gather == 2 && g_stem_col && d.stride == 1 && s.pad_lo == 1 && s.Ho == a.H && s.Wo == a.W) ? 1 : 0;
                 w.stem_col = s.stem_col != 0;
+                if (s.stem_col && g_stem_band && s.cout_p == 32) {
+                    const TensorInfo& o = n.tensors[writes[i]];
+                    if (o.pix_stride == 32 && o.chan_off == 0 && !o.padded && stem_band_geometry(a.H, a.W, s.band_r, s.band_p))
+                        s.stem_band = 1;
+                }
+                w.stem_band = s.stem_band != 0;
                 w.flat_order = s.flat != 0;
                 w.flat_bk = s.cfg.swz / 2;
                 pl.block_n = s.cfg.block_n; pl.swizzle = s.cfg.swz; pl.stages = s.cfg.stages;
@@ -1108,25 +1230,32 @@ int build_maps(y3_net& n) {
             } else if (d.ksize == 1 && d.stride == 1) {
                 rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * a.H * a.W, a.Cp, a.pix_stride, y3::kBlockM,
                                  s.cfg.swz, false);
+            } else if (s.pairw) {
+                rc = make_map_im2col_pairs(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, d.stride, s.pad_lo, s.pad_hi);
             } else {
                 rc = make_map_im2col(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, a.Cp, a.pix_stride, d.ksize, d.stride,
                                      s.pad_lo, s.pad_hi, s.cfg.swz);
             }
         }
         if (rc) return rc;
-        const uint64_t K = (s.cfg.gather == 2) ? 64 : (uint64_t)d.ksize * d.ksize * a.Cp;
+        const uint64_t K = (s.cfg.gather == 2) ? 64 : (s.pairw ? 384 : (uint64_t)d.ksize * d.ksize * a.Cp);
         rc = make_map_2d(n.ctx->drv, &s.tmB, w.w, w.cout_pad, K, K, s.cfg.block_n / (s.cfg.gather ? 1 : (s.cfg.cluster >= 2 ? 2 : 1)), s.cfg.swz, true);
         if (rc) return rc;
         const TensorInfo& o = n.tensors[s.dst];
         std::memset(&s.tmO, 0, sizeof(s.tmO));
         std::memset(&s.tmR, 0, sizeof(s.tmR));
-        if (s.tma_out) {   // decided by the planner
+        if (s.stem_band) {
+            rc = make_map_stem_out(n.ctx->drv, &s.tmO, tensor_ptr(n, s.dst), n.max_batch, s.Ho, s.Wo);
+            if (rc) return rc;
+        } else if (s.tma_out) {   // decided by the planner
             const int cw = s.tma_out;
-            const uint64_t rows = (uint64_t)n.max_batch * s.Ho * s.Wo;
-            rc = make_map_epi(n.ctx->drv, &s.tmO, tensor_ptr(n, s.dst), rows, s.cout_p, o.pix_stride, cw);
+            // pixel-pair view, stride 1: a row of the output / residual is a pixel PAIR of 2 x cout_p channels
+            const uint64_t pw = (s.pairw == 2) ? 2 : 1;
+            const uint64_t rows = (uint64_t)n.max_batch * s.Ho * s.Wo / pw;
+            rc = make_map_epi(n.ctx->drv, &s.tmO, tensor_ptr(n, s.dst), rows, s.cout_p * pw, o.pix_stride * pw, cw);
             if (rc) return rc;
             if (s.src2 >= 0) {
-                rc = make_map_epi(n.ctx->drv, &s.tmR, tensor_ptr(n, s.src2), rows, s.cout_p, n.tensors[s.src2].pix_stride, cw);
+                rc = make_map_epi(n.ctx->drv, &s.tmR, tensor_ptr(n, s.src2), rows, s.cout_p * pw, n.tensors[s.src2].pix_stride * pw, cw);
                 if (rc) return rc;
             }
         }
@@ -1151,13 +1280,28 @@ y3::ConvArgs conv_args(const Step& s, const y3_layer_desc& d, int cin, int B) {
         a.kblocks_per_tap = cin / (s.cfg.swz / 2);
         a.num_k_blocks = d.ksize * d.ksize * a.kblocks_per_tap;
     }
+    a.ksize_w = d.ksize; a.stride_w = d.stride; a.lower_w = a.lower;
     a.tiles_m = (a.M + y3::kBlockM - 1) / y3::kBlockM;
     const int cout_p = s.cout_p > 0 ? s.cout_p : d.filters;   // channels as stored (zero weights / bias beyond filters)
     a.tiles_n = (cout_p + s.cfg.block_n - 1) / s.cfg.block_n;
     a.cout = cout_p;
     a.leaky = d.activation;
     a.upsample = s.fused_up;
-    a.it_h = s.Ho; a.it_w = s.Wo;
+    if (s.pairw) {
+        // pixel-pair view of the 32-channel input (ConvArgs::ksize_w): one 64-wide K block per (row, pair column) tap
+        a.kblocks_per_tap = 1;
+        a.num_k_blocks = 6;
+        a.ksize_w = 2; a.stride_w = 1; a.lower_w = -1;
+        if (s.pairw == 2) {   // GEMM row = output pixel pair, N tile = parity of the pixel inside the pair
+            a.Wo = s.Wo / 2;
+            a.M = B * s.Ho * a.Wo;
+            a.tiles_m = (a.M + y3::kBlockM - 1) / y3::kBlockM;
+            a.tiles_n = 2;
+            a.cout = 2 * cout_p;
+            a.a_shift_n = 1;
+        }
+    }
+    a.it_h = a.Ho; a.it_w = a.Wo;
     a.out_padded = s.out_padded;
     if (s.flat || s.in_padded) {
         // the GEMM M index walks the haloed grid of the input
@@ -1312,8 +1456,9 @@ int y3_net_create(y3_ctx* ctx, const y3_layer_desc* layers, int n_layers, int H,
             cudaMemset(n->sync, 0, (size_t)n->sync_words * sizeof(uint32_t));
         }
         for (ConvWeights& w : n->convs) {
-            const size_t K = (size_t)w.k * w.k * w.cin;
-            const size_t wbytes = w.direct ? K * w.cout * 4 : (size_t)w.cout_pad * (w.stem_hilo ? 64 : K) * 2;
+            const size_t K = w.pairw ? 384 : (size_t)w.k * w.k * w.cin;
+            size_t wbytes = w.direct ? K * w.cout * 4 : (size_t)w.cout_pad * (w.stem_hilo ? 64 : K) * 2;
+            if (w.stem_band) wbytes = std::max<size_t>(wbytes, y3::kStemWBytes);
             if (cudaMalloc(&w.w, wbytes) != cudaSuccess || cudaMalloc(&w.bias, (size_t)w.cout_pad * 4) != cudaSuccess) {
                 y3_net_destroy(n);
                 return fail(Y3_ERR_CUDA, "cudaMalloc(weights) failed");
@@ -1348,6 +1493,19 @@ void y3_net_destroy(y3_net* net) {
 int y3_net_num_convs(y3_net* net) { return net ? (int)net->convs.size() : 0; }
 int y3_net_num_outputs(y3_net* net) { return net ? (int)net->outputs.size() : 0; }
 int64_t y3_net_arena_bytes(y3_net* net) { return net ? net->arena_bytes : 0; }
+
+int y3_net_read_layer(y3_net* net, int layer, int B, void* host_bf16) {
+    if (!net || !host_bf16 || layer < 0 || layer >= (int)net->layers.size()) return fail(Y3_ERR_INVALID, "bad layer");
+    if (net->ctx->device < 0 || !net->arena) return fail(Y3_ERR_STATE, "planning-only context has no activations");
+    if (B <= 0 || B > net->max_batch) return fail(Y3_ERR_INVALID, "batch exceeds max_batch");
+    const TensorInfo& t = net->tensors[layer + 1];
+    if (!t.materialized || t.fp32_output || t.buffer < 0 || t.padded)
+        return fail(Y3_ERR_UNSUPPORTED, "layer " + std::to_string(layer) + " is fused away (not materialised as a dense bf16 tensor)");
+    Y3_CUDA(cudaDeviceSynchronize());
+    Y3_CUDA(cudaMemcpy2D(host_bf16, (size_t)t.C * 2, tensor_ptr(*net, layer + 1), (size_t)t.pix_stride * 2, (size_t)t.C * 2,
+                         (size_t)B * t.H * t.W, cudaMemcpyDeviceToHost));
+    return Y3_OK;
+}
 
 int y3_net_get_plan(y3_net* net, y3_layer_plan* plans_host, int n_layers) {
     if (!net || !plans_host || n_layers != (int)net->plans.size()) return fail(Y3_ERR_INVALID, "bad plan query");
@@ -1395,6 +1553,24 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
         for (size_t kk = 0; kk < K; ++kk)
             for (int o = 0; o < cout; ++o) packed[kk * cout + o] = kernel[kk * cout + o] * scale[o];   // HWIO is already [K][Cout]
         Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    } else if (w.stem_band) {
+        // conv_stem.cuh: B_r[(j, o)][(q, c)] = w[r][s = q - j][c][o] for output pixel j of the pair, input pixel q = 0..3
+        // (pixel 2m - 1 + q), channel c (c = 3 is the zero padding channel); stored [r][K chunk = q / 2][64][8]
+        std::vector<__nv_bfloat16> packed(y3::kStemWBytes / 2, __float2bfloat16(0.0f));
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < 2; ++j)
+                for (int q = 0; q < 4; ++q) {
+                    const int sx = q - j;
+                    if (sx < 0 || sx > 2) continue;
+                    for (int c = 0; c < 3; ++c) {
+                        const size_t kk = (size_t)(r * 3 + sx) * cin_l + c;
+                        const int kidx = q * 4 + c;
+                        for (int o = 0; o < cout; ++o)
+                            packed[((size_t)(r * 2 + kidx / 8) * 64 + (j * 32 + o)) * 8 + kidx % 8] =
+                                __float2bfloat16(kernel[kk * cout + o] * scale[o]);
+                    }
+                }
+        Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     } else if (w.stem_hilo && w.stem_col) {
         // column-sharing producer: K columns in the order its threads store them (stem_col_k)
         std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * 64, __float2bfloat16(0.0f));
@@ -1409,6 +1585,27 @@ int y3_net_load_conv(y3_net* net, int conv_idx, const float* kernel, const float
                     }
                 }
         Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    } else if (w.pairw) {
+        // pixel-pair view (ConvArgs::ksize_w): row j * cout_p + o (j = output pixel parity, stride 1 only), K index
+        // ((r * 2 + S) * 2 + i) * 32 + c holds w[r][s = 2S + i + j - 1][c][o]; taps outside 0..2 stay zero
+        const int nj = w.pairw == 2 ? 2 : 1;
+        std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * 384, __float2bfloat16(0.0f));
+        for (int j = 0; j < nj; ++j)
+            for (int r = 0; r < 3; ++r)
+                for (int S = 0; S < 2; ++S)
+                    for (int i = 0; i < 2; ++i) {
+                        const int sx = 2 * S + i + j - 1;
+                        if (sx < 0 || sx > 2) continue;
+                        for (int c = 0; c < cin_l; ++c) {
+                            const size_t kk = (size_t)(r * 3 + sx) * cin_l + c;
+                            const size_t dst = (size_t)((r * 2 + S) * 2 + i) * 32 + c;
+                            for (int o = 0; o < cout; ++o)
+                                packed[(size_t)(j * w.pair_cout_p + o) * 384 + dst] = __float2bfloat16(kernel[kk * cout + o] * scale[o]);
+                        }
+                    }
+        Y3_CUDA(cudaMemcpy(w.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+        if (w.pairw == 2)   // the bias of channel o applies to both pixels of the pair
+            for (int o = 0; o < cout; ++o) shift[w.pair_cout_p + o] = shift[o];
     } else if (w.stem_hilo) {
         // columns [0,27) multiply bf16(x), columns [32,59) multiply the bf16 remainder x - bf16(x): same weights twice
         std::vector<__nv_bfloat16> packed((size_t)w.cout_pad * 64, __float2bfloat16(0.0f));
@@ -1566,7 +1763,7 @@ void plan_chain(const y3_net& net, int B, const int* out_pitch, std::vector<Chai
     }
     auto plain = [&](int si) {   // a step the flags can describe at all
         const Step& s = net.steps[si];
-        return s.kind == 1 && !s.flat && !s.in_padded && !s.out_padded && s.sync_off >= 0 && cas[si].dbg == 0;
+        return s.kind == 1 && !s.flat && !s.in_padded && !s.out_padded && !s.pairw && s.sync_off >= 0 && cas[si].dbg == 0;
     };
     if (g_chain_runs) {
         // ---- persistent runs: consecutive CTA-pair layers with the bf16 64-column TMA-store epilogue ----
@@ -1878,6 +2075,10 @@ static int net_forward_impl(y3_net* net, const void* x_in, bool x_u8, int B, flo
                 ca.out = tensor_ptr(*net, s.dst);
                 ca.out_stride = o.pix_stride;
             }
+            if (s.pairw == 2) {   // rows are pixel pairs
+                ca.out_stride *= 2;
+                ca.res_stride *= 2;
+            }
             if (chain_on && !runs) wire_chain(*net, *chainp, si, ca);
             if (s.flat) {
                 FlatGeom g;
@@ -1885,6 +2086,19 @@ static int net_forward_impl(y3_net* net, const void* x_in, bool x_u8, int B, flo
                 Y3_CUDA(launch_flat(s.cfg.swz, s.tmA, s.tmB, ca, g.smem, sms, st));
             } else if (s.cfg.gather) {
                 ca.H = a.H; ca.W = a.W;
+                if (s.stem_band) {
+                    y3::StemArgs sa{};
+                    sa.src = stem_u8 ? x_in : (const void*)x;
+                    sa.B = B; sa.H = a.H; sa.W = a.W;
+                    sa.R = s.band_r; sa.P = s.band_p;
+                    sa.wq = w.w;
+                    sa.bias = w.bias;
+                    sa.leaky = d.activation;
+                    sa.in_div = 255.0f;
+                    sa.dbg = ca.dbg;
+                    Y3_CUDA(stem_u8 ? launch_stem_band_t<true>(s.tmO, sa, sms, st) : launch_stem_band_t<false>(s.tmO, sa, sms, st));
+                    continue;
+                }
                 if (s.cfg.gather == 2) {
                     ca.src = stem_u8 ? x_in : (const void*)x;
                     ca.src_stride = 3;
