@@ -94,8 +94,10 @@ def nms_set_overlap(dec_gpu, dec_ref, max_boxes, iou_thr, score_thr, match_iou=0
             "gpu_detections": int(nvg.sum())}
 
 
-def measure(init, size, B, C, seed=3, with_nms=True, score_thr=0.1, chunk=8):
-    """GPU forward (+decode) vs oracle for one configuration; returns a dict of achieved errors."""
+def measure(init, size, B, C, seed=3, with_nms=True, score_thr=0.1, chunk=8, nms_images=None):
+    """GPU forward (+decode) vs oracle for one configuration; returns a dict of achieved errors.  ``nms_images``: the
+    informational NMS set overlap (the C oracle NMS on dense init-V boxes takes seconds per image) looks at the first
+    nms_images images only; logits and boxes are always compared for every image."""
     import torch
     import yolo_v3_tf2_b200 as y3
     from yolo_v3_tf2_b200 import configs
@@ -113,6 +115,8 @@ def measure(init, size, B, C, seed=3, with_nms=True, score_thr=0.1, chunk=8):
     dk = y3.yolo_decode([torch.from_numpy(g).cuda() for g in grids], anchors, C)
     out["decode_kernel_vs_oracle_abs"] = float(max(np.abs(a.cpu().numpy() - b).max() for a, b in zip(dk, dg)))
     if with_nms:
-        out["nms"] = nms_set_overlap(dg, dr, 100, 0.5, score_thr)
+        k = B if nms_images is None else min(B, nms_images)
+        out["nms"] = nms_set_overlap(tuple(a[:k] for a in dg), tuple(a[:k] for a in dr), 100, 0.5, score_thr)
+        out["nms"]["images"] = k
     model.close()
     return out

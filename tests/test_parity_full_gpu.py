@@ -63,6 +63,7 @@ def test_boxes_of_gpu_logits_vs_oracle(cuda, C):
                                            ("keras", 416, 64, 80)])
 def test_full_batches_vs_oracle(cuda, init, size, B, C):
     """BASELINE configs 2 (416^2 B=64), 3 (the 32-image 608^2 shard of the 8-GPU run) and 5 (37 classes, B=128) compared
-    with net_oracle.forward directly, every image (the oracle runs at ~16 images/s on 16 cores)."""
-    res = parity_util.measure(init, size, B, C, seed=17, with_nms=(B <= 64))
+    with net_oracle.forward directly, every image (the oracle runs at ~16 images/s on 16 cores); the informational NMS
+    set overlap is taken over the first 6 images (the oracle NMS of dense init-V boxes takes seconds per image)."""
+    res = parity_util.measure(init, size, B, C, seed=17, with_nms=(B <= 64), nms_images=6)
     _check(res, keras=(init == "keras"))

@@ -6,16 +6,21 @@ set -u
 TAG=${1:-rX}
 mkdir -p gpurun_out
 SMALL="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ncu"
+ONE="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --ncu"
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json
 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 480 -c 260 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "ncu launches exit $?"
-# DRAM bytes of the 75 conv launches of one forward pass of the timed region (3 warm-up passes skipped)
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:'conv_' -s 450 -c 75 --csv --log-file gpurun_out/${TAG}_traffic.csv $SMALL > gpurun_out/${TAG}_ncu4.log 2>&1
+# DRAM bytes of every conv launch (the summariser keeps the last forward pass of the capture)
+$ONE > gpurun_out/${TAG}_plain1.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:'conv_' -c 200 --csv --log-file gpurun_out/${TAG}_traffic.csv $ONE > gpurun_out/${TAG}_ncu4.log 2>&1
 echo "ncu traffic exit $?"
-ncu --set full --clock-control none --import-source on -k regex:'conv_tc2_kernel' -s 468 -c 3 -o gpurun_out/${TAG}_prof_conv $SMALL > gpurun_out/${TAG}_ncu2.log 2>&1
-echo "ncu conv exit $?"
-ncu --set full --clock-control none --import-source on -k regex:'decode_kernel|nms_kernel' -s 12 -c 2 -o gpurun_out/${TAG}_prof_post $SMALL > gpurun_out/${TAG}_ncu3.log 2>&1
+# full captures: the 50-layer persistent launch (the dominant kernel), the stem, the pixel-pair Cin = 32 layer
+ncu --set full --clock-control none --import-source on -k regex:'conv_chain_kernel' -s 9 -c 1 -o gpurun_out/${TAG}_prof_chain $ONE > gpurun_out/${TAG}_ncu2.log 2>&1
+echo "ncu chain exit $?"
+ncu --set full --clock-control none --import-source on -k regex:'conv_stem_band|conv_tc_kernel<64, 128' -s 15 -c 3 -o gpurun_out/${TAG}_prof_first $ONE > gpurun_out/${TAG}_ncu5.log 2>&1
+echo "ncu first exit $?"
+ncu --set full --clock-control none --import-source on -k regex:'decode_kernel|nms_kernel' -s 6 -c 2 -o gpurun_out/${TAG}_prof_post $ONE > gpurun_out/${TAG}_ncu3.log 2>&1
 echo "ncu post exit $?"
-ls -la gpurun_out | tail -12
+ls -la gpurun_out | tail -14

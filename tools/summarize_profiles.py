@@ -51,10 +51,17 @@ if os.path.exists(tp):
         elif u in ("ms", "msecond"):
             v *= 1e6
         d[r["Metric Name"]] = v
+    # the capture holds every conv launch of several forward passes: keep the LAST pass (it starts at the stem kernel)
+    items = list(per.values())
+    stems = [i for i, d in enumerate(items) if "conv_stem" in d["name"] or "conv_first" in d["name"] or
+             ("conv_gather_kernel<32, 128" in d["name"])]
+    if stems:
+        items = items[stems[-1]:]
+    per = collections.OrderedDict((i, d) for i, d in enumerate(items))
     rd = sum(d.get("dram__bytes_read.sum", 0) for d in per.values())
     wr = sum(d.get("dram__bytes_write.sum", 0) for d in per.values())
     tt = sum(d.get("gpu__time_duration.sum", 0) for d in per.values())
-    out.append(f"## DRAM traffic of one forward pass ({len(per)} conv launches, batch 64, 416x416)\n")
+    out.append(f"## DRAM traffic of one forward pass ({len(per)} conv launches -- the persistent multi-layer launches (conv_chain_kernel) cover 50 / 6 / 6 layers each --, batch 64, 416x416, uint8 input)\n")
     out.append(f"read {rd / 1e9:.3f} GB + write {wr / 1e9:.3f} GB = **{(rd + wr) / 1e9:.3f} GB** per forward pass "
                f"(algorithmic bytes, SURVEY 8d: 190 MB/img x 64 = 12.16 GB); serialised kernel time {tt / 1e6:.3f} ms\n")
     out.append("| # | kernel | us | DRAM read MB | DRAM write MB | tensor pipe % of elapsed |\n|---|---|---|---|---|---|")
@@ -67,7 +74,7 @@ if os.path.exists(tp):
     rec = {"dram_bytes_read": rd, "dram_bytes_write": wr, "launches": len(per), "kernel_time_ms": tt / 1e6,
            "size": 416, "batch": 64, "commit": commit, "capture": f"gpurun_out/{tag}_traffic.csv",
            "command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum ... -k regex:conv_ "
-                      "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ncu"}
+                      "python bench.py --steps 1 --warmup 3 --no-cpu-baseline --ncu (last forward pass of the capture)"}
     json.dump(rec, open(f"profiles/{name}_traffic.json", "w"), indent=1)
 
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",

@@ -37,6 +37,17 @@ struct DecodeArgs {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Which class logits can reach the float32 maximum of sigmoidf_acc over a record whose largest logit is m (p_m =
+// sigmoidf_acc(m))?  sigmoidf_acc(x) = sigmoid(x) (1 + e) with |e| <= 4e-7 (expf: 2 ulp on a term that enters with weight
+// <= 1, one rounding each for the add and the divide), so sigmoidf_acc(x) < sigmoidf_acc(m) is certain once
+// sigmoid(m) / sigmoid(x) > 1 + 8e-7.  d/dx ln sigmoid = 1 - sigmoid is decreasing, hence
+// ln sigmoid(m) - ln sigmoid(x) >= (m - x) (1 - sigmoid(m)), and x < m - 2e-6 / (1 - p_m) is out of reach with a 2.5 x
+// margin.  Where the sigmoid saturates (p_m == 1) the bound is -inf: every class stays a candidate.  Callers treat
+// m < -80 (denormal / zero probabilities, where the relative error model does not hold) separately.
+__device__ __forceinline__ float class_tie_threshold(float m, float p_m) {
+    return (p_m < 1.0f) ? m - 2e-6f / (1.0f - p_m) : -INFINITY;   // (m = +inf would give inf - inf)
+}
+
 __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs a) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const int F = 5 + a.C;
@@ -129,13 +140,11 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     if (a.probs == nullptr && a.scores != nullptr) {
         // ---- compact decode (the fused pipeline: NMS reads only boxes and scores): what is needed per record is
         // max_c sigmoid(t_c) and the FIRST class that attains it, not the C probabilities.  sigmoid is increasing, so only
-        // classes whose logit is close to the largest one, m, can attain the float32 maximum: with
-        // thr = min(m, 6) - 4e-3 every class below thr has an exact sigmoid smaller than sigmoid(min(m, 6)) by >= 1e-5
-        // relative, 50 x the rounding error of sigmoidf_acc.  Four threads per record find m, then evaluate the sigmoid of
-        // the candidates t_c >= thr only (one per record for a trained network; all of them for the near-constant
-        // logits of a random-init head) and reduce (probability, lowest class).  Records with m < -80 (zero / denormal
-        // probabilities tie far below m) or a NaN treat every class as a candidate.  The result is bit-identical to the
-        // class reduce of the probabilities this kernel writes in its non-compact mode.
+        // classes whose logit is close to the largest one, m, can attain the float32 maximum (class_tie_threshold below).
+        // Four threads per record find m, then evaluate the sigmoid of the candidates t_c >= thr only (almost always one)
+        // and reduce (probability, lowest class).  Records with m < -80 (zero / denormal probabilities tie far below m)
+        // or a NaN treat every class as a candidate.  The result is bit-identical to the class reduce of the
+        // probabilities this kernel writes in its non-compact mode.
         const int t = (int)threadIdx.x >> 2, part = (int)threadIdx.x & 3;
         static_assert(kDecodeThreads == 4 * kDecodeRecs, "four threads per record");
         const bool live = t < nrec;
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
         const bool any_nan = ((__ballot_sync(0xffffffffu, nan) >> ((threadIdx.x & 31u) & ~3u)) & 0xFu) != 0u;
-        const float thr = (any_nan || !(m >= -80.0f)) ? -INFINITY : fminf(m, 6.0f) - 4e-3f;
+        const float thr = (any_nan || !(m >= -80.0f)) ? -INFINITY : class_tie_threshold(m, sigmoidf_acc(m));
         float best = -INFINITY;
         int bi = 0x7fffffff;
         if (live)

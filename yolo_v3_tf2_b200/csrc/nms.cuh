@@ -64,6 +64,21 @@ __device__ __forceinline__ float iou_tf(const float4 a, const float4 b) {
     return __fdiv_rn(inter, uni);
 }
 
+// counts[w] = items of warp w (32 warps): woff = items of the warps before `wid`, tot = all of them.  Every warp scans the
+// 32 counts with shuffles (the first version had every thread add them up in a 32-iteration loop, per 1024-wide tile).
+__device__ __forceinline__ void warp_counts_scan(const int* counts, int wid, int lane, int& woff, int& tot) {
+    static_assert(kNmsThreads == 1024, "one count per lane");
+    const int c = counts[lane];
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    tot = __shfl_sync(0xffffffffu, inc, 31);
+    woff = __shfl_sync(0xffffffffu, inc - c, wid);
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     extern __shared__ __align__(16) uint8_t nsm[];
     uint32_t* keys = reinterpret_cast<uint32_t*>(nsm);                       // [NP]
@@ -73,6 +88,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     float4* cbox = kept + kNmsKeptCap;                                       // [kNmsChunk]
     uint32_t* mask = reinterpret_cast<uint32_t*>(cbox + kNmsChunk);          // [kNmsChunk][8]
     uint32_t* dead = mask + kNmsChunk * 8;                                   // [8] chunk-level dead bits
+    uint32_t* validw = dead + 8;                                             // [8] chunk boxes with a coordinate > 0
     // radix-select histogram [kNmsBins]: aliases the kept list, which is only used after the sort (16 KB each; at
     // N = 22 743 (608x608) keys + indices alone take 192 KB of the 227 KB)
     uint32_t* hist = reinterpret_cast<uint32_t*>(kept);
@@ -116,12 +132,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
             if (lane == 0) s_warp_cnt[wid] = __popc(bal);
             __syncthreads();
-            int woff = 0, tot = 0;
-            for (int w = 0; w < kNmsThreads / 32; ++w) {
-                const int c = s_warp_cnt[w];
-                if (w < wid) woff += c;
-                tot += c;
-            }
+            int woff, tot;
+            warp_counts_scan(s_warp_cnt, wid, lane, woff, tot);
             if (pass) {
                 const int pos = base + woff + __popc(bal & ((1u << lane) - 1u));
                 keys[pos] = score_key(s);
@@ -150,9 +162,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
             const uint32_t bmask = (pass == 2) ? 0xFFu : 0xFFFu;
             for (int i = tid; i < kNmsBins; i += kNmsThreads) hist[i] = 0u;
             __syncthreads();
-            for (int i = tid; i < ncand; i += kNmsThreads) {
-                const uint32_t k = keys[i];
-                if ((k & pmask) == prefix) atomicAdd(&hist[(k >> shift) & bmask], 1u);
+            // warp-aggregated: the lanes that hit the same bin send ONE atomic.  Detection scores share their exponent
+            // and leading mantissa bits, so in the first pass most of the 10 647 keys of a dense image fall into a
+            // handful of bins; one shared-memory atomic per key serialised them (that pass alone was ~40 % of the kernel).
+            for (int t0 = 0; t0 < ncand; t0 += kNmsThreads) {
+                const int i = t0 + tid;
+                const uint32_t k = (i < ncand) ? keys[i] : 0u;
+                const bool act = (i < ncand) && ((k & pmask) == prefix);
+                const uint32_t bin = act ? ((k >> shift) & bmask) : 0xFFFFFFFFu;
+                const uint32_t grp = __match_any_sync(0xffffffffu, bin);
+                if (act && lane == __ffs(grp) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(grp));
             }
             __syncthreads();
             // suffix sums from the top bin: thread t owns bins [4t, 4t+4), highest bins = highest t
@@ -197,12 +216,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
             if (lane == 0) s_warp_cnt[wid] = __popc(bal);
             __syncthreads();
-            int woff = 0, tot = 0;
-            for (int w = 0; w < kNmsThreads / 32; ++w) {
-                const int c = s_warp_cnt[w];
-                if (w < wid) woff += c;
-                tot += c;
-            }
+            int woff, tot;
+            warp_counts_scan(s_warp_cnt, wid, lane, woff, tot);
             if (pass && base + tot <= kNmsTopCap) {
                 const int pos = base + woff + __popc(bal & ((1u << lane) - 1u));
                 keys[pos] = k;
@@ -253,6 +268,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
                 if (pass) b = bx[oi];
             }
             cbox[tid] = b;
+            const uint32_t vb = __ballot_sync(0xffffffffu, b.x > 0.f || b.y > 0.f || b.z > 0.f || b.w > 0.f);
+            if (lane == 0) validw[wid] = vb;
         }
         if (tid < 8) dead[tid] = 0u;
         __syncthreads();
@@ -290,31 +307,48 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
         }
         __syncthreads();
 
-        // C: sequential resolution by warp 0; lane w (< 8) owns dead word w.  Only surviving rows are visited.
+        // C: sequential resolution by warp 0; lane w (< 8) owns dead word w.  The chunk is resolved in 8 blocks of 32 rows:
+        // inside a block every lane runs the same register-only loop over the still-alive rows (the row's 32-bit
+        // intra-block mask word comes from the lane that holds it, one shuffle per surviving row), then the survivors'
+        // mask words are OR-ed into the dead words of the later blocks, one lane per word.  The loop stops at the
+        // max_boxes-th valid survivor: nothing after it can be selected.  (The first version walked all 256 rows with a
+        // ballot + two find-first-set + a shuffle + a shared-memory load per surviving row while the other 31 warps
+        // waited at the barrier below: 40 % of the kernel.)
         if (wid == 0) {
             uint32_t dw = (lane < 8) ? dead[lane] : 0xffffffffu;
-            // bits beyond nc are dead
-            if (lane < 8) {
+            if (lane < 8) {   // bits beyond nc are dead
                 const int lo = lane * 32;
                 if (nc <= lo) dw = 0xffffffffu;
                 else if (nc < lo + 32) dw |= ~((1u << (nc - lo)) - 1u);
             }
-            int i = 0;
-            while (true) {
-                // next alive index >= i
-                const uint32_t alive_w = (lane < 8) ? ~dw : 0u;
-                uint32_t cand = alive_w;
-                const int wi = i >> 5;
-                if (lane < wi) cand = 0u;
-                else if (lane == wi) cand &= ~((1u << (i & 31)) - 1u);
-                const uint32_t has = __ballot_sync(0xffffffffu, cand != 0u);
-                if (has == 0u) break;
-                const int fw = __ffs(has) - 1;
-                const uint32_t wbits = __shfl_sync(0xffffffffu, cand, fw);
-                const int row = fw * 32 + (__ffs(wbits) - 1);
-                if (lane < 8) dw |= mask[row * 8 + lane];
-                i = row + 1;
-                if (i >= nc) break;
+            const uint32_t vw = (lane < 8) ? validw[lane] : 0u;
+            int need = a.max_boxes - s_nsel;          // >= 1: the chunk loop stops once max_boxes are selected
+            bool done = false;
+            for (int sb = 0; sb < kNmsChunk / 32 && sb * 32 < nc; ++sb) {
+                if (done) {                            // everything after the last needed survivor is irrelevant
+                    if (lane == sb) dw = 0xffffffffu;
+                    continue;
+                }
+                const uint32_t mrow = mask[(sb * 32 + lane) * 8 + sb];     // row (sb, lane): columns of the same block
+                uint32_t d = __shfl_sync(0xffffffffu, dw, sb);
+                const uint32_t vm = __shfl_sync(0xffffffffu, vw, sb);
+                uint32_t todo = ~d, surv = 0u;
+                while (todo != 0u) {
+                    const int r = __ffs(todo) - 1;
+                    surv |= 1u << r;
+                    if (((vm >> r) & 1u) && --need == 0) { done = true; break; }
+                    d |= __shfl_sync(0xffffffffu, mrow, r);
+                    todo = ~d & ~((2u << r) - 1u);     // alive rows after r (r == 31: the mask is all ones)
+                }
+                if (lane == sb) dw = ~surv;
+                if (lane > sb && lane < 8 && !done) {
+                    uint32_t sv = surv;
+                    while (sv != 0u) {
+                        const int r = __ffs(sv) - 1;
+                        sv &= sv - 1u;
+                        dw |= mask[(sb * 32 + r) * 8 + lane];
+                    }
+                }
             }
             if (lane < 8) dead[lane] = dw;
         }

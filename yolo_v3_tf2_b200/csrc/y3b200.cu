@@ -2297,7 +2297,7 @@ int y3_nms(y3_ctx* ctx, const float* bboxes, const float* scores, int B, int N, 
     a.max_boxes = max_boxes;
     a.iou_thr = iou_thr; a.score_thr = score_thr;
     a.selected = selected; a.num_valid = num_valid; a.status = status;
-    const size_t smem = (size_t)np * 6 + (size_t)(y3::kNmsKeptCap + y3::kNmsChunk) * 16 + (size_t)y3::kNmsChunk * 8 * 4 + 32;
+    const size_t smem = (size_t)np * 6 + (size_t)(y3::kNmsKeptCap + y3::kNmsChunk) * 16 + (size_t)y3::kNmsChunk * 8 * 4 + 64;
     Y3_CUDA(ensure_dyn_smem((const void*)y3::nms_kernel, (int)smem));   // static shared memory counts against the limit too
     y3::nms_kernel<<<B, y3::kNmsThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     Y3_CUDA(cudaGetLastError());
