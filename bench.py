@@ -26,16 +26,18 @@ def workload_name(size, batch):
             f"forward + decode + NMS(max 100, iou 0.5, score 0.1) + gather")
 
 
-def conv_flops(model, H, W):
+def conv_flops(model, H, W, batch=1):
+    """(conv FLOPs per image, kernel launches of one forward pass at this batch size).  Consecutive CTA-pair layers run
+    as ONE persistent launch (csrc/conv_chain.cuh), so the launch count is taken from the planner's step list."""
     from yolo_v3_tf2_b200 import _lib
-    p = model.plan(H, W, 1)
+    p = model.plan(H, W, batch)
     fl, ci = 0, 0
     for l, pl in zip(model.graph.layers, p["layers"]):
         if l.op == _lib.OP_CONV:
             k, cin, cout, _ = model.conv_shapes[ci]
             ci += 1
             fl += 2 * pl["H"] * pl["W"] * cout * k * k * cin
-    launches = sum(1 for pl in p["layers"] if pl["kernel"] != 0)
+    launches = sum(1 for i, st in enumerate(p["steps"]) if st["run_first"] < 0 or st["run_first"] == i)
     return fl, launches
 
 
@@ -216,7 +218,7 @@ def main():
     model = y3.ParseModel.builtin_yolov3(NCLASSES).init_weights("keras", seed=0)
     anchors = configs.coco_anchors()
     det = y3.Detector(model, anchors, NCLASSES, yolo_max_boxes=100, nms_iou_threshold=0.5, nms_score_threshold=0.1)
-    flops_img, launches_fwd = conv_flops(model, S, S)
+    flops_img, launches_fwd = conv_flops(model, S, S, B)
     mx = det.max_boxes
 
     # synthetic inputs: per-rank seed; a few rotating device buffers + pinned host copies
@@ -414,13 +416,15 @@ def main():
                     "d2h_bytes_per_step": B * (mx * 6 + 1) * 4,
                     "note": "Detector.detections_graphed() (the step replayed from a CUDA graph) on pinned host batches, "
                             "double-buffered H2D on a copy stream, detections copied back to pinned host memory every step"},
+            # kernels of this library per timed step: the conv launches + decode + NMS + gather (the memset of the
+            # layer-chaining counters is a driver memset node and is not counted)
             "gpu_launches": K * (launches_fwd + 3),
         }
         if roof:
             line["roofline"] = {
                 "bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved_tflops / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel": f"tcgen05 implicit-GEMM conv kernels (the whole forward pass: {launches_fwd} conv layers), "
+                "kernel": f"tcgen05 implicit-GEMM conv kernels (the whole forward pass: 75 conv layers in {launches_fwd} launches), "
                           "replayed from its own CUDA graph between CUDA events right after each timed-style step "
                           "(interleaved, same clocks); achieved = algorithmic conv FLOPs of one batch / that time; "
                           "algorithmic bytes = 190 MB/img",

@@ -17,7 +17,8 @@
 //   so one 128 x 64 x 16 MMA per (filter row, hi / lo) -- six per tile -- computes 256 output pixels x 32 channels, and
 //   the producers only convert each input pixel once per band: ~13 instructions per output pixel instead of ~100.
 //   The accumulator row of a pair IS its 128 output bytes (2 pixels x 32 channels, NHWC), so the epilogue is the usual
-//   TMEM -> +bias -> LeakyReLU -> bf16 -> swizzled staging -> TMA store, through a 3-D map (128 B, pairs, rows) that clips
+//   TMEM -> +bias -> LeakyReLU -> bf16 -> swizzled staging -> TMA store (one 64-byte pixel of each pair at a time), through
+//   a 3-D map (2 x 64 B, pairs, rows) that clips
 //   the junk pairs at the end of each row (the flat row pitch P is a multiple of 32 pairs so that no 32-pair store
 //   chunk straddles two image rows).
 // Arithmetic is identical to the old stem (same hi / lo split, same bf16 weights, fp32 accumulation; the summation
@@ -39,7 +40,9 @@ struct StemArgs {
     int dbg;
 };
 
-constexpr int kStemThreads = 512;        // warps: 0 weights, 1 MMA, 2 TMEM, 3 idle, 4-11 epilogue, 12-15 producers
+constexpr int kStemThreads = 768;        // warps: 0 weights, 1 MMA, 2 TMEM, 3 idle, 4-19 epilogue, 20-23 producers
+constexpr int kStemEpiWarps = 16;        // four groups of four (one TMEM lane quarter each)
+constexpr int kStemEpiWarpBytes = 4096;  // staging per epilogue warp: ring of two 32 x 64-byte half chunks
 constexpr int kStemAccStages = 8;        // 8 x 64 fp32 columns = all 512 TMEM columns
 constexpr int kStemWBytes = 6144;
 
@@ -47,7 +50,7 @@ constexpr int kStemWBytes = 6144;
 // 1024 bytes so that the epilogue's swizzled staging buffers behind the planes stay 1024-byte aligned
 __host__ __device__ inline int stem_plane_bytes(int R, int P) { return ((R + 2) * P * 16 + 256 + 1023) & ~1023; }
 __host__ __device__ inline int stem_smem_bytes(int R, int P) {
-    return 1024 + 2 * 2 * stem_plane_bytes(R, P) + kStemWBytes + 8 * kEpiWarpBytes + 1024 /*lut*/ + 512 /*barriers*/;
+    return 1024 + 2 * 2 * stem_plane_bytes(R, P) + kStemWBytes + kStemEpiWarps * kStemEpiWarpBytes + 1024 /*lut*/ + 512 /*barriers*/;
 }
 
 // no-swizzle K-major operand: 8-row core matrices of 128 contiguous bytes; lbo = distance of the second 16-byte K chunk,
@@ -82,7 +85,7 @@ conv_stem_band_kernel(const __grid_constant__ CUtensorMap tmO, const StemArgs p)
     const uint32_t smem_in = smem_base;
     const uint32_t smem_w = smem_in + 2u * buf_bytes;
     const uint32_t smem_stg = smem_w + kStemWBytes;
-    const uint32_t smem_lut = smem_stg + 8u * kEpiWarpBytes;
+    const uint32_t smem_lut = smem_stg + (uint32_t)(kStemEpiWarps * kStemEpiWarpBytes);
     const uint32_t bar_base = smem_lut + 1024u;
     auto in_full = [&](int b) { return bar_base + 8u * b; };
     auto in_empty = [&](int b) { return bar_base + 8u * (2 + b); };
@@ -171,21 +174,26 @@ conv_stem_band_kernel(const __grid_constant__ CUtensorMap tmO, const StemArgs p)
             if (leader) umma_commit(in_empty(b));
         }
         __syncwarp();
-    } else if (warp >= 4 && warp < 12) {
-        // ===================== epilogue: two groups of four warps, tiles alternate between the groups =====================
+    } else if (warp >= 4 && warp < 4 + kStemEpiWarps) {
+        // ===================== epilogue: four groups of four warps, tiles are dealt round-robin to the groups ==========
+        // A warp owns 32 accumulator lanes (= 32 pixel pairs) of its group's tiles and stores them as two half chunks:
+        // columns 0..31 = the even pixel of each pair, 32..63 = the odd one (32 channels = 64 bytes each).  Sixteen warps
+        // working on 32 columns at a time (the first version: eight warps x 64 columns, 122 registers) because the
+        // per-chunk latency chain -- TMEM load, conversion, staging stores, proxy fence, TMA store -- is what bounds the
+        // kernel, not the arithmetic.
         const int eg = (warp - 4) >> 2;
         const int q = warp & 3;
-        const uint32_t stg = smem_stg + (uint32_t)(warp - 4) * kEpiWarpBytes;
+        const uint32_t stg = smem_stg + (uint32_t)(warp - 4) * kStemEpiWarpBytes;
         const float slope = p.leaky ? 0.1f : 1.0f;
-        const uint32_t sw = (uint32_t)(lane & 7);
-        const uint32_t row_off = (uint32_t)lane * 128u;
-        uint32_t g = 0;     // chunks stored so far by this warp (ring of two 4 KB buffers)
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte piece index ^ ((row >> 1) & 3)
+        const uint32_t row_off = (uint32_t)lane * 64u;
+        uint32_t g = 0;     // half chunks stored so far by this warp (ring of two 2 KB buffers)
         int j = 0, k = 0;
         for (int band = blockIdx.x; band < num_bands; band += gridDim.x, ++k) {
             const int n = band / bands_per_img;
             const int y0 = (band - n * bands_per_img) * R;
             for (int t = 0; t < T; ++t, ++j) {
-                if ((j & 1) != eg) continue;
+                if ((j & 3) != eg) continue;
                 const int s = j & (kStemAccStages - 1);
                 mbar_wait(tfull(s), (uint32_t)((j / kStemAccStages) & 1), 0x400 + s);
                 tc_fence_after();
@@ -197,24 +205,24 @@ conv_stem_band_kernel(const __grid_constant__ CUtensorMap tmO, const StemArgs p)
                     mbar_arrive(tempty(s));
                     continue;
                 }
-                const uint32_t buf = stg + (g & 1u) * 4096u;
-                if (lane == 0) tma_store_wait_read<1>();      // the store that last used this buffer has read it
-                __syncwarp();
-                uint32_t v[64];
                 const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 64);
-                tmem_ld_32x32(t_acc, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                tmem_ld_32x32(t_acc + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                 const float4* bp = reinterpret_cast<const float4*>(p.bias);
-                float4 bz[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) bz[i] = __ldg(bp + i);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(tempty(s));
-                if (!(p.dbg & 1)) {
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t buf = stg + (g & 1u) * 2048u;
+                    if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+                    __syncwarp();
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_acc + (uint32_t)(half * 32), v);
+                    tmem_ld_wait();
+                    if (half == 1) {                           // every TMEM read of this accumulator has completed
+                        tc_fence_before();
+                        mbar_arrive(tempty(s));
+                    }
+                    if (p.dbg & 1) continue;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {              // 16-byte piece c: pixel c / 4 of the pair, channels 8 (c % 4) ..
-                        const float4 b0 = bz[2 * (c & 3)], b1 = bz[2 * (c & 3) + 1];
+                    for (int c = 0; c < 4; ++c) {              // 16-byte piece c: channels 8c .. 8c+7 of this pixel
+                        const float4 b0 = __ldg(bp + 2 * c), b1 = __ldg(bp + 2 * c + 1);
                         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         const float2 s2 = make_float2(slope, slope);
                         __nv_bfloat162 o2[4];
@@ -230,7 +238,7 @@ conv_stem_band_kernel(const __grid_constant__ CUtensorMap tmO, const StemArgs p)
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (!(p.dbg & 2)) tma_store_3d(&tmO, buf, 0, m0, n * p.H + y0 + i_out);
+                        if (!(p.dbg & 2)) tma_store_3d(&tmO, buf, half * 32, m0, n * p.H + y0 + i_out);
                         tma_store_commit();
                     }
                     ++g;
@@ -238,14 +246,14 @@ conv_stem_band_kernel(const __grid_constant__ CUtensorMap tmO, const StemArgs p)
             }
         }
         if (lane == 0) tma_store_wait<0>();
-    } else if (warp >= 12) {
+    } else if (warp >= 4 + kStemEpiWarps) {
         // ===================== producers: image rows -> flat bf16 RGBX hi / lo planes =====================
         // Task (row slot rs, column slot qs) of a thread: row i = pw + 4 rs of the band, pixels 4q-1 .. 4q+2 with
         // q = lane + 32 qs, i.e. the two 16-byte chunks 2q, 2q+1 of that row.  The global loads of a whole band (uint8:
         // 4 words per task) are issued into registers BEFORE the thread waits for the band's buffer to be released, so
         // their latency hides behind that wait; the first version loaded task by task and the producers' exposed
         // load latency (8 round trips per band) made the kernel no faster than the software-im2col stem.
-        const int pw = warp - 12;
+        const int pw = warp - 4 - kStemEpiWarps;
         const int nq = p.W / 4 + 1;
         constexpr int RS = 3;            // R + 2 <= 10 rows over 4 producer warps
         auto store_task = [&](uint32_t row_s, int qq, const uint32_t (&px)[4][3]) {

@@ -87,19 +87,103 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (spitch != pitch) {
+        // one copy per pixel (pitch * 4 bytes, a multiple of 16), each issued by its own thread (one thread issuing all
+        // 21 serialised ~1 us of the CTA's life).  A copy may complete before thread 0's arrive.expect_tx: the
+        // transaction count then goes negative for a moment, and the phase cannot complete before that one arrival.
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar_s, bulk_bytes);
+        if ((int)threadIdx.x < nrec / 3)
+            bulk_load_1d(smem_u32(rec + threadIdx.x * spitch), src + (long long)threadIdx.x * pitch, (uint32_t)pitch * 4u, bar_s);
+    } else if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(bar_s, bulk_bytes);
-        if (spitch != pitch) {
-            for (int px = 0; px < nrec / 3; ++px)     // one copy per pixel (pitch * 4 bytes, a multiple of 16)
-                bulk_load_1d(smem_u32(rec + px * spitch), src + (long long)px * pitch, (uint32_t)pitch * 4u, bar_s);
-        } else if (bulk_bytes) {
-            bulk_load_1d(smem_u32(rec), src, bulk_bytes, bar_s);
-        }
+        if (bulk_bytes) bulk_load_1d(smem_u32(rec), src, bulk_bytes, bar_s);
     }
     // the (at most 3) floats past the last 16-byte multiple
     for (int i = (int)(bulk_bytes >> 2) + threadIdx.x; i < nfl; i += kDecodeThreads) rec[i] = src[i];
     mbar_wait(bar_s, 0, 0x600);
     __syncthreads();
+
+    const int C = a.C;
+    if (a.probs == nullptr && a.conf == nullptr && a.scores != nullptr) {
+        // ---- compact decode (the fused pipeline: NMS reads only boxes and scores), four threads per record ----
+        // Box: the five transcendental evaluations of a record are spread over its four threads (sigmoid t_x + objectness,
+        // sigmoid t_y, exp t_w, exp t_h) and collected with shuffles; same operations as the per-record path below.
+        // Class: what is needed is max_c sigmoid(t_c) and the FIRST class that attains it, not the C probabilities.
+        // sigmoid is increasing, so only classes whose logit is close to the largest one, m, can attain the float32
+        // maximum (class_tie_threshold).  The four threads find m, then evaluate the sigmoid of the candidates
+        // t_c >= thr only (almost always one) and reduce (probability, lowest class).  Records with m < -80 (zero /
+        // denormal probabilities tie far below m) or a NaN treat every class as a candidate.  The result is
+        // bit-identical to the class reduce of the probabilities this kernel writes in its non-compact mode.
+        static_assert(kDecodeThreads == 4 * kDecodeRecs, "four threads per record");
+        const int t = (int)threadIdx.x >> 2, part = (int)threadIdx.x & 3;
+        const bool live = t < nrec;
+        const float* r = rec_at(live ? t : 0);
+        const long long fr = r0 + (live ? t : 0);
+        const int b = (int)(fr / per_img);
+        const int local = (int)(fr - (long long)b * per_img);
+        const int cell = local / 3;
+        const int anc = local - cell * 3;
+        const int gi = cell / a.gw[s];
+        const int gj = cell - gi * a.gw[s];
+        const long long orec = (long long)b * a.N + a.rec_off[s] + local;
+        float e0;                                   // part 0: sigmoid(t_x), 1: sigmoid(t_y), 2: w, 3: h
+        if (part < 2) e0 = sigmoidf_acc(r[part]);
+        else e0 = expf(r[part]) * a.anchors[(s * 3 + anc) * 2 + (part - 2)];
+        const float obj = sigmoidf_acc(r[4]);       // (all four threads: cheaper than another shuffle)
+        const int base = (int)(threadIdx.x & 31u) & ~3;
+        const float sx = __shfl_sync(0xffffffffu, e0, base + 0);
+        const float sy = __shfl_sync(0xffffffffu, e0, base + 1);
+        const float w = __shfl_sync(0xffffffffu, e0, base + 2);
+        const float h = __shfl_sync(0xffffffffu, e0, base + 3);
+        if (live && part == 0) {
+            const float cx = __fdiv_rn(__fadd_rn(sx, (float)gj), (float)a.gh[s]);   // the reference's (rows, cols) divisor
+            const float cy = __fdiv_rn(__fadd_rn(sy, (float)gi), (float)a.gw[s]);   // order, see the per-record path
+            const float hw = w * 0.5f, hh = h * 0.5f;
+            float4 box;
+            box.x = __fsub_rn(cx, hw);
+            box.y = __fsub_rn(cy, hh);
+            box.z = __fadd_rn(cx, hw);
+            box.w = __fadd_rn(cy, hh);
+            reinterpret_cast<float4*>(a.bboxes)[orec] = box;
+        }
+        float m = -INFINITY;
+        bool nan = false;
+        if (live)
+            for (int c = part; c < C; c += 4) {
+                const float v = r[5 + c];
+                nan |= (v != v);
+                m = fmaxf(m, v);
+            }
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        const bool any_nan = ((__ballot_sync(0xffffffffu, nan) >> base) & 0xFu) != 0u;
+        const float thr = (any_nan || !(m >= -80.0f)) ? -INFINITY : class_tie_threshold(m, sigmoidf_acc(m));
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        if (live)
+            for (int c = part; c < C; c += 4) {
+                const float v = r[5 + c];
+                if (v >= thr) {
+                    const float pc = sigmoidf_acc(v);
+                    if (pc > best) { best = pc; bi = c; }      // classes ascend: the first maximum of this thread is kept
+                }
+            }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (live && part == 0) {
+            // the sequential scan this replaces starts from class 0 and replaces it only by a strictly larger value: a NaN
+            // in class 0 is never replaced, a NaN anywhere else never wins
+            const float p0 = r[5];
+            if (p0 != p0 || bi == 0x7fffffff) { best = sigmoidf_acc(p0); bi = 0; }
+            a.scores[orec] = __fmul_rn(obj, best);
+            a.cls[orec] = (long long)bi;
+        }
+        return;
+    }
 
     // ---- (1) per-record box / objectness (+ class max) ----
     if ((int)threadIdx.x < nrec) {
@@ -135,59 +219,6 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         r[4] = obj;   // kept for the fused score in phase (3)
     }
     __syncthreads();
-
-    const int C = a.C;
-    if (a.probs == nullptr && a.scores != nullptr) {
-        // ---- compact decode (the fused pipeline: NMS reads only boxes and scores): what is needed per record is
-        // max_c sigmoid(t_c) and the FIRST class that attains it, not the C probabilities.  sigmoid is increasing, so only
-        // classes whose logit is close to the largest one, m, can attain the float32 maximum (class_tie_threshold below).
-        // Four threads per record find m, then evaluate the sigmoid of the candidates t_c >= thr only (almost always one)
-        // and reduce (probability, lowest class).  Records with m < -80 (zero / denormal probabilities tie far below m)
-        // or a NaN treat every class as a candidate.  The result is bit-identical to the class reduce of the
-        // probabilities this kernel writes in its non-compact mode.
-        const int t = (int)threadIdx.x >> 2, part = (int)threadIdx.x & 3;
-        static_assert(kDecodeThreads == 4 * kDecodeRecs, "four threads per record");
-        const bool live = t < nrec;
-        const float* r = rec_at(live ? t : 0);
-        float m = -INFINITY;
-        bool nan = false;
-        if (live)
-            for (int c = part; c < C; c += 4) {
-                const float v = r[5 + c];
-                nan |= (v != v);
-                m = fmaxf(m, v);
-            }
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        const bool any_nan = ((__ballot_sync(0xffffffffu, nan) >> ((threadIdx.x & 31u) & ~3u)) & 0xFu) != 0u;
-        const float thr = (any_nan || !(m >= -80.0f)) ? -INFINITY : class_tie_threshold(m, sigmoidf_acc(m));
-        float best = -INFINITY;
-        int bi = 0x7fffffff;
-        if (live)
-            for (int c = part; c < C; c += 4) {
-                const float v = r[5 + c];
-                if (v >= thr) {
-                    const float pc = sigmoidf_acc(v);
-                    if (pc > best) { best = pc; bi = c; }      // classes ascend: the first maximum of this thread is kept
-                }
-            }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if (live && part == 0) {
-            // the sequential scan this replaces starts from class 0 and replaces it only by a strictly larger value: a NaN
-            // in class 0 is never replaced, a NaN anywhere else never wins
-            const float p0 = r[5];
-            if (p0 != p0 || bi == 0x7fffffff) { best = sigmoidf_acc(p0); bi = 0; }
-            const long long orec = out_rec[t];
-            a.scores[orec] = __fmul_rn(r[4], best);
-            a.cls[orec] = (long long)bi;
-        }
-        return;
-    }
 
     // ---- (2) class probabilities ----
     if ((C & 3) == 0) {

@@ -79,6 +79,21 @@ __device__ __forceinline__ void warp_counts_scan(const int* counts, int wid, int
     woff = __shfl_sync(0xffffffffu, inc - c, wid);
 }
 
+// iou_tf(a, b) >= thr for thr > 0, without the division when the boxes do not intersect: inter == 0 gives
+// iou = 0 / uni = +-0 (or NaN when uni == 0), never >= a positive threshold.  Most pairs of a chunk do not overlap.
+__device__ __forceinline__ bool iou_ge_pos(const float4 a, const float4 b, float thr) {
+    const float ix1 = fmaxf(a.x, b.x), iy1 = fmaxf(a.y, b.y);
+    const float ix2 = fminf(a.z, b.z), iy2 = fminf(a.w, b.w);
+    const float iw = fmaxf(__fsub_rn(ix2, ix1), 0.0f);
+    const float ih = fmaxf(__fsub_rn(iy2, iy1), 0.0f);
+    const float inter = __fmul_rn(iw, ih);
+    if (!(inter > 0.0f)) return false;
+    const float area_a = __fmul_rn(__fsub_rn(a.w, a.y), __fsub_rn(a.z, a.x));
+    const float area_b = __fmul_rn(__fsub_rn(b.w, b.y), __fsub_rn(b.z, b.x));
+    const float uni = __fadd_rn(__fsub_rn(__fadd_rn(area_a, area_b), inter), 1e-8f);
+    return __fdiv_rn(inter, uni) >= thr;
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     extern __shared__ __align__(16) uint8_t nsm[];
     uint32_t* keys = reinterpret_cast<uint32_t*>(nsm);                       // [NP]
@@ -108,6 +123,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     // With score_thr >= 0 and iou_thr > 0 the filtered (all-zero) boxes sort after every passing box, never suppress
     // and are never selected, so only passing boxes need to be sorted/visited.  Otherwise keep all N candidates.
     const bool compact = (a.score_thr >= 0.0f) && (a.iou_thr > 0.0f);
+    const bool pos_thr = a.iou_thr > 0.0f;
 
     if (tid == 0) { s_ncand = 0; s_nkept = 0; s_nsel = 0; s_overflow = 0; }
     for (int i = tid; i < a.max_boxes; i += kNmsThreads) sel[i] = 0;
@@ -280,8 +296,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
             if (ci < nc) {
                 const float4 b = cbox[ci];
                 bool d = false;
-                for (int k = tid >> 8; k < nkept && !d; k += kNmsThreads / kNmsChunk)
-                    d = iou_tf(kept[k], b) >= a.iou_thr;
+                if (pos_thr) {
+                    for (int k = tid >> 8; k < nkept && !d; k += kNmsThreads / kNmsChunk) d = iou_ge_pos(kept[k], b, a.iou_thr);
+                } else {
+                    for (int k = tid >> 8; k < nkept && !d; k += kNmsThreads / kNmsChunk) d = iou_tf(kept[k], b) >= a.iou_thr;
+                }
                 if (d) atomicOr(&dead[ci >> 5], 1u << (ci & 31));
             }
         }
@@ -299,8 +318,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
                 if (row_alive && (w * 32 + 31) > i) {
                     const int jlo = max(w * 32, i + 1);
                     const int jhi = min(w * 32 + 32, nc);
-                    for (int j = jlo; j < jhi; ++j)
-                        if (iou_tf(bi, cbox[j]) >= a.iou_thr) bits |= 1u << (j & 31);
+                    if (pos_thr) {
+                        for (int j = jlo; j < jhi; ++j)
+                            if (iou_ge_pos(bi, cbox[j], a.iou_thr)) bits |= 1u << (j & 31);
+                    } else {
+                        for (int j = jlo; j < jhi; ++j)
+                            if (iou_tf(bi, cbox[j]) >= a.iou_thr) bits |= 1u << (j & 31);
+                    }
                 }
                 mask[i * 8 + w] = bits;
             }

@@ -491,14 +491,14 @@ bool stem_band_geometry(int H, int W, int& R, int& P) {
     }
     return false;
 }
-// output [B, H, W, 32] bf16 (dense) as (128 bytes = one pixel pair, W / 2 pairs, B * H rows); box = 32 pairs of one row
+// output [B, H, W, 32] bf16 (dense) as (128 bytes = one pixel pair, W / 2 pairs, B * H rows); box = one pixel of 32 pairs of a row
 int make_map_stem_out(const Driver& d, CUtensorMap* tm, const void* base, int B, int H, int W) {
     cuuint64_t dims[3] = {64, (cuuint64_t)(W / 2), (cuuint64_t)B * (cuuint64_t)H};
     cuuint64_t strides[2] = {128, 128ull * (uint64_t)(W / 2)};
-    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t box[3] = {32, 32, 1};   // one pixel (32 channels = 64 bytes) of each of 32 pairs
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = d.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeTiled (stem output) failed: " + std::to_string((int)r));
     return Y3_OK;
