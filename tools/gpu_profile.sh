@@ -19,7 +19,7 @@ echo "ncu traffic exit $?"
 # full captures: the 50-layer persistent launch (the dominant kernel), the stem, the pixel-pair Cin = 32 layer
 ncu --set full --clock-control none --import-source on -k regex:'conv_chain_kernel' -s 9 -c 1 -o gpurun_out/${TAG}_prof_chain $ONE > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "ncu chain exit $?"
-ncu --set full --clock-control none --import-source on -k regex:'conv_stem_band|conv_tc_kernel<64, 128' -s 15 -c 3 -o gpurun_out/${TAG}_prof_first $ONE > gpurun_out/${TAG}_ncu5.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_stem_band_kernel|conv_tc_kernel" -s 20 -c 4 -o gpurun_out/${TAG}_prof_first $ONE > gpurun_out/${TAG}_ncu5.log 2>&1
 echo "ncu first exit $?"
 ncu --set full --clock-control none --import-source on -k regex:'decode_kernel|nms_kernel' -s 6 -c 2 -o gpurun_out/${TAG}_prof_post $ONE > gpurun_out/${TAG}_ncu3.log 2>&1
 echo "ncu post exit $?"
