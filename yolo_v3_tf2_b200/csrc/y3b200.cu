@@ -22,6 +22,7 @@
 #include "conv_flat.cuh"
 #include "conv_chain.cuh"
 #include "conv_stem.cuh"
+#include "conv_band.cuh"
 #include "decode.cuh"
 #include "nms.cuh"
 #include "preprocess.cuh"
@@ -539,6 +540,67 @@ cudaError_t launch_stem_band_q(const CUtensorMap& to, const y3::StemArgs& a, int
     return cudaLaunchKernelEx(&cfg, kern, to, a);
 }
 
+// Band-resident 3x3 stride-1 Cin = 32 conv (conv_band.cuh): Y3_BAND=0 keeps the pixel-pair im2col path
+const bool g_use_band = env_int("Y3_BAND", 1) != 0;
+// flat row pitch (W + 2 rounded up to a multiple of 32, so that a 32-pixel store chunk never straddles image rows) and band
+// height for a [H, W] input and an N tile of bn channels; R = 0 if the layer does not fit
+int band_pitch(int W) { return (W + 2 + 31) / 32 * 32; }
+int band_rows(int H, int W, int bn) {
+    const int P = band_pitch(W);
+    if (P > 256 || W < 32) return 0;            // one TMA box per band: box dimensions are at most 256
+    for (int r : {8, 4, 2}) {
+        const int smem = bn == 64 ? y3::band_smem_bytes<64>(r, P) : y3::band_smem_bytes<32>(r, P);
+        if (H % r == 0 && smem <= 232448) return r;
+    }
+    return 0;
+}
+// dense 32-channel NHWC input as (C, W, H, N) with a box of 32 channels x (W + 2) pixels x (R + 2) rows
+int make_map_band_in(const Driver& d, CUtensorMap* tm, const void* base, int N, int H, int W, uint64_t pix_stride, int R) {
+    cuuint64_t dims[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {pix_stride * 2, pix_stride * 2 * (uint64_t)W, pix_stride * 2 * (uint64_t)W * (uint64_t)H};
+    cuuint32_t box[4] = {32, (cuuint32_t)band_pitch(W), (cuuint32_t)(R + 2), 1};   // x = -1 .. P - 2, zero filled outside
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = d.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeTiled (band input) failed: " + std::to_string((int)r));
+    return Y3_OK;
+}
+// output / residual view [B, H, W, C] (pixel pitch pix_stride) as (C, W, B * H); box = 32 channels x 32 pixels of one row
+int make_map_band_io(const Driver& d, CUtensorMap* tm, const void* base, int B, int H, int W, int C, uint64_t pix_stride) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)B * (cuuint64_t)H};
+    cuuint64_t strides[2] = {pix_stride * 2, pix_stride * 2 * (uint64_t)W};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = d.tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(Y3_ERR_CUDA, "cuTensorMapEncodeTiled (band output) failed: " + std::to_string((int)r));
+    return Y3_OK;
+}
+template <int BN>
+cudaError_t launch_band_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                          const y3::BandArgs& a, int sms, cudaStream_t st) {
+    auto kern = y3::conv_band_kernel<BN>;
+    const int smem = y3::band_smem_bytes<BN>(a.R, a.P);
+    {
+        cudaError_t e = ensure_dyn_smem((const void*)kern, smem);
+        if (e != cudaSuccess) return e;
+    }
+    const int bands = a.B * (a.H / a.R);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)std::max(1, std::min(bands, sms)));
+    cfg.blockDim = dim3(y3::kBandThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, a);
+}
+
 // The flat-patch 3x3 kernel (conv_flat.cuh) is parity-green but measured slower end to end than the im2col path
 // (forward 6.13 ms vs 5.52 ms at B = 64: the haloed layouts cost the neighbouring 1x1 layers more than the 3x3 layers
 // gain), so it is opt-in: Y3_FLAT=1.
@@ -675,6 +737,7 @@ struct Step {
     int stem_col = 0;      // stem through the column-sharing producer (stride 1, pad 1)
     int stem_band = 0;     // stem through conv_stem_band_kernel; band rows / pair pitch below
     int band_r = 0, band_p = 0;
+    int band = 0;          // 3x3 stride-1 Cin = 32 conv on a band-resident input (conv_band.cuh), band_r rows per band
     int pairw = 0;         // Cin = 32 3x3 conv on the pixel-pair view of its input (1: stride 2, 2: stride 1)
     int tma_out = 0;       // epilogue writes through tmO (and reads the residual through tmR)
     int rev = 0;           // walk the output tiles backwards (alternates from conv to conv, see ConvArgs::rev)
@@ -1024,7 +1087,21 @@ int plan_net(y3_net& n) {
                     s.cfg.stages = st2(128);
                 }
             }
-            if (tc_ok && s.cfg.gather == 0 && !flat_conv[i] && d.ksize == 3 && a.Cp == 32 && d.src0 != 0 &&
+            if (tc_ok && s.cfg.gather == 0 && !flat_conv[i] && g_use_band && d.ksize == 3 && d.stride == 1 && a.Cp == 32 &&
+                d.src0 != 0 && a.pix_stride % 8 == 0 && !a.padded && s.pad_lo == 1 && s.pad_hi == 1 && s.Ho == a.H &&
+                s.Wo == a.W && (s.cout_p == 32 || s.cout_p == 64) && !fused_up[i] && !n.tensors[writes[i]].fp32_output &&
+                !n.tensors[writes[i]].padded && a.W % 2 == 0) {
+                const int r = band_rows(a.H, a.W, s.cout_p);
+                if (r) {
+                    s.band = 1;
+                    s.band_r = r;
+                    s.cfg.swz = 64;
+                    s.cfg.block_n = s.cout_p;
+                    s.cfg.cluster = 1;
+                    s.cfg.stages = 2;
+                }
+            }
+            if (tc_ok && !s.band && s.cfg.gather == 0 && !flat_conv[i] && d.ksize == 3 && a.Cp == 32 && d.src0 != 0 &&
                 (g_pairw & (d.stride == 2 ? 1 : 2)) && a.W % 2 == 0 && a.pix_stride == 32 && a.chan_off == 0 && !a.padded &&
                 s.cout_p <= 64 && !fused_up[i] && !n.tensors[writes[i]].fp32_output && s.pad_lo == 1) {
                 // Cin = 32 3x3 conv on the pixel-pair view of its (dense) input: 6 TMA rows of 128 B per output, not 9 of 64 B
@@ -1098,7 +1175,7 @@ int plan_net(y3_net& n) {
             // TMA-store epilogue: bf16 output, dense pixel indexing, no fused upsample
             s.tma_out = 0;
             if (s.kind == 1 && g_use_tma_epi && !n.tensors[writes[i]].fp32_output && !s.fused_up && !s.flat && !s.in_padded &&
-                !s.out_padded)
+                !s.out_padded && !s.band)
                 s.tma_out = epi_chunk_cols(s.cfg.block_n, s.src2 >= 0);
             pl.kernel = s.kind;
             pl.fused_add = residual[i];
@@ -1230,6 +1307,8 @@ int build_maps(y3_net& n) {
             } else if (d.ksize == 1 && d.stride == 1) {
                 rc = make_map_2d(n.ctx->drv, &s.tmA, ap, (uint64_t)n.max_batch * a.H * a.W, a.Cp, a.pix_stride, y3::kBlockM,
                                  s.cfg.swz, false);
+            } else if (s.band) {
+                rc = make_map_band_in(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, a.pix_stride, s.band_r);
             } else if (s.pairw) {
                 rc = make_map_im2col_pairs(n.ctx->drv, &s.tmA, ap, n.max_batch, a.H, a.W, d.stride, s.pad_lo, s.pad_hi);
             } else {
@@ -1247,6 +1326,14 @@ int build_maps(y3_net& n) {
         if (s.stem_band) {
             rc = make_map_stem_out(n.ctx->drv, &s.tmO, tensor_ptr(n, s.dst), n.max_batch, s.Ho, s.Wo);
             if (rc) return rc;
+        } else if (s.band) {
+            rc = make_map_band_io(n.ctx->drv, &s.tmO, tensor_ptr(n, s.dst), n.max_batch, s.Ho, s.Wo, s.cout_p, o.pix_stride);
+            if (rc) return rc;
+            if (s.src2 >= 0) {
+                rc = make_map_band_io(n.ctx->drv, &s.tmR, tensor_ptr(n, s.src2), n.max_batch, s.Ho, s.Wo, s.cout_p,
+                                      n.tensors[s.src2].pix_stride);
+                if (rc) return rc;
+            }
         } else if (s.tma_out) {   // decided by the planner
             const int cw = s.tma_out;
             // pixel-pair view, stride 1: a row of the output / residual is a pixel PAIR of 2 x cout_p channels
@@ -1763,7 +1850,7 @@ void plan_chain(const y3_net& net, int B, const int* out_pitch, std::vector<Chai
     }
     auto plain = [&](int si) {   // a step the flags can describe at all
         const Step& s = net.steps[si];
-        return s.kind == 1 && !s.flat && !s.in_padded && !s.out_padded && !s.pairw && s.sync_off >= 0 && cas[si].dbg == 0;
+        return s.kind == 1 && !s.flat && !s.in_padded && !s.out_padded && !s.pairw && !s.band && s.sync_off >= 0 && cas[si].dbg == 0;
     };
     if (g_chain_runs) {
         // ---- persistent runs: consecutive CTA-pair layers with the bf16 64-column TMA-store epilogue ----
@@ -2080,7 +2167,20 @@ static int net_forward_impl(y3_net* net, const void* x_in, bool x_u8, int B, flo
                 ca.res_stride *= 2;
             }
             if (chain_on && !runs) wire_chain(*net, *chainp, si, ca);
-            if (s.flat) {
+            if (s.band) {
+                y3::BandArgs ba{};
+                ba.B = B; ba.H = a.H; ba.W = a.W;
+                ba.R = s.band_r; ba.P = band_pitch(a.W);
+                ba.T = (ba.R * ba.P + 127) / 128;
+                ba.cout = s.cout_p;
+                ba.bias = w.bias;
+                ba.leaky = d.activation;
+                ba.residual = ca.residual;
+                ba.res_stride = ca.res_stride;
+                ba.dbg = ca.dbg;
+                Y3_CUDA(s.cout_p == 64 ? launch_band_t<64>(s.tmA, s.tmB, s.tmO, s.tmR, ba, sms, st)
+                                       : launch_band_t<32>(s.tmA, s.tmB, s.tmO, s.tmR, ba, sms, st));
+            } else if (s.flat) {
                 FlatGeom g;
                 flat_geometry(a.W + 1, s.cfg.swz, s.cfg.block_n, g);
                 Y3_CUDA(launch_flat(s.cfg.swz, s.tmA, s.tmB, ca, g.smem, sms, st));
