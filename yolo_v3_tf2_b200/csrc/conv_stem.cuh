@@ -187,6 +187,7 @@ conv_stem_band_kernel(const __grid_constant__ CUtensorMap tmO, const StemArgs p)
         const float slope = p.leaky ? 0.1f : 1.0f;
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte piece index ^ ((row >> 1) & 3)
         const uint32_t row_off = (uint32_t)lane * 64u;
+        const uint32_t inv_cpr = (65536u + (uint32_t)(P >> 5) - 1u) / (uint32_t)(P >> 5);   // chunk / chunks-per-row for chunk < 256
         uint32_t g = 0;     // half chunks stored so far by this warp (ring of two 2 KB buffers)
         int j = 0, k = 0;
         for (int band = blockIdx.x; band < num_bands; band += gridDim.x, ++k) {
@@ -198,7 +199,7 @@ conv_stem_band_kernel(const __grid_constant__ CUtensorMap tmO, const StemArgs p)
                 mbar_wait(tfull(s), (uint32_t)((j / kStemAccStages) & 1), 0x400 + s);
                 tc_fence_after();
                 const int f0 = t * 128 + q * 32;              // first flat pair of this warp's 32 lanes
-                const int i_out = f0 / P;
+                const int i_out = (int)(((uint32_t)(f0 >> 5) * inv_cpr) >> 16);   // f0 / P, P % 32 == 0 (no integer division)
                 const int m0 = f0 - i_out * P;
                 if (m0 >= half_w) {                            // junk pairs past the end of the image row
                     tc_fence_before();
