@@ -285,3 +285,32 @@ def test_unfusable_graphs_fall_back_to_standalone_kernels_or_reject():
     m3 = _mini({"a": big}, [{"name": "head", "layers_config_file": "a", "outputs_layers": [-1]}])
     with pytest.raises(_lib.Y3Unsupported, match="maxpool"):
         m3.plan(64, 64, 1)
+
+
+def test_planner_first_layer_kernels():
+    """Round-2 kernel selection for the first Darknet-53 layers, through the planning-only C ABI (no GPU): the Cin = 32
+    3x3 layers leave the 64-byte-row im2col path -- stride 2 on the pixel-pair view (128-byte rows, 64-wide N tile), stride
+    1 on the band-resident kernel (64-byte swizzle, no operand ring) when the row fits one TMA box, else on the pixel-pair
+    view too -- and the chained runs cover 62 of the 75 layers in 3 launches."""
+    from yolo_v3_tf2_b200 import ParseModel
+    m = ParseModel.builtin_yolov3(80)
+    p = m.plan(416, 416, 64)
+    L = p["layers"]
+    assert (L[1]["swizzle"], L[1]["block_n"]) == (128, 64)               # 3x3/2 32->64 @208: pixel pairs
+    assert (L[3]["swizzle"], L[3]["block_n"], L[3]["stages"]) == (64, 64, 2)   # 3x3 32->64 + Add @208: band resident
+    steps = p["steps"]
+    assert steps[3]["tiles_n"] == 1 and steps[3]["posts"] == 0 and steps[3]["chained"] == 0
+    runs = {}
+    for i, s in enumerate(steps):
+        if s["run_first"] >= 0:
+            runs[s["run_first"]] = runs.get(s["run_first"], 0) + 1
+    assert sorted(runs.values(), reverse=True) == [50, 6, 6]
+    launches = sum(1 for i, s in enumerate(steps) if s["run_first"] < 0 or s["run_first"] == i)
+    assert launches == 16
+    # 608 x 608: the 304-pixel rows of that layer do not fit one 256-wide TMA box -> pixel-pair view, N tile = pixel parity
+    p6 = m.plan(608, 608, 8)
+    assert (p6["layers"][3]["swizzle"], p6["layers"][3]["block_n"]) == (128, 64)
+    assert p6["steps"][3]["tiles_n"] == 2
+    # YOLOv3-tiny: both Cin = 32 3x3 layers (16 -> 32 @208 behind the first pool, 32 -> 64 @104) run band resident
+    t = ParseModel.builtin_yolov3_tiny(80).plan(416, 416, 4)["layers"]
+    assert (t[2]["swizzle"], t[2]["block_n"]) == (64, 32) and (t[4]["swizzle"], t[4]["block_n"]) == (64, 64)
