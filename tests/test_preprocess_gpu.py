@@ -53,3 +53,20 @@ def test_preprocess_feeds_the_model(cuda):
     b = model(np.stack([po.resize(f, 96, divide_by_255=True) for f in frames]))
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+def test_batch_tensor_equals_list_of_images(cuda):
+    """preprocess_images on ONE [B, H, W, 3] tensor (vectorised descriptors, a single device copy) gives exactly what the
+    per-image list path gives (tf.image.resize of inference.py:157-158 and resize_image of core/utils.py:17-28)."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    rng = np.random.default_rng(11)
+    for dtype in (np.uint8, np.float32):
+        batch = (rng.integers(0, 256, (5, 90, 130, 3)).astype(dtype) if dtype == np.uint8
+                 else rng.random((5, 90, 130, 3), dtype=np.float32))
+        for kw in ({"divide_by_255": True}, {"preserve_aspect_ratio": True}):
+            a = y3.preprocess_images(batch, 64, 96, **kw)                      # numpy batch
+            b = y3.preprocess_images(torch.from_numpy(batch).cuda(), 64, 96, **kw)   # CUDA batch
+            c = y3.preprocess_images([torch.from_numpy(f).cuda() for f in batch], 64, 96, **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(a, c) and torch.equal(b, c)

@@ -39,6 +39,9 @@ for (h, w) in [(480, 640), (1080, 1920)]:
     # algorithmic bytes: output written once; each output pixel reads at most 4 source pixels (12 bytes), capped by the source size
     byt = B * (416 * 416 * 3 * 4 + min(416 * 416 * 4 * 3, h * w * 3))
     rows.append((f"pre-processing {B} x {h}x{w} uint8 -> 416x416 f32 (/255)", ms * 1e3, byt / ms / 1e6, f"{B / ms * 1e3:.0f} img/s"))
+    stacked = torch.stack(frames)   # one [B, h, w, 3] tensor: the vectorised-descriptor path of preprocess_images
+    ms = timeit(lambda: y3.preprocess_images(stacked, 416, 416, divide_by_255=True, out=out))
+    rows.append((f"  ... same, frames as ONE [B,h,w,3] tensor", ms * 1e3, byt / ms / 1e6, f"{B / ms * 1e3:.0f} img/s"))
     ms = timeit(lambda: y3.preprocess_images(frames, 416, 416, preserve_aspect_ratio=True, out=out))
     rows.append((f"resize_image (aspect + pad) {B} x {h}x{w} -> 416x416", ms * 1e3, byt / ms / 1e6, f"{B / ms * 1e3:.0f} img/s"))
     # the kernel alone (descriptors prebuilt on the device): what the HBM roofline applies to

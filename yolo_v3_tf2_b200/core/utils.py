@@ -62,6 +62,26 @@ def preprocess_images(images, target_height, target_width, preserve_aspect_ratio
     ctx = _lib.context()
     dev = torch.device("cuda", ctx.device)
     keep, rows = [], []
+    if (isinstance(images, np.ndarray) or torch.is_tensor(images)) and images.ndim == 4:
+        # one [B, H, W, 3] batch of equally sized images: a single device copy and vectorised descriptors (the per-image
+        # loop below costs ~15 us of host time per image, which bounded the call at 0.07 of the copy bandwidth)
+        batch = torch.from_numpy(np.ascontiguousarray(images)) if isinstance(images, np.ndarray) else images
+        if batch.shape[3] != 3:
+            raise ValueError(f"batch shape {tuple(batch.shape)} is not [B, H, W, 3]")
+        if batch.dtype not in (torch.uint8, torch.float32):
+            batch = batch.float()
+        batch = batch.to(dev).contiguous()
+        keep.append(batch)
+        nb, h, w = int(batch.shape[0]), int(batch.shape[1]), int(batch.shape[2])
+        if preserve_aspect_ratio:
+            oh, ow = _aspect_size(h, w, target_height, target_width)
+            oy, ox = (target_height - oh) // 2, (target_width - ow) // 2
+        else:
+            oh, ow, oy, ox = target_height, target_width, 0, 0
+        rows = np.empty((nb, 10), dtype=np.int64)
+        rows[:, 0] = batch.data_ptr() + np.arange(nb, dtype=np.int64) * (h * w * 3 * batch.element_size())
+        rows[:, 1:] = [h, w, 0 if batch.dtype == torch.uint8 else 1, oh, ow, oy, ox, 0, 0]
+        images = ()
     for img in images:
         if isinstance(img, np.ndarray):
             img = torch.from_numpy(np.ascontiguousarray(img))
@@ -78,8 +98,8 @@ def preprocess_images(images, target_height, target_width, preserve_aspect_ratio
         else:
             oh, ow, oy, ox = target_height, target_width, 0, 0
         rows.append([img.data_ptr(), h, w, 0 if img.dtype == torch.uint8 else 1, oh, ow, oy, ox, 0, 0])
-    B = len(keep)
     rows = np.asarray(rows, dtype=np.int64)
+    B = int(rows.shape[0])
     # the scale factors of ResizeBilinear, float32 in / float32 out, passed as bit patterns
     rows[:, 8] = (rows[:, 1].astype(np.float32) / rows[:, 4].astype(np.float32)).view(np.int32)
     rows[:, 9] = (rows[:, 2].astype(np.float32) / rows[:, 5].astype(np.float32)).view(np.int32)
@@ -97,5 +117,5 @@ def preprocess_images(images, target_height, target_width, preserve_aspect_ratio
 def resize_image(img, target_height, target_width):
     """reference core/utils.py:17-28 for one image [H, W, 3] or a batch [B, H, W, 3] (all images of a batch share H, W)."""
     if img.ndim == 4:
-        return preprocess_images(list(img), target_height, target_width, preserve_aspect_ratio=True)
+        return preprocess_images(img, target_height, target_width, preserve_aspect_ratio=True)
     return preprocess_images([img], target_height, target_width, preserve_aspect_ratio=True)[0]
