@@ -178,17 +178,33 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
             const uint32_t bmask = (pass == 2) ? 0xFFu : 0xFFFu;
             for (int i = tid; i < kNmsBins; i += kNmsThreads) hist[i] = 0u;
             __syncthreads();
-            // warp-aggregated: the lanes that hit the same bin send ONE atomic.  Detection scores share their exponent
-            // and leading mantissa bits, so in the first pass most of the 10 647 keys of a dense image fall into a
-            // handful of bins; one shared-memory atomic per key serialised them (that pass alone was ~40 % of the kernel).
+            // Detection scores share their exponent and leading mantissa bits, so in the first pass most of the 10 647
+            // keys of a dense image fall into a handful of bins and same-address shared-memory atomics serialise -- across
+            // the lanes of a warp AND across the 32 warps.  Hence two levels of aggregation: the lanes that hit the same
+            // bin send one update (match_any), and while a whole warp keeps hitting ONE bin it only counts in a register
+            // and flushes when the bin changes (one atomic per warp per run instead of one per 32 keys).
+            uint32_t run_bin = 0xFFFFFFFFu, run_cnt = 0u;      // warp-uniform
             for (int t0 = 0; t0 < ncand; t0 += kNmsThreads) {
                 const int i = t0 + tid;
                 const uint32_t k = (i < ncand) ? keys[i] : 0u;
                 const bool act = (i < ncand) && ((k & pmask) == prefix);
                 const uint32_t bin = act ? ((k >> shift) & bmask) : 0xFFFFFFFFu;
-                const uint32_t grp = __match_any_sync(0xffffffffu, bin);
-                if (act && lane == __ffs(grp) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(grp));
+                const uint32_t am = __ballot_sync(0xffffffffu, act);
+                if (am == 0u) continue;
+                const uint32_t bin0 = __shfl_sync(0xffffffffu, bin, __ffs(am) - 1);
+                if (__all_sync(0xffffffffu, !act || bin == bin0)) {       // every active lane in the same bin
+                    if (bin0 != run_bin) {
+                        if (run_cnt != 0u && lane == 0) atomicAdd(&hist[run_bin], run_cnt);
+                        run_bin = bin0;
+                        run_cnt = 0u;
+                    }
+                    run_cnt += (uint32_t)__popc(am);
+                } else {
+                    const uint32_t grp = __match_any_sync(0xffffffffu, bin);
+                    if (act && lane == __ffs(grp) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(grp));
+                }
             }
+            if (run_cnt != 0u && lane == 0) atomicAdd(&hist[run_bin], run_cnt);
             __syncthreads();
             // suffix sums from the top bin: thread t owns bins [4t, 4t+4), highest bins = highest t
             const uint32_t h0 = hist[4 * tid], h1 = hist[4 * tid + 1], h2 = hist[4 * tid + 2], h3 = hist[4 * tid + 3];
