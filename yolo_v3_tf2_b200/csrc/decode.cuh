@@ -146,39 +146,61 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
             box.w = __fadd_rn(cy, hh);
             reinterpret_cast<float4*>(a.bboxes)[orec] = box;
         }
-        float m = -INFINITY;
+        // one pass: the largest logit m1 (first class attaining it: i1) and the runner-up value m2, per thread and then
+        // merged over the record's four threads.  An exact tie sets m2 = m1, so it can never pass for "unique" below.
+        float m1 = -INFINITY, m2 = -INFINITY;
+        int i1 = 0x7fffffff;
         bool nan = false;
         if (live)
             for (int c = part; c < C; c += 4) {
                 const float v = r[5 + c];
                 nan |= (v != v);
-                m = fmaxf(m, v);
-            }
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        const bool any_nan = ((__ballot_sync(0xffffffffu, nan) >> base) & 0xFu) != 0u;
-        const float thr = (any_nan || !(m >= -80.0f)) ? -INFINITY : class_tie_threshold(m, sigmoidf_acc(m));
-        float best = -INFINITY;
-        int bi = 0x7fffffff;
-        if (live)
-            for (int c = part; c < C; c += 4) {
-                const float v = r[5 + c];
-                if (v >= thr) {
-                    const float pc = sigmoidf_acc(v);
-                    if (pc > best) { best = pc; bi = c; }      // classes ascend: the first maximum of this thread is kept
-                }
+                if (v > m1) { m2 = m1; m1 = v; i1 = c; }
+                else m2 = fmaxf(m2, v);                      // (NaN: ignored by fmaxf)
             }
 #pragma unroll
         for (int o = 1; o <= 2; o <<= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            const float o1 = __shfl_xor_sync(0xffffffffu, m1, o);
+            const float o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i1, o);
+            if (o1 > m1) { m2 = fmaxf(m1, o2); m1 = o1; i1 = oi; }
+            else if (o1 == m1) { m2 = m1; i1 = min(i1, oi); }
+            else m2 = fmaxf(m2, o1);
+        }
+        const bool any_nan = ((__ballot_sync(0xffffffffu, nan) >> base) & 0xFu) != 0u;
+        const float p_m = sigmoidf_acc(m1);
+        const float thr = (any_nan || !(m1 >= -80.0f)) ? -INFINITY : class_tie_threshold(m1, p_m);
+        // runner-up below the threshold: the arg-max of the logits is the strict arg-max of the float32 probabilities and
+        // its probability is the one just computed -- the common case costs one sigmoid per record
+        const bool unique = m2 < thr;
+        float best = p_m;
+        int bi = i1;
+        if (__any_sync(0xffffffffu, live && !unique)) {
+            // some record of this warp has several candidates (near ties, saturation, NaN, tiny probabilities): its four
+            // threads evaluate the sigmoid of every candidate and reduce (probability, lowest class)
+            float sb = -INFINITY;
+            int si = 0x7fffffff;
+            if (live && !unique)
+                for (int c = part; c < C; c += 4) {
+                    const float v = r[5 + c];
+                    if (v >= thr) {
+                        const float pc = sigmoidf_acc(v);
+                        if (pc > sb) { sb = pc; si = c; }      // classes ascend: the first maximum of this thread is kept
+                    }
+                }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, sb, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, si, o);
+                if (ob > sb || (ob == sb && oi < si)) { sb = ob; si = oi; }
+            }
+            if (!unique) { best = sb; bi = si; }
         }
         if (live && part == 0) {
             // the sequential scan this replaces starts from class 0 and replaces it only by a strictly larger value: a NaN
             // in class 0 is never replaced, a NaN anywhere else never wins
             const float p0 = r[5];
-            if (p0 != p0 || bi == 0x7fffffff) { best = sigmoidf_acc(p0); bi = 0; }
+            if (!unique && (p0 != p0 || bi == 0x7fffffff)) { best = sigmoidf_acc(p0); bi = 0; }
             a.scores[orec] = __fmul_rn(obj, best);
             a.cls[orec] = (long long)bi;
         }
