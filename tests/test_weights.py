@@ -1,4 +1,6 @@
 """Weight layouts of the reference (host side): Darknet file order (convert.py:36-74, 93-137) and Keras order."""
+import os
+
 import numpy as np
 import pytest
 
@@ -214,3 +216,55 @@ def test_anchor_generation_roundtrip(tmp_path):
     np.testing.assert_allclose(back.reshape(6, 2), anchors, atol=1e-5)
     ca.save_anchors(path, anchors, descending=True)
     np.testing.assert_allclose(y3.get_anchors(path).reshape(6, 2), anchors[::-1], atol=1e-5)
+
+
+def test_crc32c_against_tensorflow_written_bytes():
+    """The checksum of the tensor-bundle reader (crc32c::Mask(crc32c::Value), reference inference.py:102 /
+    train.py:93-104 via model.load_weights) checked on bytes TensorFlow itself wrote: the framing of the reference's own
+    TFRecord files uses the same masked crc32c (tests/golden/make_tf_written_fixture.py copies the bytes verbatim)."""
+    import ctypes as C
+    import struct
+    from yolo_v3_tf2_b200 import _lib
+    from yolo_v3_tf2_b200 import tf_checkpoint as tc
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "tf_written_crc.npz"))
+    headers = fx["headers"]
+    assert headers.shape == (100, 12)
+    lib = _lib.lib()
+    lib.y3_crc32c.restype = C.c_uint32
+    lib.y3_crc32c.argtypes = [C.c_uint32, C.c_void_p, C.c_int64]
+
+    def native(b):
+        a = np.frombuffer(b, np.uint8)
+        return int(lib.y3_crc32c(0, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    for h in headers:
+        h = h.tobytes()
+        want, = struct.unpack("<I", h[8:12])
+        assert tc._mask_crc(tc._crc32c(h[:8])) == want
+        assert tc._mask_crc(native(h[:8])) == want
+    rec = fx["record"].tobytes()
+    n, = struct.unpack_from("<Q", rec, 0)
+    assert len(rec) == 16 + n
+    want, = struct.unpack_from("<I", rec, 12 + n)
+    data = rec[12:12 + n]
+    assert tc._mask_crc(tc._crc32c(data)) == want
+    assert tc._mask_crc(native(data)) == want
+    # incremental form used by the reader on split buffers
+    assert tc._crc32c(data[1000:], tc._crc32c(data[:1000])) == tc._crc32c(data)
+    # the reader's protobuf field parser (BundleEntryProto / BundleHeaderProto) on a protobuf-library-written message:
+    # the record is a tf.train.Example {features {feature: map<string, Feature>}} (reference core/load_tfrecords.py:20-31)
+    (fn, wt, feats), = list(tc._pb_fields(data))
+    assert (fn, wt) == (1, 2)
+    keys = {}
+    for fn, wt, kv in tc._pb_fields(feats):
+        assert (fn, wt) == (1, 2)
+        (kf, _, key), (vf, _, val) = list(tc._pb_fields(kv))
+        assert (kf, vf) == (1, 2)
+        keys[key.decode()] = list(tc._pb_fields(val))
+    assert set(keys) == {"image/encoded", "image/object/bbox/xmin", "image/object/bbox/ymin", "image/object/bbox/xmax",
+                         "image/object/bbox/ymax", "image/object/class/label"}
+    (_, _, jpeg), = list(tc._pb_fields(keys["image/encoded"][0][2]))            # BytesList.value
+    assert jpeg[:3] == b"\xff\xd8\xff"                                            # a JPEG stream, intact
+    (_, _, packed), = list(tc._pb_fields(keys["image/object/bbox/xmin"][0][2]))  # FloatList.value, packed
+    xmin = np.frombuffer(packed, "<f4")
+    assert xmin.size == 3 and np.all((xmin >= 0) & (xmin <= 1))
