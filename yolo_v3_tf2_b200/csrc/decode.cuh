@@ -52,33 +52,29 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     extern __shared__ __align__(16) uint8_t dsm[];
     const int F = 5 + a.C;
     float* rec = reinterpret_cast<float*>(dsm);                         // staged records (pixel pitch as in memory)
-    int* out_rec = reinterpret_cast<int*>(dsm + a.stage_bytes);         // [kDecodeRecs] global record index
+    float4* rec_aux = reinterpret_cast<float4*>(dsm + a.stage_bytes);   // [kDecodeRecs] (cell column, cell row, anchor w, anchor h)
+    int* out_rec = reinterpret_cast<int*>(rec_aux + kDecodeRecs);       // [kDecodeRecs] global record index
     int* rec_base = out_rec + kDecodeRecs;                               // [kDecodeRecs] float offset of the record in `rec`
     __shared__ __align__(8) uint64_t bar;
 
     int s = 0;
     if ((int)blockIdx.x >= a.chunk_begin[1]) s = 1;
     if ((int)blockIdx.x >= a.chunk_begin[2]) s = 2;
-    const int chunk = blockIdx.x - a.chunk_begin[s];
-    const int per_img = a.gh[s] * a.gw[s] * 3;
-    const long long total = (long long)a.B * per_img;
+    // B * N <= 2^31 - 1 (host-checked), so records are counted in 32 bits; only byte offsets need 64
+    const unsigned chunk = blockIdx.x - a.chunk_begin[s];
+    const unsigned per_img = (unsigned)(a.gh[s] * a.gw[s] * 3);
+    const unsigned total = (unsigned)a.B * per_img;
     const int recs = a.recs[s];
     const int pitch = a.pitch[s];
     const bool padded = pitch != 3 * F;       // then recs % 3 == 0 and a chunk starts at a pixel boundary
-    const long long r0 = (long long)chunk * recs;
-    const int nrec = (int)min((long long)recs, total - r0);
-    const float* src = padded ? a.in[s] + (r0 / 3) * pitch : a.in[s] + r0 * F;
+    const unsigned r0 = chunk * (unsigned)recs;
+    const int nrec = (int)min((unsigned)recs, total - r0);
+    const float* src = padded ? a.in[s] + (size_t)(r0 / 3u) * (size_t)pitch : a.in[s] + (size_t)r0 * (size_t)F;
     const int nfl = padded ? (nrec / 3) * pitch : nrec * F;
     const uint32_t bulk_bytes = ((uint32_t)nfl * 4u) & ~15u;
-    // record t of the chunk inside the staging buffer (offsets are tabulated once: the probability loop below is bound
-    // by its instruction count, a division per element cost 50 % there)
     // A pixel pitch that is a multiple of 32 floats would put record (pixel, anchor) of every pixel in the same three
     // banks (11-way conflicts in the per-record phases: measured 135 vs 92 us); such pixels are staged 4 floats further apart.
     const int spitch = (padded && (pitch & 31) == 0) ? pitch + 4 : pitch;
-    if ((int)threadIdx.x < kDecodeRecs) {
-        const int t = threadIdx.x;
-        rec_base[t] = padded ? (t / 3) * spitch + (t - (t / 3) * 3) * F : t * F;
-    }
     auto rec_at = [&](int t) { return rec + rec_base[t]; };
 
     const uint32_t bar_s = smem_u32(&bar);
@@ -98,6 +94,22 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
         mbar_arrive_expect_tx(bar_s, bulk_bytes);
         if (bulk_bytes) bulk_load_1d(smem_u32(rec), src, bulk_bytes, bar_s);
     }
+    // Per-record tables, written by warps 2-3 while the copies are in flight: where record t of the chunk sits in the
+    // staging buffer, where it goes, its cell and its anchor (the per-record phases are bound by their instruction count:
+    // the divisions are done once per record here, not by every thread that touches the record).
+    if ((int)threadIdx.x >= kDecodeRecs && (int)threadIdx.x < 2 * kDecodeRecs) {
+        const int t = (int)threadIdx.x - kDecodeRecs;
+        rec_base[t] = padded ? (t / 3) * spitch + (t - (t / 3) * 3) * F : t * F;
+        const unsigned fr = r0 + (unsigned)min(t, max(nrec - 1, 0));
+        const unsigned b = fr / per_img;
+        const unsigned local = fr - b * per_img;
+        const unsigned cell = local / 3u;
+        const unsigned anc = local - cell * 3u;
+        const unsigned gi = cell / (unsigned)a.gw[s];
+        const unsigned gj = cell - gi * (unsigned)a.gw[s];
+        out_rec[t] = (int)(b * (unsigned)a.N + (unsigned)a.rec_off[s] + local);
+        rec_aux[t] = make_float4((float)gj, (float)gi, a.anchors[(s * 3 + (int)anc) * 2 + 0], a.anchors[(s * 3 + (int)anc) * 2 + 1]);
+    }
     // the (at most 3) floats past the last 16-byte multiple
     for (int i = (int)(bulk_bytes >> 2) + threadIdx.x; i < nfl; i += kDecodeThreads) rec[i] = src[i];
     mbar_wait(bar_s, 0, 0x600);
@@ -106,58 +118,62 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     const int C = a.C;
     if (a.probs == nullptr && a.conf == nullptr && a.scores != nullptr) {
         // ---- compact decode (the fused pipeline: NMS reads only boxes and scores), four threads per record ----
-        // Box: the five transcendental evaluations of a record are spread over its four threads (sigmoid t_x + objectness,
-        // sigmoid t_y, exp t_w, exp t_h) and collected with shuffles; same operations as the per-record path below.
-        // Class: what is needed is max_c sigmoid(t_c) and the FIRST class that attains it, not the C probabilities.
-        // sigmoid is increasing, so only classes whose logit is close to the largest one, m, can attain the float32
-        // maximum (class_tie_threshold).  The four threads find m, then evaluate the sigmoid of the candidates
-        // t_c >= thr only (almost always one) and reduce (probability, lowest class).  Records with m < -80 (zero /
-        // denormal probabilities tie far below m) or a NaN treat every class as a candidate.  The result is
-        // bit-identical to the class reduce of the probabilities this kernel writes in its non-compact mode.
+        // The kernel is bound by instructions issued per record (ncu: 82 % SM throughput at 0.40 of the HBM rate), so this
+        // path is written for instruction count:
+        //  * record -> (image, cell, anchor) index arithmetic is done ONCE per record by the two set-up warps above, while
+        //    the bulk copies are in flight (rec_aux / out_rec), not by all four threads of the record;
+        //  * Box: ONE exp + ONE division sequence per warp gives sigmoid t_x, sigmoid t_y, exp t_w, exp t_h in the four
+        //    lanes of a record (part 0..3), ONE more division gives c_x, c_y, w/2, h/2 (x / 2 == x * 0.5 exactly); each
+        //    lane then forms ONE box coordinate, so a warp stores 128 contiguous bytes with one instruction;
+        //  * Class: what is needed is max_c sigmoid(t_c) and the FIRST class that attains it, not the C probabilities.
+        //    sigmoid is increasing, so only classes whose logit is close to the largest one, m, can attain the float32
+        //    maximum (class_tie_threshold).  One pass finds m, its first index and the runner-up; objectness and
+        //    sigmoid(m) share ONE sigmoid sequence (lanes 0 / 1).  Only if the runner-up is within the threshold
+        //    (near ties, saturation, tiny probabilities, NaN) are the candidates' sigmoids evaluated and reduced as
+        //    (probability, lowest class).  Same operations on the same operands as the per-record path below: the result
+        //    is bit-identical to the class reduce of the probabilities this kernel writes in its non-compact mode.
         static_assert(kDecodeThreads == 4 * kDecodeRecs, "four threads per record");
         const int t = (int)threadIdx.x >> 2, part = (int)threadIdx.x & 3;
         const bool live = t < nrec;
-        const float* r = rec_at(live ? t : 0);
-        const long long fr = r0 + (live ? t : 0);
-        const int b = (int)(fr / per_img);
-        const int local = (int)(fr - (long long)b * per_img);
-        const int cell = local / 3;
-        const int anc = local - cell * 3;
-        const int gi = cell / a.gw[s];
-        const int gj = cell - gi * a.gw[s];
-        const long long orec = (long long)b * a.N + a.rec_off[s] + local;
-        float e0;                                   // part 0: sigmoid(t_x), 1: sigmoid(t_y), 2: w, 3: h
-        if (part < 2) e0 = sigmoidf_acc(r[part]);
-        else e0 = expf(r[part]) * a.anchors[(s * 3 + anc) * 2 + (part - 2)];
-        const float obj = sigmoidf_acc(r[4]);       // (all four threads: cheaper than another shuffle)
+        const int tl = live ? t : 0;
+        const float* r = rec + rec_base[tl];
+        const int orec = out_rec[tl];
         const int base = (int)(threadIdx.x & 31u) & ~3;
-        const float sx = __shfl_sync(0xffffffffu, e0, base + 0);
-        const float sy = __shfl_sync(0xffffffffu, e0, base + 1);
-        const float w = __shfl_sync(0xffffffffu, e0, base + 2);
-        const float h = __shfl_sync(0xffffffffu, e0, base + 3);
-        if (live && part == 0) {
-            const float cx = __fdiv_rn(__fadd_rn(sx, (float)gj), (float)a.gh[s]);   // the reference's (rows, cols) divisor
-            const float cy = __fdiv_rn(__fadd_rn(sy, (float)gi), (float)a.gw[s]);   // order, see the per-record path
-            const float hw = w * 0.5f, hh = h * 0.5f;
-            float4 box;
-            box.x = __fsub_rn(cx, hw);
-            box.y = __fsub_rn(cy, hh);
-            box.z = __fadd_rn(cx, hw);
-            box.w = __fadd_rn(cy, hh);
-            reinterpret_cast<float4*>(a.bboxes)[orec] = box;
+        {
+            const float aux = reinterpret_cast<const float*>(rec_aux)[tl * 4 + part];   // column, row, anchor w, anchor h
+            const float x = r[part];
+            const float ex = expf(part < 2 ? -x : x);                      // sigmoidf_acc(x) = 1 / (1 + expf(-x))
+            const float sg = 1.0f / (1.0f + ex);
+            // the reference divides (x, y) by (rows, cols) of the grid, see the per-record path
+            const float num = part < 2 ? __fadd_rn(sg, aux) : __fmul_rn(ex, aux);
+            const float den = part < 2 ? (float)(part == 0 ? a.gh[s] : a.gw[s]) : 2.0f;
+            const float q = __fdiv_rn(num, den);                           // c_x, c_y, w/2, h/2
+            const float c = __shfl_sync(0xffffffffu, q, base + (part & 1));
+            const float h = __shfl_sync(0xffffffffu, q, base + 2 + (part & 1));
+            const float coord = part < 2 ? __fsub_rn(c, h) : __fadd_rn(c, h);   // xmin, ymin, xmax, ymax
+            if (live) a.bboxes[(size_t)orec * 4 + part] = coord;
         }
         // one pass: the largest logit m1 (first class attaining it: i1) and the runner-up value m2, per thread and then
         // merged over the record's four threads.  An exact tie sets m2 = m1, so it can never pass for "unique" below.
-        float m1 = -INFINITY, m2 = -INFINITY;
+        // m2 = max(m2, min(m1, v)) is the runner-up update for v > m1 and for v <= m1 alike.  zsum = sum of 0 * v is NaN
+        // exactly when some v is NaN or infinite: such records take the all-candidates path (where a NaN also makes
+        // m2 = m1 here, it does not matter).
+        float m1 = -INFINITY, m2 = -INFINITY, zsum = 0.0f;
         int i1 = 0x7fffffff;
-        bool nan = false;
-        if (live)
-            for (int c = part; c < C; c += 4) {
-                const float v = r[5 + c];
-                nan |= (v != v);
-                if (v > m1) { m2 = m1; m1 = v; i1 = c; }
-                else m2 = fmaxf(m2, v);                      // (NaN: ignored by fmaxf)
+        if (live) {
+            const float* rc = r + 5 + part;
+            const int n = (C - part + 3) >> 2;
+#pragma unroll 10
+            for (int k = 0; k < n; ++k) {
+                const float v = rc[4 * k];
+                zsum = fmaf(v, 0.0f, zsum);
+                i1 = (v > m1) ? k : i1;
+                m2 = fmaxf(m2, fminf(m1, v));
+                m1 = fmaxf(m1, v);
             }
+            i1 = (i1 == 0x7fffffff) ? i1 : 4 * i1 + part;
+        }
+        const bool nan = zsum != zsum;
 #pragma unroll
         for (int o = 1; o <= 2; o <<= 1) {
             const float o1 = __shfl_xor_sync(0xffffffffu, m1, o);
@@ -168,7 +184,10 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
             else m2 = fmaxf(m2, o1);
         }
         const bool any_nan = ((__ballot_sync(0xffffffffu, nan) >> base) & 0xFu) != 0u;
-        const float p_m = sigmoidf_acc(m1);
+        // objectness (lane 0) and sigmoid(m1) (lane 1) in one sequence
+        const float sg = sigmoidf_acc(part == 0 ? r[4] : m1);
+        const float obj = __shfl_sync(0xffffffffu, sg, base);
+        const float p_m = __shfl_sync(0xffffffffu, sg, base + 1);
         const float thr = (any_nan || !(m1 >= -80.0f)) ? -INFINITY : class_tie_threshold(m1, p_m);
         // runner-up below the threshold: the arg-max of the logits is the strict arg-max of the float32 probabilities and
         // its probability is the one just computed -- the common case costs one sigmoid per record
@@ -194,13 +213,15 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
                 const int oi = __shfl_xor_sync(0xffffffffu, si, o);
                 if (ob > sb || (ob == sb && oi < si)) { sb = ob; si = oi; }
             }
-            if (!unique) { best = sb; bi = si; }
+            if (!unique) {
+                best = sb; bi = si;
+                // the sequential scan this replaces starts from class 0 and replaces it only by a strictly larger value:
+                // a NaN in class 0 is never replaced, a NaN anywhere else never wins
+                const float p0 = r[5];
+                if (p0 != p0 || bi == 0x7fffffff) { best = sigmoidf_acc(p0); bi = 0; }
+            }
         }
         if (live && part == 0) {
-            // the sequential scan this replaces starts from class 0 and replaces it only by a strictly larger value: a NaN
-            // in class 0 is never replaced, a NaN anywhere else never wins
-            const float p0 = r[5];
-            if (!unique && (p0 != p0 || bi == 0x7fffffff)) { best = sigmoidf_acc(p0); bi = 0; }
             a.scores[orec] = __fmul_rn(obj, best);
             a.cls[orec] = (long long)bi;
         }
@@ -210,26 +231,19 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeArgs
     // ---- (1) per-record box / objectness (+ class max) ----
     if ((int)threadIdx.x < nrec) {
         const int t = threadIdx.x;
-        const long long fr = r0 + t;
-        const int b = (int)(fr / per_img);
-        const int local = (int)(fr - (long long)b * per_img);
-        const int cell = local / 3;
-        const int anc = local - cell * 3;
-        const int gi = cell / a.gw[s];
-        const int gj = cell - gi * a.gw[s];
-        const long long orec = (long long)b * a.N + a.rec_off[s] + local;
-        out_rec[t] = (int)orec;
+        const long long orec = out_rec[t];
+        const float4 aux = rec_aux[t];              // cell column, cell row, anchor w, anchor h
         float* r = rec_at(t);
         const float sx = sigmoidf_acc(r[0]);
         const float sy = sigmoidf_acc(r[1]);
-        const float w = expf(r[2]) * a.anchors[(s * 3 + anc) * 2 + 0];
-        const float h = expf(r[3]) * a.anchors[(s * 3 + anc) * 2 + 1];
+        const float w = __fmul_rn(expf(r[2]), aux.z);
+        const float h = __fmul_rn(expf(r[3]), aux.w);
         const float obj = sigmoidf_acc(r[4]);
         // The reference divides the (x, y) pair elementwise by tf.shape(xy)[1:3] = (gh, gw)
         // (yolo_decode_layer.py:5,8): x by the row count, y by the column count.  Identical for square grids; mirrored
         // literally so non-square inputs give the reference's numbers.
-        const float cx = __fdiv_rn(__fadd_rn(sx, (float)gj), (float)a.gh[s]);
-        const float cy = __fdiv_rn(__fadd_rn(sy, (float)gi), (float)a.gw[s]);
+        const float cx = __fdiv_rn(__fadd_rn(sx, aux.x), (float)a.gh[s]);
+        const float cy = __fdiv_rn(__fadd_rn(sy, aux.y), (float)a.gw[s]);
         const float hw = w * 0.5f, hh = h * 0.5f;
         float4 box;
         box.x = __fsub_rn(cx, hw);

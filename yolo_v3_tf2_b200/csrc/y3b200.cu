@@ -2311,6 +2311,7 @@ static int decode_impl(y3_ctx* ctx, const float* const* grids, const int* gh, co
         a.recs[s] = y3::kDecodeRecs;
         if (s < n_scales) {
             if (!grids[s] || gh[s] <= 0 || gw[s] <= 0) return fail(Y3_ERR_INVALID, "bad grid");
+            if (gh[s] > 16383 || gw[s] > 32767) return fail(Y3_ERR_UNSUPPORTED, "grid larger than 16383 x 32767 cells");
             if ((reinterpret_cast<uintptr_t>(grids[s]) & 15) != 0) return fail(Y3_ERR_INVALID, "grid pointers must be 16-byte aligned");
             if (pix_pitch && pix_pitch[s] != 3 * F) {
                 // padded pixel pitch (y3_net_forward_pitched): a chunk is a whole number of pixels
@@ -2338,7 +2339,7 @@ static int decode_impl(y3_ctx* ctx, const float* const* grids, const int* gh, co
     a.bboxes = bboxes; a.conf = conf; a.probs = probs; a.scores = scores;
     a.cls = reinterpret_cast<long long*>(class_idx);
     a.stage_bytes = (((y3::kDecodeRecs / 3 + 1) * (max_pitch + 4) + 3) & ~3) * 4;   // +4: bank-conflict padding of the staging pitch
-    const size_t smem = (size_t)a.stage_bytes + 2 * y3::kDecodeRecs * 4;
+    const size_t smem = (size_t)a.stage_bytes + (size_t)y3::kDecodeRecs * (16 + 4 + 4);   // + rec_aux (float4), out_rec, rec_base
     if (smem > 200 * 1024) return fail(Y3_ERR_UNSUPPORTED, "nclasses too large for the decode tile");
     if (smem > 48 * 1024) Y3_CUDA(ensure_dyn_smem((const void*)y3::decode_kernel, (int)smem));
     y3::decode_kernel<<<chunks, y3::kDecodeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
