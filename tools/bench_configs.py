@@ -61,6 +61,10 @@ def config4(B=512, C=80):
         by2 = by + 12.0 * N * B
         print("| `yolo_decode` + fused scores / class ids, %s | %.1f | %.0f | %.2f | %.0f |" % (
             name, t, by2 / t / 1e3, by2 / t / 1e3 / HBM, B / t * 1e6))
+        t = timeit(lambda: y3.yolo_decode(grids, anchors, C, compact=True))
+        by4 = (N * F * 4 + 28.0 * N) * B
+        print("| compact `yolo_decode` (boxes + scores + class ids only: what the fused pipeline runs), %s | %.1f | %.0f | %.2f | %.0f |" % (
+            name, t, by4 / t / 1e3, by4 / t / 1e3 / HBM, B / t * 1e6))
         dec = y3.yolo_decode(grids, anchors, C, with_scores=True)
         bboxes, conf, probs, scores, cls = dec
         t = timeit(lambda: yolo_nms((bboxes, conf, probs), 100, 0.5, 0.1, check_status=False))
