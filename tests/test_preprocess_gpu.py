@@ -70,3 +70,25 @@ def test_batch_tensor_equals_list_of_images(cuda):
             c = y3.preprocess_images([torch.from_numpy(f).cuda() for f in batch], 64, 96, **kw)
             torch.cuda.synchronize()
             assert torch.equal(a, c) and torch.equal(b, c)
+
+
+@pytest.mark.parametrize("shape,out_hw", [((7, 91, 131, 3), (64, 96)), ((3, 5, 3, 3), (32, 32)), ((2, 417, 419, 3), (416, 416)),
+                                          ((4, 2, 2, 3), (8, 8))])
+def test_uint8_batch_unaligned_images_bit_exact(cuda, shape, out_hw):
+    """uint8 frames inside one [B, h, w, 3] tensor start at arbitrary byte alignments (h * w * 3 odd): the kernel's aligned
+    8-byte word loads, their byte-load fall-back at both ends of every image buffer, tiny images and both up- and
+    down-scaling must give the oracle's bits (tf.image.resize(...) / 255, inference.py:157-158, core/load_tfrecords.py:46)."""
+    import torch
+    import yolo_v3_tf2_b200 as y3
+    from oracle import preprocess_oracle as po
+    rng = np.random.default_rng(sum(shape))
+    batch = rng.integers(0, 256, shape, dtype=np.uint8)
+    # an odd byte offset for the whole batch as well: a view that starts 1 byte into its allocation
+    raw = torch.zeros(batch.size + 1, dtype=torch.uint8, device="cuda")
+    raw[1:] = torch.from_numpy(batch.reshape(-1)).cuda()
+    view = raw[1:].view(*shape)
+    out = y3.preprocess_images(view, out_hw[0], out_hw[1], divide_by_255=True)
+    torch.cuda.synchronize()
+    for k in range(shape[0]):
+        ref = (po.resize_bilinear(batch[k], out_hw[0], out_hw[1]) / np.float32(255.0)).astype(np.float32)
+        assert np.array_equal(out[k].cpu().numpy(), ref), f"image {k}"
