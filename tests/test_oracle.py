@@ -254,3 +254,16 @@ def test_next_rows_golden():
     for k in ("preds", "gts", "tp", "fp", "fn"):
         assert np.array_equal(c[k], z[k]), k
     assert c["examples"] == int(z["examples"])
+
+
+def test_division_free_div255_is_the_ieee_quotient(tmp_path):
+    """preprocess.cuh replaces `resize(...) / 255` (core/load_tfrecords.py:46) by a multiply and two FMAs; the C checker
+    compares it with the IEEE division on every 13th float of [0, 256] here (all of them: 34 s, run once, 0 mismatches)."""
+    import os
+    import subprocess
+    src = os.path.join(os.path.dirname(__file__), "div255_check.c")
+    exe = str(tmp_path / "div255_check")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, src, "-lm"])
+    out = subprocess.run([exe, "13"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "mismatches 0" in out.stdout

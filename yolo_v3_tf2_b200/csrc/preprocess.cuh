@@ -28,7 +28,24 @@ struct PreprocessArgs {
     int B, dst_h, dst_w;
     float mul;              // 1/255 for uint8 sources of the tfrecord path, else 1
     int use_mul;
+    unsigned long long div_magic;   // ceil(2^40 / dst_w) when idx / dst_w == (idx * magic) >> 40 for every pixel index, else 0
 };
+
+// The kernel was bound by the XU pipe (ncu: 66 % busy -- int <-> float conversions, floor / ceil and the three IEEE
+// divisions are 16-lane operations): 12 byte -> float conversions, 8 rounding / conversion steps and 3 reciprocals per
+// output pixel.  The helpers below do the same arithmetic on the ALU / FMA pipes, bit for bit.
+// exact float of an integer 0 <= i < 2^23 (no I2F): 2^23 + i has i in its mantissa
+__device__ __forceinline__ float small_uint_to_float(unsigned i) { return __fsub_rn(__uint_as_float(0x4B000000u | i), 8388608.0f); }
+// exact int of an integral float |f| < 2^22 (no F2I): 1.5 * 2^23 + f has f in its mantissa (two's complement)
+__device__ __forceinline__ int integral_float_to_int(float f) { return __float_as_int(__fadd_rn(f, 12582912.0f)) - 0x4B400000; }
+// v / 255 correctly rounded, for 0 <= v <= 256, without the reciprocal: q0 = v * RN(1/255), one residual correction.
+// Equal to the IEEE quotient for ALL 1 132 462 081 floats of that range (exhaustive check: tests/div255_check.c).
+__device__ __forceinline__ float div255(float v) {
+    const float r = 0.003921568859368563f;   // RN(1 / 255) = 0x3B808081
+    const float q0 = __fmul_rn(v, r);
+    const float e = __fmaf_rn(-q0, 255.0f, v);
+    return __fmaf_rn(e, r, q0);
+}
 
 __device__ __forceinline__ float load_px(const ImageDesc& d, long long idx) {
     if (d.dtype == 0) return (float)reinterpret_cast<const uint8_t*>(d.src)[idx];
@@ -46,17 +63,22 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessArgs a)
     const int per = a.dst_h * a.dst_w;
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= per) return;
-    const int y = idx / a.dst_w, x = idx - y * a.dst_w;
+    // (the compiler's 32-bit division goes through I2F / MUFU.RCP / F2I: three more XU operations per pixel)
+    const int y = a.div_magic ? (int)(((unsigned long long)(unsigned)idx * a.div_magic) >> 40) : idx / a.dst_w;
+    const int x = idx - y * a.dst_w;
     const int H = (int)sd.H, W = (int)sd.W, out_h = (int)sd.out_h, out_w = (int)sd.out_w;
     float r[3] = {0.f, 0.f, 0.f};
     const int yy = y - (int)sd.off_y, xx = x - (int)sd.off_x;
     if (yy >= 0 && yy < out_h && xx >= 0 && xx < out_w) {
         const float sy = __int_as_float((int)sd.scale_y), sx = __int_as_float((int)sd.scale_x);
-        const float fy = __fsub_rn(__fmul_rn(__fadd_rn((float)yy, 0.5f), sy), 0.5f);
-        const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)xx, 0.5f), sx), 0.5f);
+        const float fy = __fsub_rn(__fmul_rn(__fadd_rn(small_uint_to_float((unsigned)yy), 0.5f), sy), 0.5f);
+        const float fx = __fsub_rn(__fmul_rn(__fadd_rn(small_uint_to_float((unsigned)xx), 0.5f), sx), 0.5f);
         const float fly = floorf(fy), flx = floorf(fx);
-        const int y0 = max((int)fly, 0), y1 = min((int)ceilf(fy), H - 1);
-        const int x0 = max((int)flx, 0), x1 = min((int)ceilf(fx), W - 1);
+        // ceil(f) = floor(f) + (f > floor(f)); the conversion without F2I needs |f| < 2^22 (any real image)
+        const bool small = (H | W) < (1 << 22);
+        const int yfl = small ? integral_float_to_int(fly) : (int)fly, xfl = small ? integral_float_to_int(flx) : (int)flx;
+        const int y0 = max(yfl, 0), y1 = min(yfl + (fy > fly ? 1 : 0), H - 1);
+        const int x0 = max(xfl, 0), x1 = min(xfl + (fx > flx ? 1 : 0), W - 1);
         const float ly = __fsub_rn(fy, fly), lx = __fsub_rn(fx, flx);
         const long long r0 = (long long)y0 * W, r1 = (long long)y1 * W;
         float tl[3], tr[3], bl[3], br[3];
@@ -65,8 +87,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessArgs a)
             const uint8_t *ptl = p + (r0 + x0) * 3, *ptr_ = p + (r0 + x1) * 3, *pbl = p + (r1 + x0) * 3, *pbr = p + (r1 + x1) * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                tl[c] = (float)__ldg(ptl + c); tr[c] = (float)__ldg(ptr_ + c);
-                bl[c] = (float)__ldg(pbl + c); br[c] = (float)__ldg(pbr + c);
+                tl[c] = small_uint_to_float(__ldg(ptl + c)); tr[c] = small_uint_to_float(__ldg(ptr_ + c));
+                bl[c] = small_uint_to_float(__ldg(pbl + c)); br[c] = small_uint_to_float(__ldg(pbr + c));
             }
         } else {
             const float* p = reinterpret_cast<const float*>(sd.src);
@@ -82,7 +104,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessArgs a)
             const float top = __fadd_rn(tl[c], __fmul_rn(__fsub_rn(tr[c], tl[c]), lx));
             const float bot = __fadd_rn(bl[c], __fmul_rn(__fsub_rn(br[c], bl[c]), lx));
             float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
-            if (a.use_mul) v = __fdiv_rn(v, 255.0f);   // the reference divides: resize(...) / 255
+            // the reference divides: resize(...) / 255.  uint8 sources give 0 <= v <= 255 (div255 is the IEEE quotient
+            // there); float sources may hold anything and take the division itself
+            if (a.use_mul) v = (sd.dtype == 0) ? div255(v) : __fdiv_rn(v, 255.0f);
             r[c] = v;
         }
     }

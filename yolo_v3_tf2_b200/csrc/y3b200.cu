@@ -2433,12 +2433,18 @@ int y3_preprocess(y3_ctx* ctx, const void* image_descs_dev, int B, int dst_h, in
     if (!ctx || !image_descs_dev || !out) return fail(Y3_ERR_INVALID, "null argument");
     if (ctx->device < 0) return fail(Y3_ERR_STATE, "planning-only context cannot run (no CPU fallback)");
     if (B <= 0 || dst_h <= 0 || dst_w <= 0) return fail(Y3_ERR_INVALID, "bad shape");
+    if (dst_h >= (1 << 23) || dst_w >= (1 << 23)) return fail(Y3_ERR_UNSUPPORTED, "output larger than 2^23 pixels per side");
     y3::PreprocessArgs a{};
     a.desc = reinterpret_cast<const y3::ImageDesc*>(image_descs_dev);
     a.out = out;
     a.B = B; a.dst_h = dst_h; a.dst_w = dst_w;
     a.use_mul = divide_by_255 ? 1 : 0;
     a.mul = 1.0f;
+    // idx / dst_w as a multiplication: with M = ceil(2^40 / d), floor(n M / 2^40) == floor(n / d) whenever n d < 2^40
+    // (M d - 2^40 < d, so the error term n (M d - 2^40) / (d 2^40) stays below 1 / d)
+    a.div_magic = 0;
+    if ((double)dst_h * dst_w * dst_w < 1099511627776.0)
+        a.div_magic = ((1ull << 40) + (unsigned long long)dst_w - 1) / (unsigned long long)dst_w;
     if (B > 65535) return fail(Y3_ERR_UNSUPPORTED, "more than 65535 images per call");
     const dim3 grid((unsigned)(((long long)dst_h * dst_w + 255) / 256), (unsigned)B);
     y3::preprocess_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
