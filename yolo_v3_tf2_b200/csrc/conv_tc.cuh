@@ -869,7 +869,6 @@ __global__ void umma_shift_test_kernel(const __grid_constant__ CUtensorMap tmX, 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr int BLOCK_K = SWZ / 2;
-    const uint32_t x_bytes = (uint32_t)rows * SWZ;
     const uint32_t smem_x = smem_base;
     const uint32_t smem_w = smem_base + (uint32_t)((rows + 127) / 128) * 128u * SWZ;
     const uint32_t bar = smem_w + 64 * SWZ;

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     // N = 22 743 (608x608) keys + indices alone take 192 KB of the 227 KB)
     uint32_t* hist = reinterpret_cast<uint32_t*>(kept);
     static_assert(kNmsBins * 4 <= kNmsKeptCap * 16, "histogram must fit in the kept list");
-    __shared__ int s_ncand, s_nkept, s_nsel, s_overflow;
+    __shared__ int s_nkept, s_nsel, s_overflow;
     __shared__ int s_warp_cnt[kNmsThreads / 32];
     __shared__ int s_scan[kNmsThreads / 32];
     __shared__ uint32_t s_sel_bin, s_sel_above;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
     const bool compact = (a.score_thr >= 0.0f) && (a.iou_thr > 0.0f);
     const bool pos_thr = a.iou_thr > 0.0f;
 
-    if (tid == 0) { s_ncand = 0; s_nkept = 0; s_nsel = 0; s_overflow = 0; }
+    if (tid == 0) { s_nkept = 0; s_nsel = 0; s_overflow = 0; }
     for (int i = tid; i < a.max_boxes; i += kNmsThreads) sel[i] = 0;
     __syncthreads();
 
